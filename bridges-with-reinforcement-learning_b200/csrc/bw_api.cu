@@ -1,0 +1,573 @@
+// C ABI of bridges_b200 (include/bridges_b200.h): handle management, state allocation in HBM,
+// host<->device staging for the *_host entry points and kernel launches.  No torch types.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bw_common.cuh"
+#include "bw_kernels.cuh"
+
+using namespace bw;
+
+struct bw_handle {
+    bw_config cfg;
+    Params P;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool shapes_loaded = false;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_obs = false;
+    int smem_step = 0;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // owned device buffers
+    std::vector<void *> allocs;
+    double *d_xs = nullptr, *d_ys = nullptr;
+    ShapeDev *d_shapes = nullptr;
+    // staging for *_host calls and internal evaluations
+    bw_action *d_actions = nullptr, *d_noop = nullptr;
+    bw_step_out *d_out = nullptr, *d_scratch_out = nullptr;
+    uint8_t *d_mask = nullptr;
+    bw_task *d_tasks = nullptr;
+    float *d_img[3] = {nullptr, nullptr, nullptr};
+    float *d_binary = nullptr;
+    bw_interface *d_itf = nullptr;
+    int32_t *d_nitf = nullptr;
+    double *d_ground = nullptr, *d_offsets = nullptr;
+};
+
+static int fail(bw_handle *h, int code, const char *fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) return fail(h, BW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(bw_handle *h, T **p, size_t count, bool zero = true) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    if (zero) {
+        e = cudaMemsetAsync(q, 0, count * sizeof(T), h->stream);
+        if (e != cudaSuccess) return e;
+    }
+    *p = static_cast<T *>(q);
+    return cudaSuccess;
+}
+
+// numpy.linspace(start, stop, num) with endpoint: arange(num) * step + start, last = stop
+static void np_linspace(double start, double stop, int num, double *out) {
+    const double step = (stop - start) / (double)(num - 1);
+    for (int i = 0; i < num; i++) {
+        volatile double prod = (double)i * step;   // separately rounded, as numpy does
+        out[i] = prod + start;
+    }
+    out[num - 1] = stop;
+}
+
+static void shape_to_dev(const bw_shape_desc &s, ShapeDev &d) {
+    memset(&d, 0, sizeof(d));
+    d.n_faces = s.n_faces;
+    d.n_verts = s.n_verts;
+    d.target_faces_mask = s.target_faces_mask;
+    d.receiving_faces_mask = s.receiving_faces_mask;
+    for (int i = 0; i < BW_MAX_FACES; i++) {
+        d.face_nx[i] = s.face_nx[i]; d.face_nz[i] = s.face_nz[i];
+        d.face_cx[i] = s.face_cx[i]; d.face_cz[i] = s.face_cz[i];
+        d.end0_x[i] = s.end0_x[i]; d.end0_z[i] = s.end0_z[i];
+        d.end1_x[i] = s.end1_x[i]; d.end1_z[i] = s.end1_z[i];
+    }
+    double rad = 0.0;
+    for (int i = 0; i < BW_MAX_VERTS; i++) {
+        d.vert_x[i] = s.vert_x[i]; d.vert_z[i] = s.vert_z[i];
+        if (i < s.n_verts) {
+            const double dx = s.vert_x[i] - s.com_x, dz = s.vert_z[i] - s.com_z;
+            rad = std::fmax(rad, std::sqrt(dx * dx + dz * dz));
+        }
+    }
+    d.com_x = s.com_x; d.com_z = s.com_z; d.area = s.area; d.depth = s.depth;
+    d.radius = rad;
+}
+
+static bool shape_ok(const bw_shape_desc &s) {
+    return s.n_faces >= 3 && s.n_faces <= BW_MAX_FACES && s.n_verts >= 3 && s.n_verts <= BW_MAX_VERTS &&
+           s.area > 0.0 && s.depth > 0.0;
+}
+
+// axis-aligned box marker (cube06.urdf: <box size="0.6 0.6 0.6">) in compas' face order
+static void default_marker(ShapeDev &d) {
+    bw_shape_desc s;
+    memset(&s, 0, sizeof(s));
+    const double hx = 0.5 * 0.6, hz = 0.5 * 0.6;
+    s.n_faces = 4; s.n_verts = 4;
+    s.target_faces_mask = s.receiving_faces_mask = 0xf;
+    const double nx[4] = {0, 1, -1, 0}, nz[4] = {-1, 0, 0, 1};
+    for (int i = 0; i < 4; i++) {
+        s.face_nx[i] = nx[i]; s.face_nz[i] = nz[i];
+        s.face_cx[i] = nx[i] * hx; s.face_cz[i] = nz[i] * hz;
+    }
+    s.end0_x[0] = -hx; s.end0_z[0] = -hz; s.end1_x[0] = hx; s.end1_z[0] = -hz;
+    s.end0_x[1] = hx; s.end0_z[1] = -hz; s.end1_x[1] = hx; s.end1_z[1] = hz;
+    s.end0_x[2] = -hx; s.end0_z[2] = hz; s.end1_x[2] = -hx; s.end1_z[2] = -hz;
+    s.end0_x[3] = -hx; s.end0_z[3] = hz; s.end1_x[3] = hx; s.end1_z[3] = hz;
+    const double vx[4] = {hx, -hx, -hx, hx}, vz[4] = {-hz, -hz, hz, hz};
+    for (int i = 0; i < 4; i++) { s.vert_x[i] = vx[i]; s.vert_z[i] = vz[i]; }
+    s.area = 0.36; s.depth = 0.6;
+    shape_to_dev(s, d);
+}
+
+extern "C" {
+
+int bw_abi_version(void) { return BW_ABI_VERSION; }
+
+void bw_config_default(bw_config *cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->num_envs = 1;
+    cfg->device = 0;
+    cfg->max_steps = 0;
+    cfg->xlim[0] = -3.0; cfg->xlim[1] = 7.0;
+    cfg->ylim[0] = 0.0; cfg->ylim[1] = 10.0;
+    cfg->floor_halfwidth = 5.0;
+    cfg->floor_depth = 10.0;
+    cfg->mu = 0.8;
+    cfg->density = 1.0;
+    cfg->tmax = 1e-6;
+    cfg->amin = 1e-3;
+    cfg->stable_tol = 1e-6;
+    cfg->stream = nullptr;
+}
+
+const char *bw_last_error(const bw_handle *h) { return h ? h->err : "null handle"; }
+
+int64_t bw_kernel_launches(const bw_handle *h) { return h ? h->launches : 0; }
+
+void bw_destroy(bw_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bw_create(const bw_config *cfg, bw_handle **out) {
+    if (!cfg || !out) return BW_ERR_INVALID;
+    *out = nullptr;
+    bw_handle *h = new (std::nothrow) bw_handle();
+    if (!h) return BW_ERR_INVALID;
+    h->cfg = *cfg;
+    *out = h;   // returned even on failure so that bw_last_error works; caller destroys it
+    if (cfg->num_envs <= 0) return fail(h, BW_ERR_INVALID, "num_envs must be positive");
+    if (!(cfg->xlim[1] > cfg->xlim[0]) || !(cfg->ylim[1] > cfg->ylim[0]))
+        return fail(h, BW_ERR_INVALID, "empty raster window");
+    if (!(cfg->mu >= 0.0) || !(cfg->density > 0.0)) return fail(h, BW_ERR_INVALID, "mu/density out of range");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(h, BW_ERR_CUDA, "no CUDA device available (%s): bridges_b200 has no CPU path",
+                    cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(h, BW_ERR_INVALID, "device %d out of range", cfg->device);
+    CU(cudaSetDevice(cfg->device));
+    if (cfg->stream) {
+        h->stream = static_cast<cudaStream_t>(cfg->stream);
+    } else {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    for (auto &e : h->ev) CU(cudaEventCreate(&e));
+
+    const int E = cfg->num_envs;
+    Params &P = h->P;
+    memset(&P, 0, sizeof(P));
+    P.E = E;
+    P.max_steps = cfg->max_steps;
+    // capacity used for shared-memory sizing: max_steps blocks when given, else the ABI maximum
+    P.max_blocks = (cfg->max_steps > 0 && cfg->max_steps < BW_MAX_BLOCKS) ? cfg->max_steps : BW_MAX_BLOCKS;
+    P.max_itf = 3 * P.max_blocks < BW_MAX_INTERFACES ? 3 * P.max_blocks : BW_MAX_INTERFACES;
+    P.xlim0 = cfg->xlim[0]; P.xlim1 = cfg->xlim[1]; P.ylim0 = cfg->ylim[0]; P.ylim1 = cfg->ylim[1];
+    P.floor_halfwidth = cfg->floor_halfwidth; P.floor_depth = cfg->floor_depth;
+    P.density = cfg->density; P.tmax = cfg->tmax; P.amin = cfg->amin;
+    P.stable_tol = cfg->stable_tol > 0 ? cfg->stable_tol : 1e-6;
+    P.inv_step_x = (double)(IMG - 1) / (cfg->xlim[1] - cfg->xlim[0]);
+    P.inv_step_y = (double)(IMG - 1) / (cfg->ylim[1] - cfg->ylim[0]);
+
+    double xs[IMG], ys[IMG];
+    np_linspace(cfg->xlim[0], cfg->xlim[1], IMG, xs);
+    np_linspace(cfg->ylim[1], cfg->ylim[0], IMG, ys);
+    CU(dev_alloc(h, &h->d_xs, IMG));
+    CU(dev_alloc(h, &h->d_ys, IMG));
+    CU(cudaMemcpyAsync(h->d_xs, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ys, ys, sizeof(ys), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // xs/ys live on this stack frame
+    P.xs = h->d_xs; P.ys = h->d_ys;
+    CU(dev_alloc(h, &h->d_shapes, BW_MAX_SHAPES));
+    P.shapes = h->d_shapes;
+
+    CU(dev_alloc(h, &P.n_blocks, E));
+    CU(dev_alloc(h, &P.pose, (size_t)E * NB));
+    CU(dev_alloc(h, &P.shape_of, (size_t)E * NB));
+    CU(dev_alloc(h, &P.face_occ, (size_t)E * NB));
+    CU(dev_alloc(h, &P.static_mask, E));
+    CU(dev_alloc(h, &P.block_bits, (size_t)E * IMG));
+    CU(dev_alloc(h, &P.obst_bits, (size_t)E * IMG));
+    CU(dev_alloc(h, &P.reward_img, (size_t)E * IMG * IMG));
+    CU(dev_alloc(h, &P.task, E));
+    CU(dev_alloc(h, &P.mu, E, false));
+    CU(dev_alloc(h, &P.done, E));
+    CU(dev_alloc(h, &P.last_out, E));
+    {
+        std::vector<double> mu(E, cfg->mu);
+        CU(cudaMemcpyAsync(P.mu, mu.data(), sizeof(double) * E, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(dev_alloc(h, &h->d_actions, E));
+    CU(dev_alloc(h, &h->d_noop, E, false));
+    {
+        std::vector<bw_action> noop(E);
+        memset(noop.data(), 0, sizeof(bw_action) * E);
+        for (auto &a : noop) { a.shape = -1; a.target_block = -1; }
+        CU(cudaMemcpyAsync(h->d_noop, noop.data(), sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(dev_alloc(h, &h->d_out, E));
+    CU(dev_alloc(h, &h->d_scratch_out, E));
+    CU(dev_alloc(h, &h->d_mask, E));
+    CU(dev_alloc(h, &h->d_ground, 256));
+    CU(dev_alloc(h, &h->d_offsets, 256));
+
+    upload_step_tables();
+    // Gaussian of get_task_features (kernel_size 101, sigma 16), float32 like torch
+    {
+        float k[127];
+        double sum = 0.0;
+        for (int i = 0; i < 101; i++) {
+            const float c = (float)(i - 50);
+            k[i] = expf(-(c * c) / 512.0f);
+            sum += k[i];
+        }
+        const float fs = (float)sum;
+        for (int i = 0; i < 101; i++) k[i] = k[i] / fs;
+        ShapeDev marker;
+        default_marker(marker);
+        upload_obs_tables(k, &marker);
+    }
+    h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf);
+    CU(configure_step(h->smem_step));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_sync(bw_handle *h) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
+    if (!h || !h_shapes) return BW_ERR_INVALID;
+    if (n <= 0 || n > BW_MAX_SHAPES) return fail(h, BW_ERR_CAPACITY, "1..%d shapes supported, got %d", BW_MAX_SHAPES, n);
+    ShapeDev dev[BW_MAX_SHAPES];
+    for (int i = 0; i < n; i++) {
+        if (!shape_ok(h_shapes[i])) return fail(h, BW_ERR_INVALID, "shape %d: bad face/vertex count or mass data", i);
+        shape_to_dev(h_shapes[i], dev[i]);
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->d_shapes, dev, sizeof(ShapeDev) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->P.n_shapes = n;
+    h->shapes_loaded = true;
+    return BW_OK;
+}
+
+int bw_set_marker_shape(bw_handle *h, const bw_shape_desc *h_shape) {
+    if (!h || !h_shape) return BW_ERR_INVALID;
+    if (!shape_ok(*h_shape)) return fail(h, BW_ERR_INVALID, "marker shape: bad face/vertex count or mass data");
+    ShapeDev d;
+    shape_to_dev(*h_shape, d);
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    upload_obs_tables(nullptr, &d);
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_set_task_kernel(bw_handle *h, const float *h_kernel1d, int32_t n) {
+    if (!h || !h_kernel1d) return BW_ERR_INVALID;
+    if (n != 101) return fail(h, BW_ERR_INVALID, "the task-feature kernel has 101 taps (successor_dqn.py:78)");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    upload_obs_tables(h_kernel1d, nullptr);
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_set_mu(bw_handle *h, const double *h_mu) {
+    if (!h || !h_mu) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->P.mu, h_mu, sizeof(double) * h->P.E, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask) {
+    if (!h || !h_mask) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->P.static_mask, h_mask, sizeof(uint32_t) * h->P.E, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_set_timing(bw_handle *h, int32_t enabled) {
+    if (!h) return BW_ERR_INVALID;
+    h->timing = enabled != 0;
+    return BW_OK;
+}
+
+static int need_shapes(bw_handle *h) {
+    if (!h->shapes_loaded) return fail(h, BW_ERR_STATE, "bw_load_shapes must be called first");
+    return BW_OK;
+}
+
+int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
+    if (!h) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    launch_reset(h->P, d_tasks, d_mask, 0, h->stream);
+    h->launches++;
+    if (d_tasks != nullptr) {
+        // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
+        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, nullptr, nullptr, 0, h->smem_step, h->stream);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_reset_host(bw_handle *h, const bw_task *h_tasks, const uint8_t *h_mask) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const int E = h->P.E;
+    if (h_tasks) {
+        if (!h->d_tasks) CU(dev_alloc(h, &h->d_tasks, E));
+        CU(cudaMemcpyAsync(h->d_tasks, h_tasks, sizeof(bw_task) * E, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
+    int rc = bw_reset(h, h_tasks ? h->d_tasks : nullptr, h_mask ? h->d_mask : nullptr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_reset_done(bw_handle *h) {
+    if (!h) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    launch_reset(h->P, nullptr, nullptr, 1, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out, float *d_block_img,
+            float *d_binary) {
+    if (!h || !d_actions || !d_out) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
+    launch_step(h->P, d_actions, d_mask, d_out, nullptr, nullptr, 0, h->smem_step, h->stream);
+    h->launches++;
+    if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+    h->ev_obs = false;
+    if (d_block_img || d_binary) {
+        if (h->timing) CU(cudaEventRecord(h->ev[2], h->stream));
+        launch_observe(h->P, d_block_img, d_binary, nullptr, nullptr, h->stream);
+        h->launches += (d_block_img ? 1 : 0) + (d_binary ? 1 : 0);
+        if (h->timing) CU(cudaEventRecord(h->ev[3], h->stream));
+        h->ev_obs = true;
+    }
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_last_step_kernel_ms(bw_handle *h, float *h_ms2) {
+    if (!h || !h_ms2) return BW_ERR_INVALID;
+    if (!h->timing) return fail(h, BW_ERR_STATE, "bw_set_timing(h, 1) first");
+    CU(cudaStreamSynchronize(h->stream));
+    h_ms2[0] = h_ms2[1] = 0.0f;
+    CU(cudaEventElapsedTime(&h_ms2[0], h->ev[0], h->ev[1]));
+    if (h->ev_obs) CU(cudaEventElapsedTime(&h_ms2[1], h->ev[2], h->ev[3]));
+    return BW_OK;
+}
+
+static int ensure_img(bw_handle *h, int which) {
+    if (!h->d_img[which]) CU(dev_alloc(h, &h->d_img[which], (size_t)h->P.E * IMG * IMG, false));
+    return BW_OK;
+}
+
+int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
+                 float *h_block_img, float *h_binary) {
+    if (!h || !h_actions || !h_out) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const int E = h->P.E;
+    CU(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
+    if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
+    if (h_block_img)
+        if (int rc = ensure_img(h, 0)) return rc;
+    if (h_binary && !h->d_binary) CU(dev_alloc(h, &h->d_binary, (size_t)E * 6, false));
+    int rc = bw_step(h, h->d_actions, h_mask ? h->d_mask : nullptr, h->d_out, h_block_img ? h->d_img[0] : nullptr,
+                     h_binary ? h->d_binary : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_out, h->d_out, sizeof(bw_step_out) * E, cudaMemcpyDeviceToHost, h->stream));
+    if (h_block_img)
+        CU(cudaMemcpyAsync(h_block_img, h->d_img[0], sizeof(float) * (size_t)E * IMG * IMG, cudaMemcpyDeviceToHost,
+                           h->stream));
+    if (h_binary)
+        CU(cudaMemcpyAsync(h_binary, h->d_binary, sizeof(float) * (size_t)E * 6, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_observe(bw_handle *h, float *d_block_img, float *d_binary, float *d_obstacle_img, float *d_reward_img) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    launch_observe(h->P, d_block_img, d_binary, d_obstacle_img, d_reward_img, h->stream);
+    h->launches += (d_block_img ? 1 : 0) + (d_binary ? 1 : 0) + (d_obstacle_img ? 1 : 0) + (d_reward_img ? 1 : 0);
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_obstacle_img, float *h_reward_img) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t E = (size_t)h->P.E, img_bytes = sizeof(float) * E * IMG * IMG;
+    float *hosts[3] = {h_block_img, h_obstacle_img, h_reward_img};
+    for (int i = 0; i < 3; i++)
+        if (hosts[i])
+            if (int rc = ensure_img(h, i)) return rc;
+    if (h_binary && !h->d_binary) CU(dev_alloc(h, &h->d_binary, E * 6, false));
+    int rc = bw_observe(h, h_block_img ? h->d_img[0] : nullptr, h_binary ? h->d_binary : nullptr,
+                        h_obstacle_img ? h->d_img[1] : nullptr, h_reward_img ? h->d_img[2] : nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < 3; i++)
+        if (hosts[i]) CU(cudaMemcpyAsync(hosts[i], h->d_img[i], img_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (h_binary)
+        CU(cudaMemcpyAsync(h_binary, h->d_binary, sizeof(float) * E * 6, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
+                         int32_t n_offsets, int32_t amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand,
+                         uint64_t *d_action_bits) {
+    if (!h || !d_cand || !d_valid || !d_n_cand || amax <= 0) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    if (n_ground < 0 || n_ground > 256 || n_offsets < 0 || n_offsets > 256)
+        return fail(h, BW_ERR_CAPACITY, "at most 256 ground offsets / block offsets");
+    if ((n_ground > 0 && !h_x_discr_ground) || (n_offsets > 0 && !h_offset_values)) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    if (n_ground > 0)
+        CU(cudaMemcpyAsync(h->d_ground, h_x_discr_ground, sizeof(double) * n_ground, cudaMemcpyHostToDevice, h->stream));
+    if (n_offsets > 0)
+        CU(cudaMemcpyAsync(h->d_offsets, h_offset_values, sizeof(double) * n_offsets, cudaMemcpyHostToDevice, h->stream));
+    launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
+                     d_action_bits, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_expand_bits(bw_handle *h, const uint64_t *d_bits, int64_t n, float *d_img) {
+    if (!h || !d_bits || !d_img || n < 0) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    if (n > 0) {
+        launch_expand_bits(d_bits, n, d_img, h->stream);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
+                     int32_t amax, uint64_t seed, bw_action *d_actions, int32_t *d_index) {
+    if (!h || !d_cand || !d_valid || !d_n_cand || !d_actions || amax <= 0) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    launch_select_random(h->P, d_cand, d_valid, d_n_cand, amax, seed, d_actions, d_index, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_get_state(bw_handle *h, bw_block *h_blocks, int32_t *h_n_blocks) {
+    if (!h || !h_blocks || !h_n_blocks) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const int E = h->P.E;
+    std::vector<Pose> pose((size_t)E * NB);
+    std::vector<uint8_t> shp((size_t)E * NB);
+    std::vector<uint32_t> sm(E);
+    CU(cudaMemcpyAsync(pose.data(), h->P.pose, sizeof(Pose) * pose.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(shp.data(), h->P.shape_of, shp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(sm.data(), h->P.static_mask, sizeof(uint32_t) * E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h_n_blocks, h->P.n_blocks, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int e = 0; e < E; e++)
+        for (int i = 0; i < NB; i++) {
+            bw_block &b = h_blocks[(size_t)e * NB + i];
+            const Pose &p = pose[(size_t)e * NB + i];
+            const bool live = i < h_n_blocks[e];
+            b.x = live ? p.x : 0.0; b.z = live ? p.z : 0.0; b.c = live ? p.c : 1.0; b.s = live ? p.s : 0.0;
+            b.shape = live ? shp[(size_t)e * NB + i] : -1;
+            b.is_static = live ? (int32_t)((sm[e] >> i) & 1u) : 0;
+        }
+    return BW_OK;
+}
+
+int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits, uint64_t *h_obstacle_bits) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t bytes = sizeof(uint64_t) * (size_t)h->P.E * IMG;
+    if (h_block_bits) CU(cudaMemcpyAsync(h_block_bits, h->P.block_bits, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (h_obstacle_bits) CU(cudaMemcpyAsync(h_obstacle_bits, h->P.obst_bits, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h_n_itf) {
+    if (!h || !h_itf || !h_n_itf || variant < 0 || variant > 1) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t E = (size_t)h->P.E;
+    if (!h->d_itf) {
+        CU(dev_alloc(h, &h->d_itf, E * BW_MAX_INTERFACES));
+        CU(dev_alloc(h, &h->d_nitf, E));
+    }
+    CU(cudaMemsetAsync(h->d_itf, 0, sizeof(bw_interface) * E * BW_MAX_INTERFACES, h->stream));
+    // the state did not change since the last step: re-evaluating it reproduces the same
+    // interfaces and dual iterates, this time with the read-back enabled
+    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, h->d_itf, h->d_nitf, variant, h->smem_step, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_itf, h->d_itf, sizeof(bw_interface) * E * BW_MAX_INTERFACES, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h_n_itf, h->d_nitf, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+}  // extern "C"

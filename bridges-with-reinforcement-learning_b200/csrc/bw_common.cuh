@@ -1,0 +1,177 @@
+// Shared device-side definitions of the bridges_b200 kernels.
+//
+// Canonical arithmetic: every geometric quantity that decides a
+// raster bit, a bounds flag or a target hit is computed in float64 with individually
+// rounded multiplies and adds -- written with the __d*_rn intrinsics so that neither
+// nvcc's FMA contraction nor -use_fast_math can change a bit.  The solver is free to
+// use FMAs (its results are compared with a tolerance).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bridges_b200.h"
+
+namespace bw {
+
+constexpr int NB = BW_MAX_BLOCKS;          // 16
+constexpr int NBODY = NB + 1;              // floor + blocks; body 0 = floor, body j+1 = block j
+constexpr int NF = BW_MAX_FACES;           // 6
+constexpr int NV = BW_MAX_VERTS;           // 6
+constexpr int IMG = BW_IMG;                // 64
+constexpr int MAXITF = BW_MAX_INTERFACES;  // 48
+constexpr int MAXC = 2 * MAXITF;           // contact points
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+
+// R(x, z) = (c*x + s*z, c*z - s*x): rotation about +y, canonical operation order
+__device__ __forceinline__ void rot(double c, double s, double x, double z, double &ox, double &oz) {
+    ox = dadd(dmul(c, x), dmul(s, z));
+    oz = dsub(dmul(c, z), dmul(s, x));
+}
+
+// block library entry as stored on the device
+struct ShapeDev {
+    int32_t n_faces, n_verts;
+    uint32_t target_faces_mask, receiving_faces_mask;
+    double face_nx[NF], face_nz[NF], face_cx[NF], face_cz[NF];
+    double end0_x[NF], end0_z[NF], end1_x[NF], end1_z[NF];
+    double vert_x[NV], vert_z[NV];
+    double com_x, com_z, area, depth;
+    double radius;   // max distance com -> vertex (torque row scale)
+};
+
+// per-environment task + bookkeeping (AssemblyGym attributes)
+struct TaskDev {
+    int32_t n_obstacles, n_targets;
+    double obstacle_xz[BW_MAX_OBSTACLES][2];
+    double target_xz[BW_MAX_TARGETS][2];
+    int8_t remaining[BW_MAX_TARGETS];   // targets_remaining, as indices into targets, list order
+    int8_t reached[BW_MAX_TARGETS];     // targets_reached, in the order they were reached
+    int8_t n_remaining, n_reached;
+    int8_t pad[6];
+};
+
+struct Pose {
+    double x, z, c, s;
+};
+
+// everything a kernel needs about the handle (passed by value)
+struct Params {
+    int32_t E;
+    int32_t max_steps;
+    int32_t n_shapes;
+    int32_t max_blocks;       // capacity used for shared-memory sizing (<= NB)
+    int32_t max_itf;          // interface capacity used for shared-memory sizing (<= MAXITF)
+    double xlim0, xlim1, ylim0, ylim1;
+    double floor_halfwidth, floor_depth, density, tmax, amin, stable_tol;
+    double inv_step_x, inv_step_y;       // 1/pixel pitch (only for conservative index ranges)
+    const double *xs;          // [IMG] pixel x coordinates (numpy linspace semantics)
+    const double *ys;          // [IMG] pixel z coordinates, row 0 = top
+    const ShapeDev *shapes;    // [n_shapes]
+    // state
+    int32_t *n_blocks;         // [E]
+    Pose *pose;                // [E][NB]
+    uint8_t *shape_of;         // [E][NB]
+    uint8_t *face_occ;         // [E][NB] bit f = face f occupied (block_graph, gym_env.py:229-232)
+    uint32_t *static_mask;     // [E] bit i = block i is a support
+    uint64_t *block_bits;      // [E][IMG] raster of the placed blocks
+    uint64_t *obst_bits;       // [E][IMG] raster of the obstacles
+    float *reward_img;         // [E][IMG*IMG] Gaussian-blurred target raster
+    TaskDev *task;             // [E]
+    double *mu;                // [E]
+    uint8_t *done;             // [E] last step returned terminated | truncated
+    bw_step_out *last_out;     // [E] copy of the last step result (binary features of observe)
+};
+
+// ---------------------------------------------------------------- placement (K1)
+// create_block (gym_env.py:204-216) -> align_frames_2d (geometry.py:39-50) in canonical
+// arithmetic.  Returns 0 and the new pose, 1 for invalid indices, 2 when the env is full.
+__device__ inline int place_block(const Params &P, const Pose *poses, const uint8_t *shape_of, int n,
+                                  const bw_action &act, Pose &out) {
+    bool ok = act.shape >= 0 && act.shape < P.n_shapes && act.face >= 0 && act.target_block >= -1 &&
+              act.target_block < n;
+    if (ok) ok = act.face < P.shapes[act.shape].n_faces;
+    if (ok && act.target_block >= 0)
+        ok = act.target_face >= 0 && act.target_face < P.shapes[shape_of[act.target_block]].n_faces;
+    if (!ok) return 1;
+    if (n >= P.max_blocks) return 2;
+    double p1x = 0.0, p1z = 0.0, n1x = 0.0, n1z = 1.0;   // Frame.worldXY(): floor
+    if (act.target_block >= 0) {
+        const Pose tp = poses[act.target_block];
+        const ShapeDev &ts = P.shapes[shape_of[act.target_block]];
+        rot(tp.c, tp.s, ts.face_nx[act.target_face], ts.face_nz[act.target_face], n1x, n1z);
+        double rx, rz;
+        rot(tp.c, tp.s, ts.face_cx[act.target_face], ts.face_cz[act.target_face], rx, rz);
+        p1x = dadd(rx, tp.x);
+        p1z = dadd(rz, tp.z);
+    }
+    const ShapeDev &sh = P.shapes[act.shape];
+    const double n2x = sh.face_nx[act.face], n2z = sh.face_nz[act.face];
+    const double p2x = sh.face_cx[act.face], p2z = sh.face_cz[act.face];
+    double c = -dadd(dmul(n1x, n2x), dmul(n1z, n2z));
+    c = fmin(1.0, fmax(-1.0, c));
+    const double cross_y = dsub(dmul(n1z, n2x), dmul(n1x, n2z));
+    double s = fabs(cross_y);
+    if (!(dadd(cross_y, 1e-6) > 0.0)) s = -s;      // the "+1e-6" axis of geometry.py:47
+    const double wx = dadd(dadd(dmul(n1z, act.offset_x), dmul(n1x, act.offset_y)), p1x);
+    const double wz = dadd(dsub(dmul(n1z, act.offset_y), dmul(n1x, act.offset_x)), p1z);
+    double rx, rz;
+    rot(c, s, p2x, p2z, rx, rz);
+    out.x = dsub(wx, rx);
+    out.z = dsub(wz, rz);
+    out.c = c;
+    out.s = s;
+    return 0;
+}
+
+// posed bounding box of a shape
+__device__ inline void posed_aabb(const ShapeDev &sh, const Pose &ps, double &xmin, double &xmax, double &zmin,
+                                  double &zmax) {
+    xmin = 1e300; xmax = -1e300; zmin = 1e300; zmax = -1e300;
+    for (int v = 0; v < sh.n_verts; v++) {
+        double vx, vz;
+        rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+        vx = dadd(vx, ps.x);
+        vz = dadd(vz, ps.z);
+        xmin = fmin(xmin, vx); xmax = fmax(xmax, vx);
+        zmin = fmin(zmin, vz); zmax = fmax(zmax, vz);
+    }
+}
+
+// ---------------------------------------------------------------- raster (K4)
+// Bits of image row `row` covered by shape `sh` posed at `ps`: contains_2d
+// (assembly_env.py:126-137) at the pixel nodes of render_blocks_2d (rendering.py:105-113).
+// Half-plane value (px-cx)*nx + (pz-cz)*nz with individually rounded operations, `<= 0`.
+// Only a conservative index window around the bounding box is visited.
+__device__ inline uint64_t raster_row(const Params &P, const ShapeDev &sh, const Pose &ps, int row) {
+    double xmin, xmax, zmin, zmax;
+    posed_aabb(sh, ps, xmin, xmax, zmin, zmax);
+    int j_lo = (int)floor((xmin - P.xlim0) * P.inv_step_x) - 1;
+    int j_hi = (int)ceil((xmax - P.xlim0) * P.inv_step_x) + 1;
+    const int i_lo = (int)floor((P.ylim1 - zmax) * P.inv_step_y) - 1;
+    const int i_hi = (int)ceil((P.ylim1 - zmin) * P.inv_step_y) + 1;
+    j_lo = max(j_lo, 0);
+    j_hi = min(j_hi, IMG - 1);
+    if (row < i_lo || row > i_hi || j_hi < j_lo) return 0;
+    const double pz = P.ys[row];
+    uint64_t bits = (j_hi - j_lo + 1 >= 64) ? ~0ull : (((1ull << (j_hi - j_lo + 1)) - 1) << j_lo);
+    for (int k = 0; k < sh.n_faces; k++) {
+        double nx, nz, ax, az;
+        rot(ps.c, ps.s, sh.face_nx[k], sh.face_nz[k], nx, nz);
+        rot(ps.c, ps.s, sh.face_cx[k], sh.face_cz[k], ax, az);
+        const double cx = dadd(ax, ps.x), cz = dadd(az, ps.z);
+        const double vz = dmul(dsub(pz, cz), nz);
+        uint64_t keep = 0;
+        for (int j = j_lo; j <= j_hi; j++) {
+            if (!((bits >> j) & 1ull)) continue;
+            const double v = dadd(dmul(dsub(P.xs[j], cx), nx), vz);
+            if (v <= 0.0) keep |= 1ull << j;
+        }
+        bits &= keep;
+        if (!bits) break;
+    }
+    return bits;
+}
+
+}  // namespace bw

@@ -1,0 +1,28 @@
+// Host-callable launchers of the bridges_b200 kernels (one per .cu file).
+#pragma once
+#include "bw_common.cuh"
+
+namespace bw {
+
+// bw_step.cu
+void upload_step_tables();
+int step_smem_bytes(int max_blocks, int max_itf);
+cudaError_t configure_step(int smem_bytes);
+void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
+                 bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes, cudaStream_t stream);
+
+// bw_obs.cu
+void upload_obs_tables(const float *gauss, const ShapeDev *marker);
+void launch_reset(const Params &P, const bw_task *d_tasks, const uint8_t *d_mask, int only_done, cudaStream_t stream);
+void launch_observe(const Params &P, float *d_block_img, float *d_binary, float *d_obstacle_img, float *d_reward_img,
+                    cudaStream_t stream);
+void launch_expand_bits(const uint64_t *d_bits, int64_t n, float *d_img, cudaStream_t stream);
+
+// bw_actions.cu
+void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
+                      int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
+                      cudaStream_t stream);
+void launch_select_random(const Params &P, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
+                          int amax, uint64_t seed, bw_action *d_actions, int32_t *d_index, cudaStream_t stream);
+
+}  // namespace bw

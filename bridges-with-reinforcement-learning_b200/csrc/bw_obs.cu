@@ -1,0 +1,192 @@
+// K4: reset-time rasters and the observation tensors.
+//
+//   reset_kernel    AssemblyGym.reset gym_env.py:255-289 + get_task_features
+//                   successor_dqn.py:67-85 (obstacle raster, Gaussian-blurred target raster,
+//                   convolve_with_gaussian robotoddler/utils/utils.py:93-114)
+//   observe_kernel  get_state_features successor_dqn.py:47-64 / render_blocks_2d
+//                   rendering.py:105-113: bit raster -> f32 [E,1,64,64], binary features [E,6]
+//
+// Rasters are kept bit-packed in HBM (512 B per image); the f32 expansion is a pure
+// streaming write (16 KB per image) with 16-byte coalesced stores.
+#include "bw_common.cuh"
+#include "bw_kernels.cuh"
+
+namespace bw {
+
+constexpr int KSIZE = 101;   // successor_dqn.py:78-79
+__constant__ float c_gauss[KSIZE];
+__constant__ ShapeDev c_marker;   // cube06: obstacles and target markers (gym_env.py:277, successor_dqn.py:73)
+
+void upload_obs_tables(const float *gauss, const ShapeDev *marker) {
+    if (gauss) cudaMemcpyToSymbol(c_gauss, gauss, sizeof(float) * KSIZE);
+    if (marker) cudaMemcpyToSymbol(c_marker, marker, sizeof(ShapeDev));
+}
+
+__global__ void __launch_bounds__(64)
+reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restrict__ mask, int only_done) {
+    const int e = blockIdx.x;
+    if (mask != nullptr && mask[e] == 0) return;
+    if (only_done && P.done[e] == 0) return;
+    const int tid = threadIdx.x;
+    __shared__ TaskDev tk;
+    __shared__ float s_tmp[IMG][IMG + 1];
+    __shared__ uint64_t s_tbits[IMG];
+    __shared__ Pose s_pose[NB];
+    __shared__ uint8_t s_shape[NB];
+    __shared__ int s_n;
+
+    if (tid == 0) {
+        if (tasks != nullptr) {
+            const bw_task &t = tasks[e];
+            tk.n_obstacles = min(max(t.n_obstacles, 0), BW_MAX_OBSTACLES);
+            tk.n_targets = min(max(t.n_targets, 0), BW_MAX_TARGETS);
+            for (int i = 0; i < BW_MAX_OBSTACLES; i++) {
+                tk.obstacle_xz[i][0] = t.obstacle_xz[i][0];
+                tk.obstacle_xz[i][1] = t.obstacle_xz[i][1];
+            }
+            for (int i = 0; i < BW_MAX_TARGETS; i++) {
+                tk.target_xz[i][0] = t.target_xz[i][0];
+                tk.target_xz[i][1] = t.target_xz[i][1];
+            }
+            int nb = min(max(t.n_blocks, 0), P.max_blocks);
+            uint32_t sm = 0;
+            for (int i = 0; i < nb; i++) {
+                Pose ps;
+                ps.x = t.blocks[i].x; ps.z = t.blocks[i].z; ps.c = t.blocks[i].c; ps.s = t.blocks[i].s;
+                s_pose[i] = ps;
+                s_shape[i] = (uint8_t)t.blocks[i].shape;
+                if (t.blocks[i].is_static) sm |= 1u << i;
+                P.pose[(size_t)e * NB + i] = ps;
+                P.shape_of[(size_t)e * NB + i] = (uint8_t)t.blocks[i].shape;
+            }
+            s_n = nb;
+            P.static_mask[e] = sm;
+        } else {
+            tk = P.task[e];
+            s_n = 0;
+            P.static_mask[e] = 0;
+        }
+        for (int i = 0; i < BW_MAX_TARGETS; i++) { tk.remaining[i] = (int8_t)i; tk.reached[i] = -1; }
+        tk.n_remaining = (int8_t)tk.n_targets;
+        tk.n_reached = 0;
+        P.task[e] = tk;
+        P.n_blocks[e] = s_n;
+        P.done[e] = 0;
+        bw_step_out o;
+        memset(&o, 0, sizeof(o));
+        o.stable = 1;                     // empty assembly: stability.py:53-56
+        o.stable_unfrozen = 1;
+        for (int i = 0; i < BW_MAX_TARGETS; i++) o.distance_to_targets[i] = INFINITY;
+        P.last_out[e] = o;
+    }
+    if (tid < NB) P.face_occ[(size_t)e * NB + tid] = 0;
+    __syncthreads();
+
+    // rasters: one thread per image row
+    const int row = tid;
+    uint64_t bbits = 0;
+    for (int i = 0; i < s_n; i++) bbits |= raster_row(P, P.shapes[s_shape[i]], s_pose[i], row);
+    P.block_bits[(size_t)e * IMG + row] = bbits;
+    if (tasks == nullptr) return;   // obstacles / targets unchanged: keep their rasters
+
+    uint64_t obits = 0, tbits = 0;
+    for (int i = 0; i < tk.n_obstacles; i++) {
+        Pose ps;
+        ps.x = tk.obstacle_xz[i][0]; ps.z = tk.obstacle_xz[i][1]; ps.c = 1.0; ps.s = 0.0;
+        obits |= raster_row(P, c_marker, ps, row);
+    }
+    for (int i = 0; i < tk.n_targets; i++) {
+        Pose ps;
+        ps.x = tk.target_xz[i][0]; ps.z = tk.target_xz[i][1]; ps.c = 1.0; ps.s = 0.0;
+        tbits |= raster_row(P, c_marker, ps, row);
+    }
+    P.obst_bits[(size_t)e * IMG + row] = obits;
+    s_tbits[row] = tbits;
+    // horizontal pass: tmp[row][j] = sum_v k[v - j + 50] * in[row][v]
+    for (int j = 0; j < IMG; j++) {
+        float acc = 0.0f;
+        uint64_t bb = tbits;
+        while (bb) {
+            const int v = __ffsll((long long)bb) - 1;
+            bb &= bb - 1;
+            const int k = v - j + KSIZE / 2;
+            if (k >= 0 && k < KSIZE) acc += c_gauss[k];
+        }
+        s_tmp[row][j] = acc;
+    }
+    __syncthreads();
+    // vertical pass, thread = column
+    const int col = tid;
+    float *dst = P.reward_img + (size_t)e * IMG * IMG;
+    for (int i = 0; i < IMG; i++) {
+        float acc = 0.0f;
+        for (int u = 0; u < IMG; u++) {
+            if (s_tbits[u] == 0) continue;
+            const int k = u - i + KSIZE / 2;
+            if (k >= 0 && k < KSIZE) acc += c_gauss[k] * s_tmp[u][col];
+        }
+        dst[i * IMG + col] = acc;
+    }
+}
+
+void launch_reset(const Params &P, const bw_task *d_tasks, const uint8_t *d_mask, int only_done, cudaStream_t stream) {
+    reset_kernel<<<P.E, 64, 0, stream>>>(P, d_tasks, d_mask, only_done);
+}
+
+// ------------------------------------------------------------------ observation tensors
+__device__ __forceinline__ float4 nibble_to_float4(uint64_t rowbits, int c4) {
+    const unsigned nib = (unsigned)(rowbits >> (4 * c4)) & 0xfu;
+    return make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                       (nib & 8u) ? 1.0f : 0.0f);
+}
+
+// grid-stride over float4 elements of [n,64,64]; 16 float4 per image row
+__global__ void __launch_bounds__(256)
+expand_bits_kernel(const uint64_t *__restrict__ bits, int64_t n_vec4, float4 *__restrict__ img) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t rowbits = __ldg(bits + (i >> 4));
+        __stcs(img + i, nibble_to_float4(rowbits, (int)(i & 15)));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+copy_f4_kernel(const float4 *__restrict__ src, int64_t n_vec4, float4 *__restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += (int64_t)gridDim.x * blockDim.x)
+        __stcs(dst + i, __ldcs(src + i));
+}
+
+__global__ void binary_kernel(Params P, float *__restrict__ binary) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.E) return;
+    const bw_step_out &o = P.last_out[e];
+    float *b = binary + (size_t)e * 6;
+    b[0] = o.stable; b[1] = o.collision; b[2] = o.collision_block;
+    b[3] = o.collision_obstacle; b[4] = o.collision_floor; b[5] = o.collision_boundary;
+}
+
+static int grid_for(int64_t n_items, int threads) {
+    int64_t blocks = (n_items + threads - 1) / threads;
+    const int64_t cap = 148LL * 16;          // a few waves of the 148 SMs; grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+void launch_expand_bits(const uint64_t *d_bits, int64_t n, float *d_img, cudaStream_t stream) {
+    const int64_t n4 = n * (IMG * IMG / 4);
+    expand_bits_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(d_bits, n4, reinterpret_cast<float4 *>(d_img));
+}
+
+void launch_observe(const Params &P, float *d_block_img, float *d_binary, float *d_obstacle_img, float *d_reward_img,
+                    cudaStream_t stream) {
+    if (d_block_img) launch_expand_bits(P.block_bits, P.E, d_block_img, stream);
+    if (d_obstacle_img) launch_expand_bits(P.obst_bits, P.E, d_obstacle_img, stream);
+    if (d_reward_img) {
+        const int64_t n4 = (int64_t)P.E * (IMG * IMG / 4);
+        copy_f4_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(P.reward_img), n4,
+                                                              reinterpret_cast<float4 *>(d_reward_img));
+    }
+    if (d_binary) binary_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, d_binary);
+}
+
+}  // namespace bw

@@ -1,0 +1,843 @@
+// K1+K2+K3 (+ the raster update of K4): one CTA (two warps) per environment.
+//
+//   phase 1  block placement            create_block gym_env.py:204-216 -> align_frames_2d geometry.py:39-50
+//   phase 2  contact interfaces         _reset_cra_assembly assembly_env.py:281-304 -> assembly_interfaces_numpy
+//   phase 3  rigid-block equilibrium    is_stable_rbe stability.py:49-71 -> rbe_solve, twice:
+//            warp 0 = supports as step() leaves them (new block frozen, gym_env.py:238-245),
+//            warp 1 = last block released (stabilities_freezing gym_env.py:325-333)
+//   phase 4  targets / reward / termination / block_graph  gym_env.py:11-22,141-168,224-232
+//   phase 5  raster update of the new block (render_blocks_2d rendering.py:105-113) + lin_reward
+//
+// The equilibrium check is the cone-constrained least-squares problem
+//     r* = min_{f in K} ||A f - b|| / ||b||,   K = product of 2-D friction cones,
+// solved in its dual (3 unknowns per free block) by a proximal-point iteration whose
+// sub-problems are solved by a semismooth Newton method.  Each
+// problem lives in the shared memory of its warp; reductions are warp shuffles.
+#include "bw_common.cuh"
+#include "bw_kernels.cuh"
+
+namespace bw {
+
+// lexicographic body pairs (a < b) over NBODY = 17 bodies
+__constant__ uint8_t c_pair_a[NBODY * (NBODY - 1) / 2];
+__constant__ uint8_t c_pair_b[NBODY * (NBODY - 1) / 2];
+// (I >= J) index pairs of the lower triangle of a 16 x 16 block matrix, row-major
+__constant__ uint8_t c_tri_i[NB * (NB + 1) / 2];
+__constant__ uint8_t c_tri_j[NB * (NB + 1) / 2];
+
+constexpr int NPAIR = NBODY * (NBODY - 1) / 2;  // 136
+constexpr int NSCHED = 6;
+__constant__ double c_rho[NSCHED] = {1e2, 1e4, 1e6, 1e8, 1e8, 1e8};
+constexpr int MAX_NEWTON = 60;
+constexpr unsigned FULL = 0xffffffffu;
+
+void upload_step_tables() {
+    uint8_t pa[NPAIR], pb[NPAIR], ti[NB * (NB + 1) / 2], tj[NB * (NB + 1) / 2];
+    int p = 0;
+    for (int a = 0; a < NBODY; a++)
+        for (int b = a + 1; b < NBODY; b++) { pa[p] = (uint8_t)a; pb[p] = (uint8_t)b; p++; }
+    p = 0;
+    for (int i = 0; i < NB; i++)
+        for (int j = 0; j <= i; j++) { ti[p] = (uint8_t)i; tj[p] = (uint8_t)j; p++; }
+    cudaMemcpyToSymbol(c_pair_a, pa, sizeof(pa));
+    cudaMemcpyToSymbol(c_pair_b, pb, sizeof(pb));
+    cudaMemcpyToSymbol(c_tri_i, ti, sizeof(ti));
+    cudaMemcpyToSymbol(c_tri_j, tj, sizeof(tj));
+}
+
+// ------------------------------------------------------------------ shared memory layout
+struct Layout {
+    // offsets in bytes from the start of dynamic shared memory
+    int pose, body, faces, pairs, contacts_G, contacts_ab, adj, prob[2], total;
+    int MM, MC, HS;
+};
+
+struct ProbOff {  // offsets inside one problem block
+    int y, yk, rhs, d, b, g, h, f, invd, H, typ, rowbase, freebody, size;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
+    ProbOff o;
+    int p = 0;
+    o.y = p; p += MM * 8;
+    o.yk = p; p += MM * 8;
+    o.rhs = p; p += MM * 8;
+    o.d = p; p += MM * 8;
+    o.b = p; p += MM * 8;
+    o.invd = p; p += MM * 8;
+    o.g = p; p += 2 * MC * 8;
+    o.h = p; p += 2 * MC * 8;
+    o.f = p; p += 2 * MC * 8;
+    o.H = p; p += HS * 8;
+    o.typ = p; p += align16(MC);
+    o.rowbase = p; p += align16(NBODY);
+    o.freebody = p; p += align16(NB);
+    o.size = align16(p);
+    return o;
+}
+
+constexpr int BODY_DOUBLES = 8;   // comx, comz, weight, depth, xmin, xmax, zmin, zmax
+constexpr int FACE_DOUBLES = 8;   // nx, nz, cx, cz, e0x, e0z, e1x, e1z
+
+__host__ __device__ inline Layout make_layout(int max_blocks, int max_itf) {
+    Layout L;
+    L.MM = 3 * max_blocks;
+    L.MC = 2 * max_itf;
+    L.HS = L.MM * (L.MM + 1) / 2;
+    int p = 0;
+    L.pose = p; p += NB * (int)sizeof(Pose) + align16(NB);          // poses + shape ids
+    L.body = p; p += NBODY * BODY_DOUBLES * 8;
+    L.contacts_G = p; p += L.MC * 12 * 8;
+    L.contacts_ab = p; p += align16(2 * L.MC);
+    L.adj = p; p += align16(NBODY + 1) + align16(2 * L.MC);
+    ProbOff po = prob_layout(L.MM, L.MC, L.HS);
+    L.prob[0] = p; p += po.size;
+    L.prob[1] = p; p += po.size;
+    // faces + pair scratch are dead once the contacts are assembled: they alias the
+    // H matrices (the first bytes of problem 0 are y.. vectors which are initialised later)
+    L.faces = L.prob[0];
+    L.pairs = L.faces + NBODY * NF * FACE_DOUBLES * 8;
+    int scratch_end = L.pairs + NPAIR * 16 + align16(NPAIR * 2);
+    if (scratch_end > p) p = scratch_end;
+    L.total = align16(p);
+    return L;
+}
+
+int step_smem_bytes(int max_blocks, int max_itf) { return make_layout(max_blocks, max_itf).total; }
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// projection of (gn, gt) onto the friction cone |ft| <= mu fn.
+// typ: 0 = polar cone (f = 0), 1 = interior, 2 = ray ft = +mu fn, 3 = ray ft = -mu fn
+__device__ __forceinline__ void project_cone(double gn, double gt, double mu, double inv_den, double &fn, double &ft,
+                                             int &typ) {
+    double agt = fabs(gt);
+    if (agt <= mu * gn) {
+        fn = gn; ft = gt; typ = 1;
+    } else if (mu * agt <= -gn) {
+        fn = 0.0; ft = 0.0; typ = 0;
+    } else {
+        double k = (gn + mu * agt) * inv_den;
+        fn = k;
+        if (gt > 0) { ft = mu * k; typ = 2; } else { ft = -mu * k; typ = 3; }
+    }
+}
+
+struct Solver {
+    // shared, read-only during the solve
+    const double *G;         // [nc][12]
+    const uint8_t *c_a, *c_b;
+    const uint8_t *adj_ptr;  // [NBODY+1]
+    const uint8_t *adj;      // entries: contact | side << 7
+    // per problem
+    double *y, *yk, *rhs, *d, *b, *g, *h, *f, *invd, *H;
+    uint8_t *typ;
+    int8_t *rowbase;
+    uint8_t *freebody;
+    int m, nfree, nc, lane;
+    double mu, inv_den;
+
+    // g = A^T v for every contact point (lanes over contacts)
+    __device__ __forceinline__ void at_times(const double *v, double *out) const {
+        for (int c = lane; c < nc; c += 32) {
+            const double *Gc = G + c * 12;
+            int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
+            double gn = 0.0, gt = 0.0;
+            if (ra >= 0) {
+                double v0 = v[ra], v1 = v[ra + 1], v2 = v[ra + 2];
+                gn += Gc[0] * v0 + Gc[1] * v1 + Gc[2] * v2;
+                gt += Gc[3] * v0 + Gc[4] * v1 + Gc[5] * v2;
+            }
+            if (rb >= 0) {
+                double v0 = v[rb], v1 = v[rb + 1], v2 = v[rb + 2];
+                gn += Gc[6] * v0 + Gc[7] * v1 + Gc[8] * v2;
+                gt += Gc[9] * v0 + Gc[10] * v1 + Gc[11] * v2;
+            }
+            out[2 * c] = gn;
+            out[2 * c + 1] = gt;
+        }
+    }
+
+    // f = P_K(g), typ
+    __device__ __forceinline__ void project_all() {
+        for (int c = lane; c < nc; c += 32) {
+            double fn, ft;
+            int t;
+            project_cone(g[2 * c], g[2 * c + 1], mu, inv_den, fn, ft, t);
+            f[2 * c] = fn;
+            f[2 * c + 1] = ft;
+            typ[c] = (uint8_t)t;
+        }
+    }
+
+    // (A f)_i for row i
+    __device__ __forceinline__ double a_times_f_row(int i) const {
+        int I = i / 3, k = i - 3 * I;
+        int body = freebody[I];
+        double acc = 0.0;
+        for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
+            int e = adj[q];
+            int c = e & 0x7f, side = e >> 7;
+            const double *Gc = G + c * 12 + side * 6;
+            acc += Gc[k] * f[2 * c] + Gc[3 + k] * f[2 * c + 1];
+        }
+        return acc;
+    }
+
+    // H = A J A^T + I/rho (packed lower)
+    __device__ void assemble_H(double inv_rho) {
+        int ntile = (nfree * (nfree + 1)) >> 1;
+        const double isd = sqrt(inv_den);
+        for (int t = lane; t < ntile; t += 32) {
+            int I = c_tri_i[t], J = c_tri_j[t];
+            int bi = freebody[I], bj = freebody[J];
+            double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
+            for (int q = adj_ptr[bi]; q < adj_ptr[bi + 1]; q++) {
+                int e = adj[q];
+                int c = e & 0x7f, side = e >> 7;
+                int other = side ? c_a[c] : c_b[c];
+                int tp = typ[c];
+                if (tp == 0) continue;
+                const double *Gi = G + c * 12 + side * 6;
+                const double *Gj;
+                if (I == J) Gj = Gi;
+                else if (other == bj) Gj = G + c * 12 + (1 - side) * 6;
+                else continue;
+                if (tp == 1) {
+                    // both columns
+#pragma unroll
+                    for (int col = 0; col < 2; col++) {
+                        double u0 = Gi[3 * col], u1 = Gi[3 * col + 1], u2 = Gi[3 * col + 2];
+                        double w0 = Gj[3 * col], w1 = Gj[3 * col + 1], w2 = Gj[3 * col + 2];
+                        a00 += u0 * w0; a01 += u0 * w1; a02 += u0 * w2;
+                        a10 += u1 * w0; a11 += u1 * w1; a12 += u1 * w2;
+                        a20 += u2 * w0; a21 += u2 * w1; a22 += u2 * w2;
+                    }
+                } else {
+                    double sm = (tp == 2 ? mu : -mu);
+                    double u0 = (Gi[0] + sm * Gi[3]) * isd, u1 = (Gi[1] + sm * Gi[4]) * isd, u2 = (Gi[2] + sm * Gi[5]) * isd;
+                    double w0 = (Gj[0] + sm * Gj[3]) * isd, w1 = (Gj[1] + sm * Gj[4]) * isd, w2 = (Gj[2] + sm * Gj[5]) * isd;
+                    a00 += u0 * w0; a01 += u0 * w1; a02 += u0 * w2;
+                    a10 += u1 * w0; a11 += u1 * w1; a12 += u1 * w2;
+                    a20 += u2 * w0; a21 += u2 * w1; a22 += u2 * w2;
+                }
+            }
+            int r0 = 3 * I, c0 = 3 * J;
+            if (I == J) {
+                H[tri(r0) + c0] = a00 + inv_rho;
+                H[tri(r0 + 1) + c0] = a10; H[tri(r0 + 1) + c0 + 1] = a11 + inv_rho;
+                H[tri(r0 + 2) + c0] = a20; H[tri(r0 + 2) + c0 + 1] = a21; H[tri(r0 + 2) + c0 + 2] = a22 + inv_rho;
+            } else {
+                H[tri(r0) + c0] = a00; H[tri(r0) + c0 + 1] = a01; H[tri(r0) + c0 + 2] = a02;
+                H[tri(r0 + 1) + c0] = a10; H[tri(r0 + 1) + c0 + 1] = a11; H[tri(r0 + 1) + c0 + 2] = a12;
+                H[tri(r0 + 2) + c0] = a20; H[tri(r0 + 2) + c0 + 1] = a21; H[tri(r0 + 2) + c0 + 2] = a22;
+            }
+        }
+    }
+
+    // solve H d = rhs by Cholesky; rows owned by lanes (i, i + 32); result in d[]
+    __device__ void chol_solve(double inv_rho) {
+        const int i0 = lane, i1 = lane + 32;
+        double z0 = (i0 < m) ? rhs[i0] : 0.0;
+        double z1 = (i1 < m) ? rhs[i1] : 0.0;
+        for (int j = 0; j < m; j++) {
+            double piv = H[tri(j) + j];
+            if (!(piv > 1e-300)) piv = inv_rho;
+            double inv = rsqrt(piv);
+            double l0 = 0.0, l1 = 0.0;
+            if (i0 > j && i0 < m) { l0 = H[tri(i0) + j] * inv; H[tri(i0) + j] = l0; }
+            if (i1 > j && i1 < m) { l1 = H[tri(i1) + j] * inv; H[tri(i1) + j] = l1; }
+            if (lane == 0) invd[j] = inv;
+            double zj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * inv;
+            if (i0 == j) z0 = zj;
+            if (i1 == j) z1 = zj;
+            if (i0 > j) z0 -= l0 * zj;
+            if (i1 > j) z1 -= l1 * zj;
+            __syncwarp();
+            // trailing update, rows >= k of column k
+            int k = j + 1;
+            for (; k + 3 < m; k += 4) {
+                double lk0 = H[tri(k) + j], lk1 = H[tri(k + 1) + j], lk2 = H[tri(k + 2) + j], lk3 = H[tri(k + 3) + j];
+                if (i0 < m && i0 >= k) {
+                    double *row = H + tri(i0);
+                    double h0 = row[k], h1 = 0, h2 = 0, h3 = 0;
+                    bool b1 = i0 >= k + 1, b2 = i0 >= k + 2, b3 = i0 >= k + 3;
+                    if (b1) h1 = row[k + 1];
+                    if (b2) h2 = row[k + 2];
+                    if (b3) h3 = row[k + 3];
+                    row[k] = h0 - l0 * lk0;
+                    if (b1) row[k + 1] = h1 - l0 * lk1;
+                    if (b2) row[k + 2] = h2 - l0 * lk2;
+                    if (b3) row[k + 3] = h3 - l0 * lk3;
+                }
+                if (i1 < m && i1 >= k) {
+                    double *row = H + tri(i1);
+                    double h0 = row[k], h1 = 0, h2 = 0, h3 = 0;
+                    bool b1 = i1 >= k + 1, b2 = i1 >= k + 2, b3 = i1 >= k + 3;
+                    if (b1) h1 = row[k + 1];
+                    if (b2) h2 = row[k + 2];
+                    if (b3) h3 = row[k + 3];
+                    row[k] = h0 - l1 * lk0;
+                    if (b1) row[k + 1] = h1 - l1 * lk1;
+                    if (b2) row[k + 2] = h2 - l1 * lk2;
+                    if (b3) row[k + 3] = h3 - l1 * lk3;
+                }
+            }
+            for (; k < m; k++) {
+                double lkj = H[tri(k) + j];
+                if (i0 < m && i0 >= k) H[tri(i0) + k] -= l0 * lkj;
+                if (i1 < m && i1 >= k) H[tri(i1) + k] -= l1 * lkj;
+            }
+            __syncwarp();
+        }
+        // back substitution L^T d = z
+        for (int j = m - 1; j >= 0; j--) {
+            double dj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
+            if (i0 == j) z0 = dj;
+            if (i1 == j) z1 = dj;
+            const double *row = H + tri(j);
+            if (i0 < j) z0 -= row[i0] * dj;
+            if (i1 < j) z1 -= row[i1] * dj;
+        }
+        if (i0 < m) d[i0] = z0;
+        if (i1 < m) d[i1] = z1;
+        __syncwarp();
+    }
+
+    // relative residual ||b - A P_K(A^T y)|| (b is normalised)
+    __device__ double residual() {
+        at_times(y, g);
+        __syncwarp();
+        project_all();
+        __syncwarp();
+        double acc = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            double r = b[i] - a_times_f_row(i);
+            acc += r * r;
+        }
+        return sqrt(warp_sum(acc));
+    }
+
+    // returns status: 0 feasible (r <= 1e-9), 1 stagnated at r* > 0, 2 not converged
+    __device__ int solve(double &r_out, int &iters_out) {
+        for (int i = lane; i < m; i += 32) y[i] = 0.0;
+        __syncwarp();
+        double rprev = -1.0, r = 1.0;
+        int status = 2, iters = 0;
+        for (int k = 0; k < NSCHED; k++) {
+            const double rho = c_rho[k], inv_rho = 1.0 / rho;
+            for (int i = lane; i < m; i += 32) yk[i] = y[i];
+            __syncwarp();
+            for (int it = 0; it < MAX_NEWTON; it++) {
+                at_times(y, g);
+                __syncwarp();
+                project_all();
+                __syncwarp();
+                double acc = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    double gr = b[i] - a_times_f_row(i) - (y[i] - yk[i]) * inv_rho;
+                    rhs[i] = gr;
+                    acc += gr * gr;
+                }
+                double gn2 = warp_sum(acc);
+                if (gn2 <= 1e-20) break;
+                assemble_H(inv_rho);
+                __syncwarp();
+                chol_solve(inv_rho);
+                at_times(d, h);
+                __syncwarp();
+                // dots for the line search
+                double dd = 0.0, bd = 0.0, yd = 0.0, gd = 0.0, yy = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    double di = d[i];
+                    dd += di * di;
+                    bd += b[i] * di;
+                    yd += (y[i] - yk[i]) * di;
+                    gd += rhs[i] * di;
+                    yy += y[i] * y[i];
+                }
+                dd = warp_sum(dd); bd = warp_sum(bd); yd = warp_sum(yd); gd = warp_sum(gd); yy = warp_sum(yy);
+                const double phi0 = gd;
+                if (!(phi0 > 1e-30)) break;
+                // derivative of the concave dual along d: phi'(t) = b.d - P_K(g + t h).h - (yd + t dd)/rho
+                double t = 1.0;
+                double p;
+                for (int ls = 0; ls < 30; ls++) {
+                    double fh = 0.0;
+                    for (int c = lane; c < nc; c += 32) {
+                        double fn, ft;
+                        int tp;
+                        project_cone(g[2 * c] + t * h[2 * c], g[2 * c + 1] + t * h[2 * c + 1], mu, inv_den, fn, ft, tp);
+                        fh += fn * h[2 * c] + ft * h[2 * c + 1];
+                    }
+                    fh = warp_sum(fh);
+                    p = bd - fh - (yd + t * dd) * inv_rho;
+                    if (p >= -1e-12 * phi0) break;
+                    double ts = t * phi0 / (phi0 - p);
+                    t = fmin(fmax(ts, 0.05 * t), 0.95 * t);
+                }
+                for (int i = lane; i < m; i += 32) y[i] += t * d[i];
+                __syncwarp();
+                iters++;
+                if (t * sqrt(dd) <= 1e-15 * fmax(1.0, sqrt(yy))) break;
+            }
+            r = residual();
+            if (r <= 1e-9) { status = 0; break; }
+            if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
+            rprev = r;
+        }
+        r_out = r;
+        iters_out = iters;
+        return status;
+    }
+};
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(64)
+step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
+            bw_step_out *__restrict__ out, bw_interface *__restrict__ save_itf, int32_t *__restrict__ save_nitf,
+            int save_variant) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int e = blockIdx.x;
+    if (mask != nullptr && mask[e] == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Layout L = make_layout(P.max_blocks, P.max_itf);
+
+    Pose *s_pose = reinterpret_cast<Pose *>(smem + L.pose);
+    uint8_t *s_shape = smem + L.pose + NB * sizeof(Pose);
+    double *s_body = reinterpret_cast<double *>(smem + L.body);       // [NBODY][8]
+    double *s_face = reinterpret_cast<double *>(smem + L.faces);      // [NBODY*NF][8]
+    double *s_pair_lohi = reinterpret_cast<double *>(smem + L.pairs); // [NPAIR][2]
+    uint16_t *s_pair_faces = reinterpret_cast<uint16_t *>(smem + L.pairs + NPAIR * 16);
+    double *s_G = reinterpret_cast<double *>(smem + L.contacts_G);
+    uint8_t *s_ca = smem + L.contacts_ab;
+    uint8_t *s_cb = s_ca + L.MC;
+    uint8_t *s_adj_ptr = smem + L.adj;
+    uint8_t *s_adj = s_adj_ptr + align16(NBODY + 1);
+
+    __shared__ int sh_n, sh_error, sh_nitf, sh_cnt[3][2], sh_placed;
+    __shared__ double sh_L0;
+    __shared__ double sh_res[2];
+    __shared__ int sh_status[2], sh_iters[2], sh_stable[2];
+    __shared__ double sh_lin[2];
+
+    const bw_action act = actions[e];
+    const int n_old = P.n_blocks[e];
+    if (tid < n_old) {
+        s_pose[tid] = P.pose[(size_t)e * NB + tid];
+        s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
+    }
+    if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; }
+    __syncthreads();
+
+    // ---------------- phase 1: placement (thread 0)
+    if (tid == 0) {
+        int n = n_old;
+        if (act.shape >= 0) {
+            Pose np;
+            const int err = place_block(P, s_pose, s_shape, n_old, act, np);
+            if (err) sh_error = err;
+            else {
+                s_pose[n] = np;
+                s_shape[n] = (uint8_t)act.shape;
+                n = n_old + 1;
+                sh_placed = 1;
+            }
+        }
+        sh_n = n;
+    }
+    __syncthreads();
+    const int n = sh_n;
+    const int nbody = n + 1;
+    const bool placed = sh_placed != 0;
+    if (sh_error != 0) {
+        if (tid == 0) {
+            bw_step_out o;
+            memset(&o, 0, sizeof(o));
+            o.error = (uint8_t)sh_error;
+            o.n_blocks = n_old;
+            out[e] = o;
+        }
+        return;
+    }
+
+    // ---------------- posed bodies and faces
+    for (int bdy = tid; bdy < nbody; bdy += 64) {
+        double *B = s_body + bdy * BODY_DOUBLES;
+        if (bdy == 0) {
+            B[0] = 0.0; B[1] = -0.05 * P.floor_halfwidth; B[2] = 0.0; B[3] = P.floor_depth;
+            B[4] = -P.floor_halfwidth; B[5] = P.floor_halfwidth; B[6] = -0.1 * P.floor_halfwidth; B[7] = 0.0;
+        } else {
+            const Pose ps = s_pose[bdy - 1];
+            const ShapeDev &sh = P.shapes[s_shape[bdy - 1]];
+            double cx, cz;
+            rot(ps.c, ps.s, sh.com_x, sh.com_z, cx, cz);
+            B[0] = dadd(cx, ps.x);
+            B[1] = dadd(cz, ps.z);
+            B[2] = P.density * sh.area * sh.depth;
+            B[3] = sh.depth;
+            double xmin = 1e300, xmax = -1e300, zmin = 1e300, zmax = -1e300;
+            for (int v = 0; v < sh.n_verts; v++) {
+                double vx, vz;
+                rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+                vx = dadd(vx, ps.x);
+                vz = dadd(vz, ps.z);
+                xmin = fmin(xmin, vx); xmax = fmax(xmax, vx);
+                zmin = fmin(zmin, vz); zmax = fmax(zmax, vz);
+            }
+            B[4] = xmin; B[5] = xmax; B[6] = zmin; B[7] = zmax;
+        }
+    }
+    for (int q = tid; q < nbody * NF; q += 64) {
+        const int bdy = q / NF, fc = q - bdy * NF;
+        double *F = s_face + q * FACE_DOUBLES;
+        if (bdy == 0) {
+            if (fc == 0) {
+                F[0] = 0.0; F[1] = 1.0; F[2] = 0.0; F[3] = 0.0;
+                F[4] = -P.floor_halfwidth; F[5] = 0.0; F[6] = P.floor_halfwidth; F[7] = 0.0;
+            }
+        } else {
+            const Pose ps = s_pose[bdy - 1];
+            const ShapeDev &sh = P.shapes[s_shape[bdy - 1]];
+            if (fc < sh.n_faces) {
+                double ax, az;
+                rot(ps.c, ps.s, sh.face_nx[fc], sh.face_nz[fc], F[0], F[1]);
+                rot(ps.c, ps.s, sh.face_cx[fc], sh.face_cz[fc], ax, az);
+                F[2] = dadd(ax, ps.x); F[3] = dadd(az, ps.z);
+                rot(ps.c, ps.s, sh.end0_x[fc], sh.end0_z[fc], ax, az);
+                F[4] = dadd(ax, ps.x); F[5] = dadd(az, ps.z);
+                rot(ps.c, ps.s, sh.end1_x[fc], sh.end1_z[fc], ax, az);
+                F[6] = dadd(ax, ps.x); F[7] = dadd(az, ps.z);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: interfaces (one candidate per body pair, lexicographic order)
+    unsigned hitmask = 0;  // bit r = pair (r*64 + tid) has an interface
+    for (int r = 0; r < 3; r++) {
+        const int p = r * 64 + tid;
+        bool hit = false;
+        if (p < NPAIR) {
+            const int A = c_pair_a[p], B = c_pair_b[p];
+            if (B < nbody) {
+                const double *BA = s_body + A * BODY_DOUBLES, *BB = s_body + B * BODY_DOUBLES;
+                const double slack = P.tmax + 1e-9;
+                if (BA[4] <= BB[5] + slack && BB[4] <= BA[5] + slack && BA[6] <= BB[7] + slack && BB[6] <= BA[7] + slack) {
+                    const int nfa = (A == 0) ? 1 : P.shapes[s_shape[A - 1]].n_faces;
+                    const int nfb = P.shapes[s_shape[B - 1]].n_faces;
+                    const double dmin = fmin(BA[3], BB[3]);
+                    for (int fa = 0; fa < nfa && !hit; fa++) {
+                        const double *FA = s_face + (A * NF + fa) * FACE_DOUBLES;
+                        const double nx = FA[0], nz = FA[1], cx = FA[2], cz = FA[3];
+                        const double tx = nz, tz = -nx;
+                        const double sa0 = dadd(dmul(dsub(FA[4], cx), tx), dmul(dsub(FA[5], cz), tz));
+                        const double sa1 = dadd(dmul(dsub(FA[6], cx), tx), dmul(dsub(FA[7], cz), tz));
+                        const double alo = fmin(sa0, sa1), ahi = fmax(sa0, sa1);
+                        for (int fb = 0; fb < nfb; fb++) {
+                            const double *FB = s_face + (B * NF + fb) * FACE_DOUBLES;
+                            if (dadd(dmul(nx, FB[0]), dmul(nz, FB[1])) >= 0.0) continue;
+                            const double d0 = dadd(dmul(dsub(FB[4], cx), nx), dmul(dsub(FB[5], cz), nz));
+                            const double d1 = dadd(dmul(dsub(FB[6], cx), nx), dmul(dsub(FB[7], cz), nz));
+                            if (fabs(d0) > P.tmax || fabs(d1) > P.tmax) continue;
+                            const double sb0 = dadd(dmul(dsub(FB[4], cx), tx), dmul(dsub(FB[5], cz), tz));
+                            const double sb1 = dadd(dmul(dsub(FB[6], cx), tx), dmul(dsub(FB[7], cz), tz));
+                            const double lo = fmax(alo, fmin(sb0, sb1));
+                            const double hi = fmin(ahi, fmax(sb0, sb1));
+                            const double size = dmul(dsub(hi, lo), dmin);
+                            if (!(size >= P.amin)) continue;
+                            s_pair_lohi[2 * p] = lo;
+                            s_pair_lohi[2 * p + 1] = hi;
+                            s_pair_faces[p] = (uint16_t)(fa * 8 + fb);
+                            hit = true;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (lane == 0) sh_cnt[r][warp] = __popc(bal);
+        if (hit) hitmask |= (1u << r) | ((unsigned)__popc(bal & ((1u << lane) - 1)) << (8 + 8 * r));
+    }
+    {   // torque scale: largest shape radius among the blocks
+        double rad = 0.0;
+        if (tid < n) rad = P.shapes[s_shape[tid]].radius;
+        rad = warp_max(rad);
+        if (warp == 0 && lane == 0) sh_L0 = rad;
+    }
+    __syncthreads();
+    const double invL0 = 1.0 / fmax(sh_L0, 1e-300);
+    int nitf = 0;
+    for (int r = 0; r < 3; r++) nitf += sh_cnt[r][0] + sh_cnt[r][1];
+    const bool overflow = nitf > P.max_itf;
+    const int nc = overflow ? 0 : 2 * nitf;
+    // contacts are written in pair order; the scratch (faces / pairs) is read here and dead afterwards
+    if (!overflow) {
+        int base = 0;
+        for (int r = 0; r < 3; r++) {
+            if (hitmask & (1u << r)) {
+                const int p = r * 64 + tid;
+                const int idx = base + (warp == 1 ? sh_cnt[r][0] : 0) + (int)((hitmask >> (8 + 8 * r)) & 0xff);
+                const int A = c_pair_a[p], B = c_pair_b[p];
+                const int fa = s_pair_faces[p] >> 3, fb = s_pair_faces[p] & 7;
+                const double *FA = s_face + (A * NF + fa) * FACE_DOUBLES;
+                const double nx = FA[0], nz = FA[1], cx = FA[2], cz = FA[3];
+                const double tx = nz, tz = -nx;
+                const double lohi[2] = {s_pair_lohi[2 * p], s_pair_lohi[2 * p + 1]};
+                double pxs[2], pzs[2];
+                for (int q = 0; q < 2; q++) {
+                    const double px = dadd(cx, dmul(lohi[q], tx)), pz = dadd(cz, dmul(lohi[q], tz));
+                    pxs[q] = px; pzs[q] = pz;
+                    const int c = 2 * idx + q;
+                    s_ca[c] = (uint8_t)A;
+                    s_cb[c] = (uint8_t)B;
+                    double *Gc = s_G + c * 12;
+                    const double *BA = s_body + A * BODY_DOUBLES, *BB = s_body + B * BODY_DOUBLES;
+                    double rx = px - BA[0], rz = pz - BA[1];
+                    Gc[0] = -nx; Gc[1] = -nz; Gc[2] = -(rx * nz - rz * nx) * invL0;
+                    Gc[3] = -tx; Gc[4] = -tz; Gc[5] = -(rx * tz - rz * tx) * invL0;
+                    rx = px - BB[0]; rz = pz - BB[1];
+                    Gc[6] = nx; Gc[7] = nz; Gc[8] = (rx * nz - rz * nx) * invL0;
+                    Gc[9] = tx; Gc[10] = tz; Gc[11] = (rx * tz - rz * tx) * invL0;
+                }
+                if (save_itf != nullptr && idx < BW_MAX_INTERFACES) {
+                    bw_interface &I = save_itf[(size_t)e * BW_MAX_INTERFACES + idx];
+                    I.body_a = A - 1; I.body_b = B - 1; I.face_a = fa; I.face_b = fb;
+                    I.nx = nx; I.nz = nz;
+                    I.p0x = pxs[0]; I.p0z = pzs[0]; I.p1x = pxs[1]; I.p1z = pzs[1];
+                    I.fn0 = I.ft0 = I.fn1 = I.ft1 = 0.0;
+                }
+            }
+            base += sh_cnt[r][0] + sh_cnt[r][1];
+        }
+    }
+    if (save_nitf != nullptr && tid == 0) save_nitf[e] = nitf;
+    __syncthreads();
+
+    // adjacency lists body -> contacts (deterministic order)
+    if (tid == 0) {
+        int acc = 0;
+        // counts first
+        uint8_t cnt[NBODY];
+        for (int b = 0; b < NBODY; b++) cnt[b] = 0;
+        for (int c = 0; c < nc; c++) { cnt[s_ca[c]]++; cnt[s_cb[c]]++; }
+        for (int b = 0; b < NBODY; b++) { s_adj_ptr[b] = (uint8_t)acc; acc += cnt[b]; }
+        s_adj_ptr[NBODY] = (uint8_t)acc;
+    }
+    __syncthreads();
+    if (tid < nbody) {
+        int w = s_adj_ptr[tid];
+        for (int c = 0; c < nc; c++) {
+            if (s_ca[c] == tid) s_adj[w++] = (uint8_t)c;
+            else if (s_cb[c] == tid) s_adj[w++] = (uint8_t)(c | 0x80);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: two equilibrium problems, one warp each
+    uint32_t smask = P.static_mask[e];
+    if (placed) {
+        if (n >= 2) smask &= ~(1u << (n - 2));   // unfreeze_block(n-2), gym_env.py:235-236
+        smask |= 1u << (n - 1);                  // action.frozen = True; freeze_block(n-1)
+    }
+    {
+        const uint32_t vmask = (warp == 0) ? smask : (n > 0 ? (smask & ~(1u << (n - 1))) : smask);
+        const ProbOff po = prob_layout(L.MM, L.MC, L.HS);
+        unsigned char *pb = smem + L.prob[warp];
+        Solver S;
+        S.G = s_G; S.c_a = s_ca; S.c_b = s_cb; S.adj_ptr = s_adj_ptr; S.adj = s_adj;
+        S.y = reinterpret_cast<double *>(pb + po.y);
+        S.yk = reinterpret_cast<double *>(pb + po.yk);
+        S.rhs = reinterpret_cast<double *>(pb + po.rhs);
+        S.d = reinterpret_cast<double *>(pb + po.d);
+        S.b = reinterpret_cast<double *>(pb + po.b);
+        S.g = reinterpret_cast<double *>(pb + po.g);
+        S.h = reinterpret_cast<double *>(pb + po.h);
+        S.f = reinterpret_cast<double *>(pb + po.f);
+        S.invd = reinterpret_cast<double *>(pb + po.invd);
+        S.H = reinterpret_cast<double *>(pb + po.H);
+        S.typ = pb + po.typ;
+        S.rowbase = reinterpret_cast<int8_t *>(pb + po.rowbase);
+        S.freebody = pb + po.freebody;
+        S.lane = lane;
+        S.nc = nc;
+        S.mu = P.mu[e];
+        S.inv_den = 1.0 / (1.0 + S.mu * S.mu);
+        // free blocks -> rows
+        const bool is_free = (lane < n) && !((vmask >> lane) & 1u);
+        const unsigned fb = __ballot_sync(FULL, is_free);
+        const int nfree = __popc(fb);
+        const int myrow = __popc(fb & ((1u << lane) - 1));
+        if (lane == 0) S.rowbase[0] = -1;
+        if (lane < n) S.rowbase[lane + 1] = is_free ? (int8_t)(3 * myrow) : (int8_t)-1;
+        if (is_free) S.freebody[myrow] = (uint8_t)(lane + 1);
+        S.nfree = nfree;
+        S.m = 3 * nfree;
+        double w = is_free ? s_body[(lane + 1) * BODY_DOUBLES + 2] : 0.0;
+        const double nb = sqrt(warp_sum(w * w));
+        __syncwarp();
+        if (is_free) {
+            S.b[3 * myrow] = 0.0;
+            S.b[3 * myrow + 1] = w / nb;
+            S.b[3 * myrow + 2] = 0.0;
+        }
+        __syncwarp();
+        int stable, status = 0, iters = 0;
+        double res = 0.0;
+        if (overflow) {
+            stable = 0; status = 2; res = 1.0;
+        } else if (nitf == 0) {
+            stable = (nfree == 0);                // stability.py:53-56
+            res = stable ? 0.0 : 1.0;
+        } else if (nfree == 0) {
+            stable = 1;
+        } else {
+            status = S.solve(res, iters);
+            stable = (status != 2) && (res <= P.stable_tol);
+        }
+        if (lane == 0) {
+            sh_res[warp] = res; sh_status[warp] = status; sh_iters[warp] = iters; sh_stable[warp] = stable;
+        }
+        if (save_itf != nullptr && warp == save_variant && !overflow && nitf > 0 && nfree > 0) {
+            // physical forces: f = P_K(A^T y) * ||weights||   (f[] holds the projection of the last residual())
+            for (int c = lane; c < nc; c += 32) {
+                bw_interface &I = save_itf[(size_t)e * BW_MAX_INTERFACES + (c >> 1)];
+                if (c & 1) { I.fn1 = S.f[2 * c] * nb; I.ft1 = S.f[2 * c + 1] * nb; }
+                else { I.fn0 = S.f[2 * c] * nb; I.ft0 = S.f[2 * c + 1] * nb; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 4: bookkeeping (thread 0)
+    TaskDev *task = P.task + e;
+    const int stable_frozen = sh_stable[0], stable_unfrozen = sh_stable[1];
+    if (tid == 0) {
+        bw_step_out o;
+        memset(&o, 0, sizeof(o));
+        TaskDev tk = *task;
+        if (placed) {
+            // _update_targets (gym_env.py:162-168): AABB test, removal while iterating
+            const double *B = s_body + n * BODY_DOUBLES;
+            const double tol = 1e-6;
+            int idx = 0;
+            while (idx < tk.n_remaining) {
+                const int t = tk.remaining[idx];
+                idx++;
+                const double px = tk.target_xz[t][0], pz = tk.target_xz[t][1];
+                if (dsub(B[4], tol) <= px && px <= dadd(B[5], tol) && dsub(B[6], tol) <= pz && pz <= dadd(B[7], tol) &&
+                    -0.5 * B[3] - tol <= 0.0 && 0.0 <= 0.5 * B[3] + tol) {
+                    tk.reached[tk.n_reached++] = (int8_t)t;
+                    // list.remove(target): first entry with equal coordinates
+                    int k = 0;
+                    for (; k < tk.n_remaining; k++) {
+                        const int u = tk.remaining[k];
+                        if (tk.target_xz[u][0] == px && tk.target_xz[u][1] == pz) break;
+                    }
+                    for (int q = k; q + 1 < tk.n_remaining; q++) tk.remaining[q] = tk.remaining[q + 1];
+                    tk.n_remaining--;
+                }
+            }
+            // block_graph occupancy (gym_env.py:224-232)
+            uint8_t *occ = P.face_occ + (size_t)e * NB;
+            if (act.target_block >= 0) occ[act.target_block] |= (uint8_t)(1u << act.target_face);
+            occ[n - 1] = (uint8_t)(1u << act.face);
+            *task = tk;
+            P.n_blocks[e] = n;
+            P.pose[(size_t)e * NB + (n - 1)] = s_pose[n - 1];
+            P.shape_of[(size_t)e * NB + (n - 1)] = s_shape[n - 1];
+            P.static_mask[e] = smask;
+        }
+        // distance_to_targets (gym_env.py:154-160, geometry.py:89-105)
+        for (int t = 0; t < tk.n_targets; t++) {
+            double best = INFINITY;
+            const double px = tk.target_xz[t][0], pz = tk.target_xz[t][1];
+            for (int j = 1; j <= n; j++) {
+                const double *B = s_body + j * BODY_DOUBLES;
+                const double tol = 1e-6;
+                double dist;
+                if (dsub(B[4], tol) <= px && px <= dadd(B[5], tol) && dsub(B[6], tol) <= pz && pz <= dadd(B[7], tol)) {
+                    dist = 0.0;
+                } else {
+                    const double qx = fmin(fmax(px, B[4]), B[5]), qz = fmin(fmax(pz, B[6]), B[7]);
+                    const double dx = dsub(px, qx), dz = dsub(pz, qz);
+                    dist = sqrt(dadd(dmul(dx, dx), dmul(dz, dz)));
+                }
+                best = fmin(best, dist);
+            }
+            o.distance_to_targets[t] = best;
+        }
+        o.stable = (uint8_t)stable_frozen;
+        o.stable_unfrozen = (uint8_t)stable_unfrozen;
+        o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0));
+        o.residual = sh_res[0];
+        o.residual_unfrozen = sh_res[1];
+        o.newton_iters = sh_iters[0] + sh_iters[1];
+        o.n_blocks = n;
+        o.n_interfaces = nitf;
+        o.n_targets_reached = (uint8_t)tk.n_reached;
+        o.error = overflow ? 2 : 0;
+        const bool all_reached = tk.n_remaining == 0;
+        o.terminated = (uint8_t)(!stable_frozen || all_reached);
+        o.truncated = (uint8_t)(P.max_steps > 0 && n >= P.max_steps);
+        if (!stable_frozen) o.reward = -1.0f;
+        else if (!all_reached) o.reward = (float)(-1 + tk.n_reached);
+        else o.reward = (float)tk.n_reached;
+        out[e] = o;   // lin_reward is patched below
+        if (placed) P.done[e] = (uint8_t)(o.terminated | o.truncated);
+    }
+
+    // ---------------- phase 5: raster update of the new block, one thread per image row
+    if (placed) {
+        double lin = 0.0;
+        const int row = tid;
+        const uint64_t bits = raster_row(P, P.shapes[s_shape[n - 1]], s_pose[n - 1], row);
+        if (bits) {
+            P.block_bits[(size_t)e * IMG + row] |= bits;
+            const float *rw = P.reward_img + (size_t)e * IMG * IMG + row * IMG;
+            uint64_t bb = bits;
+            while (bb) {
+                const int j = __ffsll((long long)bb) - 1;
+                bb &= bb - 1;
+                lin += (double)rw[j];
+            }
+        }
+        lin = warp_sum(lin);
+        if (lane == 0) sh_lin[warp] = lin;
+        __syncthreads();
+        if (tid == 0) {
+            // successor_dqn.py:397-401
+            const float s = (float)(sh_lin[0] + sh_lin[1]);
+            float lr = 0.0f;
+            if (stable_frozen) lr = s / 100.0f;
+            if (stable_unfrozen) lr = s;
+            out[e].lin_reward = lr;
+        }
+    }
+    if (tid == 0) P.last_out[e] = out[e];
+}
+
+void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
+                 bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes, cudaStream_t stream) {
+    step_kernel<<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_itf, d_nitf, variant);
+}
+
+cudaError_t configure_step(int smem_bytes) {
+    return cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
+}  // namespace bw

@@ -1,0 +1,167 @@
+"""ctypes binding of libbridges_b200.so (C ABI: include/bridges_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `csrc/Makefile`.  Loading fails
+loudly when it is missing: there is no CPU implementation behind this package.
+"""
+import ctypes as C
+import os
+
+BW_MAX_BLOCKS = 16
+BW_MAX_FACES = 6
+BW_MAX_VERTS = 6
+BW_MAX_SHAPES = 8
+BW_MAX_OBSTACLES = 8
+BW_MAX_TARGETS = 4
+BW_MAX_INTERFACES = 48
+BW_IMG = 64
+BW_ABI_VERSION = 1
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbridges_b200.so")
+
+
+class bw_config(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("max_steps", C.c_int32), ("reserved0", C.c_int32),
+                ("xlim", C.c_double * 2), ("ylim", C.c_double * 2),
+                ("floor_halfwidth", C.c_double), ("floor_depth", C.c_double),
+                ("mu", C.c_double), ("density", C.c_double), ("tmax", C.c_double), ("amin", C.c_double),
+                ("stable_tol", C.c_double), ("stream", C.c_void_p)]
+
+
+class bw_shape_desc(C.Structure):
+    _fields_ = [("n_faces", C.c_int32), ("n_verts", C.c_int32),
+                ("target_faces_mask", C.c_uint32), ("receiving_faces_mask", C.c_uint32),
+                ("face_nx", C.c_double * BW_MAX_FACES), ("face_nz", C.c_double * BW_MAX_FACES),
+                ("face_cx", C.c_double * BW_MAX_FACES), ("face_cz", C.c_double * BW_MAX_FACES),
+                ("end0_x", C.c_double * BW_MAX_FACES), ("end0_z", C.c_double * BW_MAX_FACES),
+                ("end1_x", C.c_double * BW_MAX_FACES), ("end1_z", C.c_double * BW_MAX_FACES),
+                ("vert_x", C.c_double * BW_MAX_VERTS), ("vert_z", C.c_double * BW_MAX_VERTS),
+                ("com_x", C.c_double), ("com_z", C.c_double), ("area", C.c_double), ("depth", C.c_double)]
+
+
+class bw_action(C.Structure):
+    _fields_ = [("target_block", C.c_int32), ("target_face", C.c_int32), ("shape", C.c_int32), ("face", C.c_int32),
+                ("offset_x", C.c_double), ("offset_y", C.c_double), ("frozen", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class bw_block(C.Structure):
+    _fields_ = [("x", C.c_double), ("z", C.c_double), ("c", C.c_double), ("s", C.c_double),
+                ("shape", C.c_int32), ("is_static", C.c_int32)]
+
+
+class bw_task(C.Structure):
+    _fields_ = [("n_obstacles", C.c_int32), ("n_targets", C.c_int32), ("n_blocks", C.c_int32), ("reserved0", C.c_int32),
+                ("obstacle_xz", (C.c_double * 2) * BW_MAX_OBSTACLES),
+                ("target_xz", (C.c_double * 2) * BW_MAX_TARGETS),
+                ("blocks", bw_block * BW_MAX_BLOCKS)]
+
+
+class bw_step_out(C.Structure):
+    _fields_ = [("residual", C.c_double), ("residual_unfrozen", C.c_double),
+                ("distance_to_targets", C.c_double * BW_MAX_TARGETS),
+                ("reward", C.c_float), ("lin_reward", C.c_float),
+                ("n_blocks", C.c_int32), ("n_interfaces", C.c_int32), ("newton_iters", C.c_int32),
+                ("reserved0", C.c_int32),
+                ("stable", C.c_uint8), ("stable_unfrozen", C.c_uint8), ("collision", C.c_uint8),
+                ("collision_block", C.c_uint8), ("collision_obstacle", C.c_uint8), ("collision_floor", C.c_uint8),
+                ("collision_boundary", C.c_uint8), ("terminated", C.c_uint8), ("truncated", C.c_uint8),
+                ("solver_status", C.c_uint8), ("error", C.c_uint8), ("n_targets_reached", C.c_uint8),
+                ("reserved1", C.c_uint8 * 4)]
+
+
+class bw_interface(C.Structure):
+    _fields_ = [("body_a", C.c_int32), ("body_b", C.c_int32), ("face_a", C.c_int32), ("face_b", C.c_int32),
+                ("nx", C.c_double), ("nz", C.c_double),
+                ("p0x", C.c_double), ("p0z", C.c_double), ("p1x", C.c_double), ("p1z", C.c_double),
+                ("fn0", C.c_double), ("ft0", C.c_double), ("fn1", C.c_double), ("ft1", C.c_double)]
+
+
+# numpy views of the same layouts (for bulk transfers)
+def np_dtypes():
+    import numpy as np
+    action = np.dtype([("target_block", "<i4"), ("target_face", "<i4"), ("shape", "<i4"), ("face", "<i4"),
+                       ("offset_x", "<f8"), ("offset_y", "<f8"), ("frozen", "<i4"), ("reserved0", "<i4")])
+    step_out = np.dtype([("residual", "<f8"), ("residual_unfrozen", "<f8"),
+                         ("distance_to_targets", "<f8", (BW_MAX_TARGETS,)),
+                         ("reward", "<f4"), ("lin_reward", "<f4"),
+                         ("n_blocks", "<i4"), ("n_interfaces", "<i4"), ("newton_iters", "<i4"), ("reserved0", "<i4"),
+                         ("stable", "u1"), ("stable_unfrozen", "u1"), ("collision", "u1"), ("collision_block", "u1"),
+                         ("collision_obstacle", "u1"), ("collision_floor", "u1"), ("collision_boundary", "u1"),
+                         ("terminated", "u1"), ("truncated", "u1"), ("solver_status", "u1"), ("error", "u1"),
+                         ("n_targets_reached", "u1"), ("reserved1", "u1", (4,))])
+    block = np.dtype([("x", "<f8"), ("z", "<f8"), ("c", "<f8"), ("s", "<f8"), ("shape", "<i4"), ("is_static", "<i4")])
+    task = np.dtype([("n_obstacles", "<i4"), ("n_targets", "<i4"), ("n_blocks", "<i4"), ("reserved0", "<i4"),
+                     ("obstacle_xz", "<f8", (BW_MAX_OBSTACLES, 2)), ("target_xz", "<f8", (BW_MAX_TARGETS, 2)),
+                     ("blocks", block, (BW_MAX_BLOCKS,))])
+    interface = np.dtype([("body_a", "<i4"), ("body_b", "<i4"), ("face_a", "<i4"), ("face_b", "<i4"),
+                          ("nx", "<f8"), ("nz", "<f8"), ("p0x", "<f8"), ("p0z", "<f8"), ("p1x", "<f8"),
+                          ("p1z", "<f8"), ("fn0", "<f8"), ("ft0", "<f8"), ("fn1", "<f8"), ("ft1", "<f8")])
+    assert action.itemsize == C.sizeof(bw_action) and step_out.itemsize == C.sizeof(bw_step_out)
+    assert block.itemsize == C.sizeof(bw_block) and task.itemsize == C.sizeof(bw_task)
+    assert interface.itemsize == C.sizeof(bw_interface)
+    return dict(action=action, step_out=step_out, block=block, task=task, interface=interface)
+
+
+# every symbol include/bridges_b200.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+_P = C.c_void_p
+SIGNATURES = {
+    "bw_abi_version": (C.c_int, []),
+    "bw_create": (C.c_int, [C.POINTER(bw_config), C.POINTER(_H)]),
+    "bw_destroy": (None, [_H]),
+    "bw_last_error": (C.c_char_p, [_H]),
+    "bw_config_default": (None, [C.POINTER(bw_config)]),
+    "bw_sync": (C.c_int, [_H]),
+    "bw_load_shapes": (C.c_int, [_H, C.POINTER(bw_shape_desc), C.c_int32]),
+    "bw_set_marker_shape": (C.c_int, [_H, C.POINTER(bw_shape_desc)]),
+    "bw_set_task_kernel": (C.c_int, [_H, _P, C.c_int32]),
+    "bw_set_mu": (C.c_int, [_H, _P]),
+    "bw_reset": (C.c_int, [_H, _P, _P]),
+    "bw_reset_host": (C.c_int, [_H, _P, _P]),
+    "bw_reset_done": (C.c_int, [_H]),
+    "bw_step": (C.c_int, [_H, _P, _P, _P, _P, _P]),
+    "bw_step_host": (C.c_int, [_H, _P, _P, _P, _P, _P]),
+    "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),
+    "bw_observe_host": (C.c_int, [_H, _P, _P, _P, _P]),
+    "bw_enumerate_actions": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "bw_expand_bits": (C.c_int, [_H, _P, C.c_int64, _P]),
+    "bw_select_random": (C.c_int, [_H, _P, _P, _P, C.c_int32, C.c_uint64, _P, _P]),
+    "bw_get_state": (C.c_int, [_H, _P, _P]),
+    "bw_get_raster_bits": (C.c_int, [_H, _P, _P]),
+    "bw_get_forces": (C.c_int, [_H, C.c_int32, _P, _P]),
+    "bw_set_static_mask": (C.c_int, [_H, _P]),
+    "bw_set_timing": (C.c_int, [_H, C.c_int32]),
+    "bw_last_step_kernel_ms": (C.c_int, [_H, _P]),
+    "bw_kernel_launches": (C.c_int64, [_H]),
+}
+
+_lib = None
+
+
+class BridgesError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BridgesError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(bridges_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bw_abi_version() != BW_ABI_VERSION:
+        raise BridgesError("libbridges_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, rc):
+    if rc != 0:
+        msg = lib.bw_last_error(handle)
+        raise BridgesError(f"bridges_b200 error {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,235 @@
+/*
+ * bridges_b200 -- C ABI of the B200-native batched assembly_gym environment step.
+ *
+ * The reference (syghmon/bridges-with-reinforcement-learning) has no FFI boundary: its
+ * boundary is the Python object API of
+ *     assembly_gym/assembly_gym/envs/gym_env.py      (AssemblyGym, Action)
+ *     assembly_gym/assembly_gym/envs/assembly_env.py (AssemblyEnv, Shape, Block)
+ *     assembly_gym/assembly_gym/utils/rendering.py   (render_blocks_2d)
+ *     robotoddler/utils/actions.py                   (generate_actions, filter_actions)
+ * Each entry point below names the reference interface it replaces (file:line relative
+ * to the reference root).  The Python adapter in bridges_b200/ binds these with ctypes
+ * (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns BW_OK (0) or a negative bw_status;
+ *     bw_last_error() gives the message of the last failure on that handle.
+ *   - one handle per GPU; a handle is not thread-safe, distinct handles are independent.
+ *   - pointers named d_* are DEVICE pointers owned by the caller; pointers named h_* are
+ *     HOST pointers.  All work is enqueued on the handle's stream; calls with d_* arguments
+ *     only are asynchronous, calls with h_* arguments return after their copies completed.
+ *   - lengths: E = number of lock-step environments of the handle.
+ *   - all geometry is float64; observation tensors are float32 (what the Q-network eats).
+ */
+#ifndef BRIDGES_B200_H
+#define BRIDGES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BW_ABI_VERSION 1
+
+/* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
+#define BW_MAX_BLOCKS 16
+#define BW_MAX_FACES 6      /* 2-D faces per shape (hexagon) */
+#define BW_MAX_VERTS 6
+#define BW_MAX_SHAPES 8
+#define BW_MAX_OBSTACLES 8
+#define BW_MAX_TARGETS 4
+#define BW_MAX_INTERFACES 48
+#define BW_IMG 64           /* observation rasters are BW_IMG x BW_IMG (successor_dqn.py:585) */
+
+typedef enum {
+    BW_OK = 0,
+    BW_ERR_INVALID = -1,   /* bad argument */
+    BW_ERR_CUDA = -2,      /* CUDA runtime failure (message has the CUDA error string) */
+    BW_ERR_CAPACITY = -3,  /* a compile-time capacity above would be exceeded */
+    BW_ERR_STATE = -4      /* call order (e.g. step before load_shapes) */
+} bw_status;
+
+typedef struct bw_handle bw_handle;
+
+/* Constructor arguments of AssemblyEnv (assembly_env.py:164) and AssemblyGym (gym_env.py:116)
+ * plus the raster window of the training script (successor_dqn.py:615-616). */
+typedef struct {
+    int32_t num_envs;
+    int32_t device;          /* CUDA device ordinal */
+    int32_t max_steps;       /* AssemblyGym(max_steps); 0 = None */
+    int32_t reserved0;
+    double xlim[2];          /* raster / bounds window in x (default -3, 7) */
+    double ylim[2];          /* raster / bounds window in z (default 0, 10) */
+    double floor_halfwidth;  /* support Box half width: 0.5*(bounds[1][0]-bounds[0][0]) = 5 (assembly_env.py:290) */
+    double floor_depth;      /* bounds[1][1]-bounds[0][1] = 10 */
+    double mu;               /* friction coefficient, default 0.8 */
+    double density;          /* default 1.0 */
+    double tmax;             /* interface coplanarity tolerance (compas_cra default 1e-6) */
+    double amin;             /* minimum interface area, 0.001 (assembly_env.py:304) */
+    double stable_tol;       /* verdict threshold on the relative equilibrium residual, default 1e-6 */
+    void *stream;            /* cudaStream_t to enqueue on; NULL = the library creates one */
+} bw_config;
+
+/* One entry of the block library: what Shape.from_urdf (assembly_env.py:54-68) extracts,
+ * reduced to the xz-plane.  Face k is the reference's 2-D face index k (Action.face). */
+typedef struct {
+    int32_t n_faces;
+    int32_t n_verts;
+    uint32_t target_faces_mask;     /* Shape.target_faces_2d as a bit mask (bit k = face k) */
+    uint32_t receiving_faces_mask;  /* Shape.receiving_faces_2d (kept for completeness; placed
+                                       blocks offer all faces, assembly_env.py:153) */
+    double face_nx[BW_MAX_FACES], face_nz[BW_MAX_FACES];   /* outward unit normals */
+    double face_cx[BW_MAX_FACES], face_cz[BW_MAX_FACES];   /* face centres */
+    double end0_x[BW_MAX_FACES], end0_z[BW_MAX_FACES];     /* face end points */
+    double end1_x[BW_MAX_FACES], end1_z[BW_MAX_FACES];
+    double vert_x[BW_MAX_VERTS], vert_z[BW_MAX_VERTS];     /* polygon (Shape.vertices_2d order) */
+    double com_x, com_z;            /* area centroid = centre of mass of the prism */
+    double area;                    /* polygon area; weight = density*area*depth */
+    double depth;                   /* extent along y */
+} bw_shape_desc;
+
+/* Action dataclass, gym_env.py:102-110 */
+typedef struct {
+    int32_t target_block;   /* -1 = floor */
+    int32_t target_face;
+    int32_t shape;          /* -1 = no placement (evaluate the current assembly only) */
+    int32_t face;
+    double offset_x;
+    double offset_y;
+    int32_t frozen;         /* ignored by step (forced True, gym_env.py:238) */
+    int32_t reserved0;
+} bw_action;
+
+/* A posed block: canonical pose (x, z, cos, sin) of DESIGN.md section 4 */
+typedef struct {
+    double x, z, c, s;
+    int32_t shape;
+    int32_t is_static;
+} bw_block;
+
+/* Arguments of AssemblyGym.reset (gym_env.py:255-289) for one environment */
+typedef struct {
+    int32_t n_obstacles, n_targets, n_blocks, reserved0;
+    double obstacle_xz[BW_MAX_OBSTACLES][2];
+    double target_xz[BW_MAX_TARGETS][2];
+    bw_block blocks[BW_MAX_BLOCKS];     /* pre-placed blocks (reset(blocks=...)) */
+} bw_task;
+
+/* What AssemblyGym.step returns besides the images (gym_env.py:218-253) plus the pair
+ * returned by stabilities_freezing (gym_env.py:325-333) */
+typedef struct {
+    double residual;              /* relative equilibrium residual r of the frozen solve (verdict margin) */
+    double residual_unfrozen;     /* same, nothing frozen */
+    double distance_to_targets[BW_MAX_TARGETS];   /* gym_env.py:154-160 (inf when no block) */
+    float reward;                 /* sparse_reward, gym_env.py:11-22 */
+    float lin_reward;             /* successor_dqn.py:397-401 (uses the reward image rendered by reset) */
+    int32_t n_blocks;
+    int32_t n_interfaces;
+    int32_t newton_iters;         /* Newton steps of both solves */
+    int32_t reserved0;
+    uint8_t stable;               /* obs['stable']: verdict with only the new block frozen */
+    uint8_t stable_unfrozen;      /* stabilities_freezing()[1]: last block released */
+    uint8_t collision;            /* constant 0 without PyBullet (assembly_env.py:310-312) */
+    uint8_t collision_block, collision_obstacle, collision_floor, collision_boundary;
+    uint8_t terminated;           /* gym_env.py:141-144 */
+    uint8_t truncated;            /* max_steps reached */
+    uint8_t solver_status;        /* bit0 / bit1: frozen / unfrozen solve did not converge (stable=None) */
+    uint8_t error;                /* 1 = invalid action indices, 2 = capacity exceeded */
+    uint8_t n_targets_reached;
+    uint8_t reserved1[4];
+} bw_step_out;
+
+/* One contact interface with its two contact points and their forces (bw_get_forces) */
+typedef struct {
+    int32_t body_a, body_b;       /* -1 = floor; a < b */
+    int32_t face_a, face_b;
+    double nx, nz;                /* contact normal = outward normal of a's face */
+    double p0x, p0z, p1x, p1z;    /* contact points */
+    double fn0, ft0, fn1, ft1;    /* min-norm equilibrium forces acting on b at p0 / p1 */
+} bw_interface;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int bw_abi_version(void);
+/* AssemblyEnv(...) + AssemblyGym(...) constructors */
+int bw_create(const bw_config *cfg, bw_handle **out);
+void bw_destroy(bw_handle *h);
+const char *bw_last_error(const bw_handle *h);
+void bw_config_default(bw_config *cfg);
+/* cudaStreamSynchronize on the handle's stream */
+int bw_sync(bw_handle *h);
+/* AssemblyGym.shapes: the library the Action.shape index refers to (host pointer) */
+int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n);
+/* the 0.6 cube drawn for obstacles and target markers (Shape('shapes/cube06.urdf'),
+ * gym_env.py:277, successor_dqn.py:73); default: an exact 0.6 x 0.6 axis-aligned box */
+int bw_set_marker_shape(bw_handle *h, const bw_shape_desc *h_shape);
+/* normalised 1-D Gaussian (101 float32 taps) of get_task_features / convolve_with_gaussian
+ * (successor_dqn.py:78-80, robotoddler/utils/utils.py:93-114); default: sigma 16 */
+int bw_set_task_kernel(bw_handle *h, const float *h_kernel1d, int32_t n);
+/* per-environment friction coefficient (AssemblyEnv.mu); host array of E doubles */
+int bw_set_mu(bw_handle *h, const double *h_mu);
+
+/* ---- reset: AssemblyGym.reset, gym_env.py:255-289 ---------------------------------------
+ * d_tasks: E tasks, or NULL to keep every env's obstacles/targets and only clear its blocks.
+ * d_mask:  E bytes, env e is reset iff d_mask[e] != 0; NULL = all.
+ * Also renders the obstacle raster and the Gaussian-blurred target raster
+ * (get_task_features, successor_dqn.py:67-85). */
+int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask);
+int bw_reset_host(bw_handle *h, const bw_task *h_tasks, const uint8_t *h_mask);
+/* reset exactly the envs whose last step returned terminated|truncated (keeps their task) */
+int bw_reset_done(bw_handle *h);
+
+/* ---- step: AssemblyGym.step (gym_env.py:218-253) + stabilities_freezing (:325-333) ------
+ * d_actions[E], d_mask (NULL = all), d_out[E].  Optional observation outputs (may be NULL):
+ * d_block_img [E,1,64,64] f32 = get_state_features image (successor_dqn.py:47-64),
+ * d_binary [E,6] f32 = (stable, collision, collision_block, _obstacle, _floor, _boundary). */
+int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
+            float *d_block_img, float *d_binary);
+int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
+                 float *h_block_img, float *h_binary);
+
+/* ---- observations: _get_obs + get_state_features / get_task_features ----------------
+ * any pointer may be NULL.  Images are [E,1,64,64] f32, row 0 = top (rendering.py:105-113). */
+int bw_observe(bw_handle *h, float *d_block_img, float *d_binary, float *d_obstacle_img, float *d_reward_img);
+int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_obstacle_img, float *h_reward_img);
+
+/* ---- candidate actions: generate_actions + get_action_features + filter_actions --------
+ * (robotoddler/utils/actions.py:7-82, successor_dqn.py:88-94).  Candidates are written in
+ * the reference's generation order, Amax per env; d_n_cand[e] of them are meaningful.
+ * d_valid[e,a] = 1 iff the candidate survives filter_actions (bounds test of
+ * collision_on_action gym_env.py:304-323, no raster overlap with blocks / obstacles).
+ * d_action_bits (optional): [E,Amax,64] u64, bit x of word r = pixel (row r, col x). */
+int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
+                         const double *h_offset_values, int32_t n_offsets, int32_t amax,
+                         bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits);
+/* expand bit rasters [n,64] u64 -> [n,1,64,64] f32 */
+int bw_expand_bits(bw_handle *h, const uint64_t *d_bits, int64_t n, float *d_img);
+/* synthetic policy for benchmarks/tests: pick for every env a uniformly random valid candidate
+ * (counter-based hash of seed, env, step); envs without a valid candidate get shape = -1. */
+int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
+                     int32_t amax, uint64_t seed, bw_action *d_actions, int32_t *d_index);
+
+/* ---- state read-back (adapters, checkpointing, tests) ------------------------------ */
+int bw_get_state(bw_handle *h, bw_block *h_blocks /*[E,BW_MAX_BLOCKS]*/, int32_t *h_n_blocks /*[E]*/);
+int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits /*[E,64]*/, uint64_t *h_obstacle_bits /*[E,64]*/);
+/* interfaces and min-norm contact forces of the last step / evaluation (frozen variant) */
+/* variant 0: supports as in the last step's verdict (new block frozen); 1: last block released */
+int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf /*[E,BW_MAX_INTERFACES]*/, int32_t *h_n_itf /*[E]*/);
+/* AssemblyEnv.freeze_block / unfreeze_block (assembly_env.py:404-438): host array [E] of
+ * bit masks (bit i = block i is a support) used by the next bw_step(shape=-1) evaluation */
+int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask);
+
+/* ---- measurement helpers ------------------------------------------------------------- */
+/* bw_set_timing(h, 1) brackets every kernel of bw_step with CUDA events on the handle's
+ * stream; bw_last_step_kernel_ms then returns (after synchronising) the elapsed ms of
+ * [0] the step kernel (placement, interfaces, two solves, bookkeeping, raster update) and
+ * [1] the observation kernel (bit raster -> f32 image + binary features; 0 if not launched) */
+int bw_set_timing(bw_handle *h, int32_t enabled);
+int bw_last_step_kernel_ms(bw_handle *h, float *h_ms2);
+/* number of kernels launched by this handle so far */
+int64_t bw_kernel_launches(const bw_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIDGES_B200_H */
