@@ -125,6 +125,47 @@ void launch_enumerate(const Params &P, const double *d_ground, int n_ground, con
                                                           d_valid, d_n_cand, d_action_bits);
 }
 
+// create_block + collision_on_action for one hypothetical action per env (state untouched)
+__global__ void query_placement_kernel(Params P, const bw_action *__restrict__ actions, double xl, double xh, double zl,
+                                       double zh, bw_block *__restrict__ blocks, uint8_t *__restrict__ flags) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.E) return;
+    const bw_action act = actions[e];
+    Pose ps;
+    ps.x = ps.z = ps.s = 0.0; ps.c = 1.0;
+    const int err = place_block(P, P.pose + (size_t)e * NB, P.shape_of + (size_t)e * NB, P.n_blocks[e], act, ps);
+    uint8_t fl = 0;
+    if (err == 1) fl |= 1;
+    if (err == 2) fl |= 2;
+    if (err != 1) {
+        if (err == 2) {   // the pose of a block that does not fit any more is still well defined
+            bw_action a2 = act;
+            Params P2 = P;
+            P2.max_blocks = NB + 1;
+            place_block(P2, P.pose + (size_t)e * NB, P.shape_of + (size_t)e * NB, P.n_blocks[e], a2, ps);
+        }
+        const ShapeDev &sh = P.shapes[act.shape];
+        const double eps = 1e-6;
+        for (int v = 0; v < sh.n_verts; v++) {
+            double vx, vz;
+            rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+            vx = dadd(vx, ps.x);
+            vz = dadd(vz, ps.z);
+            if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) fl |= 4;
+        }
+    }
+    bw_block b;
+    b.x = ps.x; b.z = ps.z; b.c = ps.c; b.s = ps.s;
+    b.shape = act.shape; b.is_static = 0;
+    blocks[e] = b;
+    flags[e] = fl;
+}
+
+void launch_query_placement(const Params &P, const bw_action *d_actions, double xl, double xh, double zl, double zh,
+                            bw_block *d_blocks, uint8_t *d_flags, cudaStream_t stream) {
+    query_placement_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, d_actions, xl, xh, zl, zh, d_blocks, d_flags);
+}
+
 // splitmix64: counter-based, reproducible on the host
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

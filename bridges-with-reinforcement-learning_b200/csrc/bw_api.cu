@@ -38,6 +38,11 @@ struct bw_handle {
     bw_interface *d_itf = nullptr;
     int32_t *d_nitf = nullptr;
     double *d_ground = nullptr, *d_offsets = nullptr;
+    bw_block *d_qblocks = nullptr, *d_rblocks = nullptr;
+    uint8_t *d_qflags = nullptr;
+    ShapeDev *d_rshapes = nullptr;
+    uint64_t *d_rbits = nullptr;
+    double *d_rxs = nullptr, *d_rys = nullptr;
 };
 
 static int fail(bw_handle *h, int code, const char *fmt, ...) {
@@ -546,6 +551,93 @@ int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits, uint64_t *h_obstacl
     if (h_block_bits) CU(cudaMemcpyAsync(h_block_bits, h->P.block_bits, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (h_obstacle_bits) CU(cudaMemcpyAsync(h_obstacle_bits, h->P.obst_bits, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_get_target_state(bw_handle *h, int8_t *h_remaining, int8_t *h_reached, int32_t *h_counts) {
+    if (!h || !h_remaining || !h_reached || !h_counts) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const int E = h->P.E;
+    std::vector<TaskDev> tk(E);
+    CU(cudaMemcpyAsync(tk.data(), h->P.task, sizeof(TaskDev) * E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int e = 0; e < E; e++) {
+        for (int i = 0; i < BW_MAX_TARGETS; i++) {
+            h_remaining[e * BW_MAX_TARGETS + i] = i < tk[e].n_remaining ? tk[e].remaining[i] : (int8_t)-1;
+            h_reached[e * BW_MAX_TARGETS + i] = i < tk[e].n_reached ? tk[e].reached[i] : (int8_t)-1;
+        }
+        h_counts[2 * e] = tk[e].n_remaining;
+        h_counts[2 * e + 1] = tk[e].n_reached;
+    }
+    return BW_OK;
+}
+
+int bw_query_placement_host(bw_handle *h, const bw_action *h_actions, const double *xlim2, const double *ylim2,
+                            bw_block *h_blocks, uint8_t *h_flags) {
+    if (!h || !h_actions || !h_blocks || !h_flags) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    const int E = h->P.E;
+    if (!h->d_qblocks) {
+        CU(dev_alloc(h, &h->d_qblocks, E));
+        CU(dev_alloc(h, &h->d_qflags, E));
+    }
+    const double eps = 1e-6;
+    const double x0 = xlim2 ? xlim2[0] : h->P.xlim0, x1 = xlim2 ? xlim2[1] : h->P.xlim1;
+    const double z0 = ylim2 ? ylim2[0] : h->P.ylim0, z1 = ylim2 ? ylim2[1] : h->P.ylim1;
+    CU(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
+    launch_query_placement(h->P, h->d_actions, x0 - eps, x1 + eps, z0 - eps, z1 + eps, h->d_qblocks, h->d_qflags,
+                           h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_blocks, h->d_qblocks, sizeof(bw_block) * E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h_flags, h->d_qflags, E, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_render_blocks_host(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n_shapes, const bw_block *h_blocks,
+                          int32_t n_blocks, const double *xlim2, const double *ylim2, uint64_t *h_bits) {
+    if (!h || !h_bits || n_blocks < 0 || (n_blocks > 0 && (!h_shapes || !h_blocks))) return BW_ERR_INVALID;
+    if (n_shapes < 0 || n_shapes > BW_MAX_SHAPES) return fail(h, BW_ERR_CAPACITY, "at most %d shapes", BW_MAX_SHAPES);
+    if (n_blocks > 256) return fail(h, BW_ERR_CAPACITY, "at most 256 blocks per render call");
+    CU(cudaSetDevice(h->cfg.device));
+    if (!h->d_rshapes) {
+        CU(dev_alloc(h, &h->d_rshapes, BW_MAX_SHAPES));
+        CU(dev_alloc(h, &h->d_rblocks, 256));
+        CU(dev_alloc(h, &h->d_rbits, IMG));
+        CU(dev_alloc(h, &h->d_rxs, IMG));
+        CU(dev_alloc(h, &h->d_rys, IMG));
+    }
+    ShapeDev dev[BW_MAX_SHAPES];
+    for (int i = 0; i < n_shapes; i++) {
+        if (!shape_ok(h_shapes[i])) return fail(h, BW_ERR_INVALID, "shape %d: bad face/vertex count or mass data", i);
+        shape_to_dev(h_shapes[i], dev[i]);
+    }
+    for (int i = 0; i < n_blocks; i++)
+        if (h_blocks[i].shape < 0 || h_blocks[i].shape >= n_shapes)
+            return fail(h, BW_ERR_INVALID, "block %d: shape index out of range", i);
+    Params P = h->P;
+    if (xlim2) { P.xlim0 = xlim2[0]; P.xlim1 = xlim2[1]; }
+    if (ylim2) { P.ylim0 = ylim2[0]; P.ylim1 = ylim2[1]; }
+    if (!(P.xlim1 > P.xlim0) || !(P.ylim1 > P.ylim0)) return fail(h, BW_ERR_INVALID, "empty raster window");
+    P.inv_step_x = (double)(IMG - 1) / (P.xlim1 - P.xlim0);
+    P.inv_step_y = (double)(IMG - 1) / (P.ylim1 - P.ylim0);
+    double xs[IMG], ys[IMG];
+    np_linspace(P.xlim0, P.xlim1, IMG, xs);
+    np_linspace(P.ylim1, P.ylim0, IMG, ys);
+    CU(cudaMemcpyAsync(h->d_rxs, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_rys, ys, sizeof(ys), cudaMemcpyHostToDevice, h->stream));
+    if (n_shapes > 0)
+        CU(cudaMemcpyAsync(h->d_rshapes, dev, sizeof(ShapeDev) * n_shapes, cudaMemcpyHostToDevice, h->stream));
+    if (n_blocks > 0)
+        CU(cudaMemcpyAsync(h->d_rblocks, h_blocks, sizeof(bw_block) * n_blocks, cudaMemcpyHostToDevice, h->stream));
+    P.xs = h->d_rxs; P.ys = h->d_rys;
+    launch_render_blocks(P, h->d_rshapes, h->d_rblocks, n_blocks, h->d_rbits, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_bits, h->d_rbits, sizeof(uint64_t) * IMG, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // xs/ys/dev live on this stack frame
     return BW_OK;
 }
 

@@ -18,7 +18,12 @@ void launch_observe(const Params &P, float *d_block_img, float *d_binary, float 
                     cudaStream_t stream);
 void launch_expand_bits(const uint64_t *d_bits, int64_t n, float *d_img, cudaStream_t stream);
 
+void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_block *d_blocks, int n_blocks,
+                          uint64_t *d_bits, cudaStream_t stream);
+
 // bw_actions.cu
+void launch_query_placement(const Params &P, const bw_action *d_actions, double xl, double xh, double zl, double zh,
+                            bw_block *d_blocks, uint8_t *d_flags, cudaStream_t stream);
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       cudaStream_t stream);

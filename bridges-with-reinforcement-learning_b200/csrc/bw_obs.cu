@@ -133,6 +133,25 @@ void launch_reset(const Params &P, const bw_task *d_tasks, const uint8_t *d_mask
     reset_kernel<<<P.E, 64, 0, stream>>>(P, d_tasks, d_mask, only_done);
 }
 
+// render_blocks_2d for an explicit list of posed blocks (P.xs / P.ys give the pixel nodes)
+__global__ void __launch_bounds__(64)
+render_blocks_kernel(Params P, const ShapeDev *__restrict__ shapes, const bw_block *__restrict__ blocks, int n_blocks,
+                     uint64_t *__restrict__ bits) {
+    const int row = threadIdx.x;
+    uint64_t acc = 0;
+    for (int i = 0; i < n_blocks; i++) {
+        Pose ps;
+        ps.x = blocks[i].x; ps.z = blocks[i].z; ps.c = blocks[i].c; ps.s = blocks[i].s;
+        acc |= raster_row(P, shapes[blocks[i].shape], ps, row);
+    }
+    bits[row] = acc;
+}
+
+void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_block *d_blocks, int n_blocks,
+                          uint64_t *d_bits, cudaStream_t stream) {
+    render_blocks_kernel<<<1, 64, 0, stream>>>(P, d_shapes, d_blocks, n_blocks, d_bits);
+}
+
 // ------------------------------------------------------------------ observation tensors
 __device__ __forceinline__ float4 nibble_to_float4(uint64_t rowbits, int c4) {
     const unsigned nib = (unsigned)(rowbits >> (4 * c4)) & 0xfu;

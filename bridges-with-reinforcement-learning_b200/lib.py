@@ -128,6 +128,9 @@ SIGNATURES = {
     "bw_get_state": (C.c_int, [_H, _P, _P]),
     "bw_get_raster_bits": (C.c_int, [_H, _P, _P]),
     "bw_get_forces": (C.c_int, [_H, C.c_int32, _P, _P]),
+    "bw_get_target_state": (C.c_int, [_H, _P, _P, _P]),
+    "bw_query_placement_host": (C.c_int, [_H, _P, _P, _P, _P, _P]),
+    "bw_render_blocks_host": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "bw_set_static_mask": (C.c_int, [_H, _P]),
     "bw_set_timing": (C.c_int, [_H, C.c_int32]),
     "bw_last_step_kernel_ms": (C.c_int, [_H, _P]),

@@ -212,6 +212,20 @@ int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_val
 /* ---- state read-back (adapters, checkpointing, tests) ------------------------------ */
 int bw_get_state(bw_handle *h, bw_block *h_blocks /*[E,BW_MAX_BLOCKS]*/, int32_t *h_n_blocks /*[E]*/);
 int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits /*[E,64]*/, uint64_t *h_obstacle_bits /*[E,64]*/);
+/* targets_remaining / targets_reached of AssemblyGym (gym_env.py:162-168) as indices into the
+ * task's target list, in list order; h_counts[e] = {n_remaining, n_reached} */
+int bw_get_target_state(bw_handle *h, int8_t *h_remaining /*[E,BW_MAX_TARGETS]*/,
+                        int8_t *h_reached /*[E,BW_MAX_TARGETS]*/, int32_t *h_counts /*[E,2]*/);
+/* AssemblyGym.create_block (gym_env.py:204-216) + collision_on_action (gym_env.py:304-323)
+ * for one hypothetical action per env, without touching the state.  h_blocks[e] = posed block;
+ * h_flags[e]: bit0 invalid indices, bit1 env full, bit2 a vertex leaves xlim/ylim (+-1e-6) or
+ * dips below z = -1e-6 */
+int bw_query_placement_host(bw_handle *h, const bw_action *h_actions, const double *xlim2, const double *ylim2,
+                            bw_block *h_blocks, uint8_t *h_flags);
+/* render_blocks_2d (rendering.py:105-113) for an arbitrary list of posed blocks, 64 x 64 only:
+ * blocks[i].shape indexes h_shapes; h_bits[64], bit x of word r = pixel (row r, col x) */
+int bw_render_blocks_host(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n_shapes, const bw_block *h_blocks,
+                          int32_t n_blocks, const double *xlim2, const double *ylim2, uint64_t *h_bits);
 /* interfaces and min-norm contact forces of the last step / evaluation (frozen variant) */
 /* variant 0: supports as in the last step's verdict (new block frozen); 1: last block released */
 int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf /*[E,BW_MAX_INTERFACES]*/, int32_t *h_n_itf /*[E]*/);

@@ -97,6 +97,8 @@ class Shape:
             cz += (za + zb) * w
         self.area = abs(a2) / 2.0
         self.centroid_2d = (cx / (3.0 * a2), cz / (3.0 * a2))
+        # largest centre-of-mass -> vertex distance: length unit of the torque rows
+        self.radius = max(math.sqrt((x - self.centroid_2d[0]) ** 2 + (z - self.centroid_2d[1]) ** 2) for x, z in poly)
 
     def _vertices_2d_from_mesh(self):
         vertices = None
@@ -191,6 +193,7 @@ class Block(Shape):
         self._all_faces = shape._all_faces
         self.depth = shape.depth
         self.area = shape.area
+        self.radius = shape.radius
         self.face_normals_2d = [rot(c, s, nx, nz) for nx, nz in shape.face_normals_2d]
         self.face_centers_2d = [self._apply(p) for p in shape.face_centers_2d]
         self.face_ends_2d = [(self._apply(a), self._apply(b)) for a, b in shape.face_ends_2d]

@@ -38,7 +38,7 @@ class Interface:
 
 
 class _Body:
-    __slots__ = ("node", "normals", "centers", "ends", "depth", "com", "area", "is_support")
+    __slots__ = ("node", "normals", "centers", "ends", "depth", "com", "area", "is_support", "radius")
 
 
 def _floor_body(bounds):
@@ -55,6 +55,7 @@ def _floor_body(bounds):
     body.com = (0.0, -0.025 * width)
     body.area = width * 0.05 * width
     body.is_support = True
+    body.radius = 0.0
     return body
 
 
@@ -68,6 +69,7 @@ def _block_body(node, block):
     body.com = block.centroid_2d
     body.area = block.area
     body.is_support = bool(block.is_static)
+    body.radius = block.radius
     return body
 
 
@@ -130,11 +132,14 @@ class CRAAssembly:
 def equilibrium_system(assembly, mu, density):
     """A f = b with f = (fn_0, ft_0, fn_1, ft_1, ...) over the contact points of all
     interfaces.  Force on body b of an interface: fn*n + ft*t, on body a the opposite.
-    Rows per free block j: sum Fx = 0, sum Fz = W_j, sum (p - com_j) x F = 0,
-    W_j = density * area_j * depth_j  (weight acts along -z)."""
+    Rows per free block j: sum Fx = 0, sum Fz = W_j, sum (p - com_j) x F / L0 = 0,
+    W_j = density * area_j * depth_j  (weight acts along -z).  L0, the largest
+    centre-of-mass -> vertex distance among the blocks, makes the torque rows
+    commensurable with the force rows (it only matters for the residual r*)."""
     free = assembly.free_nodes()
     row_of = {node: 3 * k for k, node in enumerate(free)}
     ncp = 2 * len(assembly.interfaces)
+    L0 = max([body.radius for body in assembly.bodies] + [1e-300])
     A = np.zeros((3 * len(free), 2 * ncp))
     b = np.zeros(3 * len(free))
     for node in free:
@@ -152,10 +157,10 @@ def equilibrium_system(assembly, mu, density):
                     rx, rz = px - gx, pz - gz
                     A[r + 0, col] = sign * nx
                     A[r + 1, col] = sign * nz
-                    A[r + 2, col] = sign * (rx * nz - rz * nx)
+                    A[r + 2, col] = sign * (rx * nz - rz * nx) / L0
                     A[r + 0, col + 1] = sign * tx
                     A[r + 1, col + 1] = sign * tz
-                    A[r + 2, col + 1] = sign * (rx * tz - rz * tx)
+                    A[r + 2, col + 1] = sign * (rx * tz - rz * tx) / L0
             col += 2
     return A, b
 

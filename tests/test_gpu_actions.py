@@ -1,0 +1,92 @@
+"""Parity of the candidate-action kernel, task features and lin_reward with the oracle."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+XG = np.linspace(-2, 0, 10)
+
+
+def _run(shape_names, urdfs, obstacles, targets, actions, mu=0.8, shape_kwargs=None, offsets=(0.0,)):
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    from oracle import actions as oact
+    from oracle import features as ofeat
+    from oracle.gym_env import Action as OAction
+    oenv = H.oracle_env(shape_names, obstacles, targets, mu=mu, shape_kwargs=shape_kwargs)
+    obs, _ = oenv.reset()
+    reward_f, obstacle_f = ofeat.get_task_features(obs, H.XLIM, H.YLIM, H.IMG)
+    env = BatchedAssemblyGym(2, urdfs, mu=mu)
+    if shape_kwargs:
+        from bridges_b200.envs.assembly_env import Shape
+        env.set_shapes([Shape(urdf_file=H.URDF[n], **shape_kwargs.get(i, {})) for i, n in enumerate(shape_names)])
+    env.reset(dict(obstacles=obstacles, targets=targets))
+    feats = env.observe(block=True, binary=True, obstacle=True, reward=True)
+    assert np.array_equal(feats["obstacle"][0].cpu().numpy(), obstacle_f)                 # bit-exact
+    assert np.allclose(feats["reward"][0].cpu().numpy(), reward_f, rtol=1e-5, atol=1e-7)  # f32 convolution
+    for k, a in enumerate([None] + list(actions)):
+        if a is not None:
+            obs, reward, terminated, truncated, _ = oenv.step(OAction(*a))
+            frozen, unfrozen = oenv.stabilities_freezing()
+            env.step([a, a])
+            out = env.read_out()
+            new_block = oenv.assembly_env.blocks[-1]
+            from oracle.rendering import render_blocks_2d
+            action_f = render_blocks_2d([new_block], H.XLIM, H.YLIM, H.IMG).astype(np.float32)[None]
+            want = ofeat.lin_reward(action_f, reward_f, frozen, unfrozen)
+            assert abs(float(out[0]["lin_reward"]) - float(want)) <= 1e-5 * max(1.0, abs(float(want))), k
+        block_f, binary_f = ofeat.get_state_features(obs, H.XLIM, H.YLIM, H.IMG)
+        feats = env.observe()
+        assert np.array_equal(feats["block"][1].cpu().numpy(), block_f), k
+        assert np.array_equal(feats["binary"][1].cpu().numpy(), binary_f), k
+        cands = [*oact.generate_actions(oenv, XG, list(offsets))]
+        cand_f = ofeat.get_action_features(oenv, cands, H.XLIM, H.YLIM, H.IMG)
+        _, _, mask = oact.filter_actions(oenv, cands, cand_f, block_f, obstacle_f, H.XLIM, H.YLIM)
+        c = env.enumerate_actions(XG, offsets, amax=256)
+        env.sync()
+        n = int(c["n"][0].item())
+        assert n == len(cands), (k, n, len(cands))
+        got = c["cand"].cpu().numpy().view(env.dt["action"]).reshape(2, 256)[0][:n]
+        for i, ca in enumerate(cands):
+            assert (got[i]["target_block"], got[i]["target_face"], got[i]["shape"], got[i]["face"],
+                    got[i]["offset_x"], got[i]["offset_y"]) == \
+                   (ca.target_block, ca.target_face, ca.shape, ca.face, ca.offset_x, ca.offset_y), (k, i)
+        assert np.array_equal(c["valid"][0, :n].cpu().numpy().astype(bool), mask), k
+        img = env.expand_bits(c["bits"][0, :n].contiguous())
+        assert np.array_equal(img.cpu().numpy(), cand_f), k                                # bit-exact rasters
+    return env
+
+
+
+
+def test_bridge_golden_candidates():
+    obstacles = [(i * 0.6, 0, 0.3) for i in range(1, 8)]
+    targets = [(7 * 0.6 + 2.5 * 0.6, 0, 0.3)]
+    actions = [(-1, 0, 0, 2, -0.45), (0, 0, 0, 1, 0), (1, 3, 0, 1, 0), (2, 3, 0, 0, 0), (3, 3, 0, 1, 0),
+               (4, 3, 0, 1, 0), (5, 3, 0, 3, 0), (6, 1, 0, 2, 0)]
+    _run(["trapezoid"], [H.URDF["trapezoid"]], obstacles, targets, actions, mu=2.0)
+
+
+def test_mixed_library_with_face_restrictions_and_offsets():
+    actions = [(-1, 0, 1, 0, 0, 0), (-1, 0, 1, 0, -1.2, 0), (0, 3, 0, 3, 0.25, 0), (2, 1, 1, 0, 0, 0)]
+    _run(["trapezoid", "cube1"], [H.URDF["trapezoid"], H.URDF["cube1"]], [[0, 0, 2.0]],
+         [[0, 0, 0.5], [0, 0, 5.5]], actions,
+         shape_kwargs={1: dict(receiving_faces_2d=[0], target_faces_2d=[2])}, offsets=(0.0, 0.25, -0.25))
+
+
+def test_hexagon_candidates_and_random_policy():
+    import torch
+    env = _run(["hexagon"], [H.URDF["hexagon"]], [(0.6, 0, 0.3)], [(0.6, 0, 0.9)],
+               [(-1, 0, 0, 0, -1.0, 0), (0, 5, 0, 0, 0, 0)])
+    # the synthetic policy only ever picks valid candidates and is reproducible
+    c = env.enumerate_actions(XG, (0.0,), amax=256)
+    a1, i1 = env.select_random(seed=5)
+    i1 = i1.clone()
+    a2, i2 = env.select_random(seed=5)
+    env.sync()
+    assert torch.equal(i1, i2)
+    valid = c["valid"].cpu().numpy()
+    for e, idx in enumerate(i1.cpu().numpy()):
+        assert idx >= 0 and valid[e, idx] == 1
