@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- stability-checked env steps/sec of the batched assembly_gym step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # restated reference CPU env
+
+Workload (BASELINE.json configs[1]): 1024 lock-step envs per GPU, the `tower_height=2` task
+(one 0.6-cube obstacle at x=0.6, target just above it; trapezoid blocks; max_steps=10),
+synthetic uniformly-random valid actions from the candidate kernel, auto-reset on termination.
+One "step" = one `bw_step` over the whole batch: block placement, contact interfaces, the two
+equilibrium verdicts (new block frozen / released), targets, reward, termination, raster
+update and the f32 [E,1,64,64] observation + [E,6] binary features.
+
+Timing: every step is bracketed by CUDA events on the stream the kernel is launched on; the L2
+is flushed (256 MiB write) between steps, outside the event pairs; the whole loop is bracketed by
+barrier + synchronize and the max over ranks is reported.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stability-checked env steps/sec"
+UNIT = "env_steps/s"
+X_GROUND = [-2.0 + 2.0 * i / 9 for i in range(10)]   # np.linspace(-2, 0, 10), successor_dqn.py:611
+
+
+def task_def(tower_height, square=0.6):
+    obstacles = [(square, 0, i * square + square / 2) for i in range(tower_height - 1)]
+    targets = [(square, 0, (tower_height - 1) * square + square / 2)]
+    return dict(obstacles=obstacles, targets=targets)
+
+
+def config_dict(args, n_gpus):
+    return {"workload": f"tower_height={args.tower_height} trapezoid task, {args.envs} lock-step envs per GPU, "
+                        f"max_steps={args.max_steps}, random valid actions, auto-reset (BASELINE.json configs[1])",
+            "envs_per_gpu": args.envs, "tower_height": args.tower_height, "max_steps": args.max_steps,
+            "image": "64x64 f32", "mu": 0.8, "parallelism": f"env-sharded x{n_gpus}, no collective on the step path",
+            "cache": "L2 flushed between timed steps (256 MiB write outside the event pairs)"}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(job):
+    """Restated reference CPU env (oracle/) with the reference's call pattern per step:
+    env.step (placement, 2 interface rebuilds, 2 RBE solves) + stabilities_freezing (1 rebuild,
+    3 solves) + get_state_features (1 raster).  Candidate generation for the random policy runs
+    outside the timed sections."""
+    seed, budget_s, tower_height, max_steps, max_env_steps = job
+    import numpy as np
+    from oracle import actions as oact
+    from oracle import features as ofeat
+    from oracle.assembly_env import AssemblyEnv, Shape
+    from oracle.gym_env import AssemblyGym, sparse_reward
+    from oracle.rendering import render_blocks_2d
+    rng = np.random.default_rng(seed)
+    xlim, ylim, img = (-3.0, 7.0), (0.0, 10.0), (64, 64)
+    t = task_def(tower_height)
+    env = AssemblyGym(shapes=[Shape(urdf_file="shapes/trapezoid.urdf", name="trapezoid")], obstacles=t["obstacles"],
+                      targets=t["targets"], reward_fct=sparse_reward, restrict_2d=True, max_steps=max_steps,
+                      assembly_env=AssemblyEnv())
+    steps, timed = 0, 0.0
+    t_end = time.perf_counter() + budget_s
+    while time.perf_counter() < t_end and steps < max_env_steps:
+        obs, _ = env.reset()
+        obstacle_f = render_blocks_2d(obs['obstacle_blocks'], xlim, ylim, img).astype(np.float32)[None]
+        done = False
+        while not done and time.perf_counter() < t_end and steps < max_env_steps:
+            block_f, _ = ofeat.get_state_features(obs, xlim, ylim, img)
+            cands = [*oact.generate_actions(env, X_GROUND, [0.0])]
+            cand_f = ofeat.get_action_features(env, cands, xlim, ylim, img)
+            kept, _, _ = oact.filter_actions(env, cands, cand_f, block_f, obstacle_f, xlim, ylim)
+            if not kept:
+                break
+            action = kept[int(rng.integers(len(kept)))]
+            t0 = time.perf_counter()
+            obs, reward, terminated, truncated, _ = env.step(action)
+            env.stabilities_freezing()
+            ofeat.get_state_features(obs, xlim, ylim, img)
+            timed += time.perf_counter() - t0
+            steps += 1
+            done = bool(terminated or truncated)
+    return steps, timed
+
+
+def cpu_env_rate(cores, budget_s, tower_height, max_steps, max_env_steps=10 ** 9):
+    """Aggregate env steps/s of `cores` independent oracle envs."""
+    jobs = [(1000 + i, budget_s, tower_height, max_steps, max_env_steps) for i in range(cores)]
+    if cores == 1:
+        results = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            results = pool.map(_cpu_worker, jobs)
+    steps = sum(r[0] for r in results)
+    rate = sum(r[0] / r[1] for r in results if r[1] > 0)
+    return rate, steps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # one "step" of this arm = a bounded sample: every worker advances ~4 env steps
+    per_step = 4 * cores
+    total_env_steps = per_step * (args.steps + args.warmup)
+    budget = min(150.0, max(10.0, 0.05 * total_env_steps))
+    t0 = time.perf_counter()
+    rate, steps = cpu_env_rate(cores, budget, args.tower_height, args.max_steps,
+                               max_env_steps=max(8, total_env_steps // cores))
+    wall = time.perf_counter() - t0
+    k_done = max(1, min(args.steps, steps // per_step))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": k_done,
+            "warmup": args.warmup, "ms_per_step": 1e3 * per_step / rate if rate > 0 else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, world),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} env steps of the restated reference env (oracle/, numpy + HiGHS; "
+                                       f"reference unbuildable here: compas/compas_cra/pyomo/ipopt absent) in "
+                                       f"{wall:.1f} s wall on {cores} processes"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("step_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_gpu(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bridges_b200 import lib as L
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bridges_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first (rank 0, N=1 only), before this process touches CUDA in earnest
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        rate, steps = cpu_env_rate(cores, args.cpu_budget, args.tower_height, args.max_steps)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{steps} env steps of the restated reference CPU env (oracle/: numpy + HiGHS, "
+                              f"reference call pattern 5 solves + 3 interface rebuilds + 1 raster per step) in "
+                              f"{time.perf_counter() - t0:.1f} s wall on {cores} processes; same task and policy"}
+
+    E, K, W = args.envs, args.steps, args.warmup
+    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=args.max_steps, device=local_rank)
+    lib, h = env.lib, env.handle
+    env.reset(task_def(args.tower_height))
+    n_obs_tgt = (args.tower_height - 1) + 1
+    dt = env.dt
+    block_img = torch.empty((E, 1, 64, 64), dtype=torch.float32, device=dev)
+    binary = torch.empty((E, 6), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    amax = 128
+    lib.bw_set_timing(h, 0)
+
+    def choose_actions(step_id):
+        env.enumerate_actions(X_GROUND, (0.0,), amax=amax, with_bits=False)
+        return env.select_random(seed=args.seed * 1000003 + step_id * 7919 + rank)[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also brings the env population to its steady-state mix of block counts)
+    for i in range(W):
+        acts = choose_actions(i)
+        env.step(acts, block_img=block_img, binary=binary)
+        env.reset_done()
+    barrier()
+
+    # ---- device-timed loop
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    stats = []
+    sampler = ClockSampler(local_rank)
+    launches0 = env.kernel_launches()
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        acts = choose_actions(W + i)
+        flush.fill_(i & 0xff)                       # evict the 126 MB L2
+        ev[i][0].record()
+        env.step(acts, block_img=block_img, binary=binary)
+        ev[i][1].record()
+        if i % max(1, K // 16) == 0:
+            stats.append(env._out.clone())
+        env.reset_done()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = env.kernel_launches() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = sum(step_ms) * 1e-3
+
+    # ---- statistics of the sampled steps (algorithmic bytes / flops per launch)
+    outs = np.concatenate([s.cpu().numpy().view(dt["step_out"]) for s in stats])
+    n_pre = np.maximum(outs["n_blocks"].astype(np.float64) - 1, 0)
+    bytes_per_launch = float(E * (16528 + 16 * n_obs_tgt) + 32 * n_pre.mean() * E)
+    flops_per_launch = float(outs["solver_kflops"].astype(np.float64).mean() * 1e3 * E)
+    fp64 = C.c_double(0.0)
+    lib.bw_fp64_peak_gflops(h, C.byref(fp64))
+
+    # ---- end-to-end loop: host actions in, host results (records, images, binary) out
+    h_act = torch.empty(E * dt["action"].itemsize, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(E * dt["step_out"].itemsize, dtype=torch.uint8).pin_memory()
+    h_img = torch.empty((E, 1, 64, 64), dtype=torch.float32).pin_memory()
+    h_bin = torch.empty((E, 6), dtype=torch.float32).pin_memory()
+    Ke = min(K, args.e2e_steps)
+    barrier()
+    t_e2e = 0.0
+    for i in range(Ke):
+        acts = choose_actions(W + K + i)
+        h_act.copy_(acts)                           # the policy's actions arrive on the host
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.bw_step_host(h, h_act.data_ptr(), None, h_out.data_ptr(), h_img.data_ptr(), h_bin.data_ptr())
+        t_e2e += time.perf_counter() - t0
+        L.check(lib, h, rc)
+        env.reset_done()
+    barrier()
+    h2d = E * dt["action"].itemsize
+    d2h = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
+
+    # ---- max over ranks
+    red = torch.tensor([t_dev, t_e2e, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, wall = (float(x) for x in red.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    ms_kernel = 1e3 * t_dev / K
+    achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
+    value = world * E * K / t_dev
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_kernel, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+        "clocks": clocks,
+        "e2e": {"value": world * E * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "api": "bw_step_host (pinned host actions in; step records, f32 images, binary out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "note": "latency/FP64-bound kernel: see roofline_fp64 for the solver"},
+        "roofline_fp64": {"kernel": "step_kernel (equilibrium solves)", "bound": "fp64-fma",
+                          "achieved": flops_per_launch / (ms_kernel * 1e-3) / 1e12, "peak": fp64.value / 1e3,
+                          "unit": "TFLOP/s", "frac": (flops_per_launch / (ms_kernel * 1e-3) / 1e9) / max(fp64.value, 1e-9),
+                          "peak_source": "bw_fp64_peak_gflops micro-benchmark, same job",
+                          "flops_per_launch": flops_per_launch},
+        "env_stats": {"mean_blocks": float(outs["n_blocks"].mean()), "mean_interfaces": float(outs["n_interfaces"].mean()),
+                      "mean_newton_iters_per_step": float(outs["newton_iters"].mean()),
+                      "stable_frac": float(outs["stable"].mean()), "terminated_frac": float(outs["terminated"].mean()),
+                      "solver_not_converged": int((outs["solver_status"] != 0).sum())},
+        "wall_s_timed_region": wall,
+    }
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=1024, help="lock-step envs per GPU")
+    ap.add_argument("--tower-height", type=int, default=2)
+    ap.add_argument("--max-steps", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline sampling")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

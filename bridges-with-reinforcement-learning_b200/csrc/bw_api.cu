@@ -190,7 +190,7 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
                     cudaGetErrorString(ce));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(h, BW_ERR_INVALID, "device %d out of range", cfg->device);
     CU(cudaSetDevice(cfg->device));
-    if (cfg->stream) {
+    if (cfg->use_caller_stream) {
         h->stream = static_cast<cudaStream_t>(cfg->stream);
     } else {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -340,6 +340,15 @@ int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask) {
     return BW_OK;
 }
 
+int bw_fp64_peak_gflops(bw_handle *h, double *h_gflops) {
+    if (!h || !h_gflops) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    *h_gflops = measure_fp64_gflops(h->stream);
+    h->launches += 4;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
 int bw_set_timing(bw_handle *h, int32_t enabled) {
     if (!h) return BW_ERR_INVALID;
     h->timing = enabled != 0;
@@ -359,7 +368,8 @@ int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
     h->launches++;
     if (d_tasks != nullptr) {
         // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
-        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, nullptr, nullptr, 0, h->smem_step, h->stream);
+        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, nullptr, nullptr, nullptr, nullptr, 0, h->smem_step,
+                    h->stream);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -397,17 +407,11 @@ int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_
     if (int rc = need_shapes(h)) return rc;
     CU(cudaSetDevice(h->cfg.device));
     if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
-    launch_step(h->P, d_actions, d_mask, d_out, nullptr, nullptr, 0, h->smem_step, h->stream);
+    // one kernel: placement, interfaces, both solves, bookkeeping, raster update and the
+    // f32 observation write
+    launch_step(h->P, d_actions, d_mask, d_out, d_block_img, d_binary, nullptr, nullptr, 0, h->smem_step, h->stream);
     h->launches++;
     if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
-    h->ev_obs = false;
-    if (d_block_img || d_binary) {
-        if (h->timing) CU(cudaEventRecord(h->ev[2], h->stream));
-        launch_observe(h->P, d_block_img, d_binary, nullptr, nullptr, h->stream);
-        h->launches += (d_block_img ? 1 : 0) + (d_binary ? 1 : 0);
-        if (h->timing) CU(cudaEventRecord(h->ev[3], h->stream));
-        h->ev_obs = true;
-    }
     CU(cudaGetLastError());
     return BW_OK;
 }
@@ -418,7 +422,6 @@ int bw_last_step_kernel_ms(bw_handle *h, float *h_ms2) {
     CU(cudaStreamSynchronize(h->stream));
     h_ms2[0] = h_ms2[1] = 0.0f;
     CU(cudaEventElapsedTime(&h_ms2[0], h->ev[0], h->ev[1]));
-    if (h->ev_obs) CU(cudaEventElapsedTime(&h_ms2[1], h->ev[2], h->ev[3]));
     return BW_OK;
 }
 
@@ -653,7 +656,8 @@ int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h
     CU(cudaMemsetAsync(h->d_itf, 0, sizeof(bw_interface) * E * BW_MAX_INTERFACES, h->stream));
     // the state did not change since the last step: re-evaluating it reproduces the same
     // interfaces and dual iterates, this time with the read-back enabled
-    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, h->d_itf, h->d_nitf, variant, h->smem_step, h->stream);
+    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, nullptr, nullptr, h->d_itf, h->d_nitf, variant,
+                h->smem_step, h->stream);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_itf, h->d_itf, sizeof(bw_interface) * E * BW_MAX_INTERFACES, cudaMemcpyDeviceToHost, h->stream));

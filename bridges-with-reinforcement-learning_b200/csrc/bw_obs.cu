@@ -208,4 +208,41 @@ void launch_observe(const Params &P, float *d_block_img, float *d_binary, float 
     if (d_binary) binary_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, d_binary);
 }
 
+// ------------------------------------------------------------------ FP64 FMA micro-benchmark
+// Denominator of the solver's compute roofline (MEASURED_PEAKS.json has no FP64 entry):
+// 8 independent FMA chains per thread, 1024 threads per SM-resident CTA pair.
+__global__ void __launch_bounds__(512) fp64_fma_kernel(double *sink, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) sink[0] = s;
+}
+
+double measure_fp64_gflops(cudaStream_t stream) {
+    double *sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = 148 * 4, threads = 512, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, stream);
+        fp64_fma_kernel<<<blocks, threads, 0, stream>>>(sink, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double gflops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) * 1e-9;
+        if (rep > 0 && gflops > best) best = gflops;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
 }  // namespace bw

@@ -332,6 +332,11 @@ struct Solver {
     }
 
     // returns status: 0 feasible (r <= 1e-9), 1 stagnated at r* > 0, 2 not converged
+    // work estimate (flops) of the last solve: per Newton step one Cholesky (m^3/3), two
+    // triangular solves (2 m^2), the assembly of H (54 flops per contact column pair), two sparse
+    // products with A (24 nc each) and per line-search evaluation one cone projection sweep
+    double flops = 0.0;
+
     __device__ int solve(double &r_out, int &iters_out) {
         for (int i = lane; i < m; i += 32) y[i] = 0.0;
         __syncwarp();
@@ -385,6 +390,7 @@ struct Solver {
                     }
                     fh = warp_sum(fh);
                     p = bd - fh - (yd + t * dd) * inv_rho;
+                    flops += 20.0 * nc;
                     if (p >= -1e-12 * phi0) break;
                     double ts = t * phi0 / (phi0 - p);
                     t = fmin(fmax(ts, 0.05 * t), 0.95 * t);
@@ -392,6 +398,7 @@ struct Solver {
                 for (int i = lane; i < m; i += 32) y[i] += t * d[i];
                 __syncwarp();
                 iters++;
+                flops += (double)m * m * m / 3.0 + 2.0 * m * m + 54.0 * 2.0 * nc + 48.0 * nc + 12.0 * m;
                 if (t * sqrt(dd) <= 1e-15 * fmax(1.0, sqrt(yy))) break;
             }
             r = residual();
@@ -408,8 +415,8 @@ struct Solver {
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(64)
 step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
-            bw_step_out *__restrict__ out, bw_interface *__restrict__ save_itf, int32_t *__restrict__ save_nitf,
-            int save_variant) {
+            bw_step_out *__restrict__ out, float *__restrict__ block_img, float *__restrict__ binary,
+            bw_interface *__restrict__ save_itf, int32_t *__restrict__ save_nitf, int save_variant) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
@@ -432,6 +439,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     __shared__ double sh_L0;
     __shared__ double sh_res[2];
     __shared__ int sh_status[2], sh_iters[2], sh_stable[2];
+    __shared__ double sh_flops[2];
     __shared__ double sh_lin[2];
 
     const bw_action act = actions[e];
@@ -711,6 +719,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         }
         if (lane == 0) {
             sh_res[warp] = res; sh_status[warp] = status; sh_iters[warp] = iters; sh_stable[warp] = stable;
+            sh_flops[warp] = S.flops;
         }
         if (save_itf != nullptr && warp == save_variant && !overflow && nitf > 0 && nfree > 0) {
             // physical forces: f = P_K(A^T y) * ||weights||   (f[] holds the projection of the last residual())
@@ -787,6 +796,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         o.residual = sh_res[0];
         o.residual_unfrozen = sh_res[1];
         o.newton_iters = sh_iters[0] + sh_iters[1];
+        o.solver_kflops = (int32_t)fmin(2e9, (sh_flops[0] + sh_flops[1]) * 1e-3);
         o.n_blocks = n;
         o.n_interfaces = nitf;
         o.n_targets_reached = (uint8_t)tk.n_reached;
@@ -801,25 +811,34 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         if (placed) P.done[e] = (uint8_t)(o.terminated | o.truncated);
     }
 
-    // ---------------- phase 5: raster update of the new block, one thread per image row
-    if (placed) {
-        double lin = 0.0;
+    // ---------------- phase 5: raster update of the new block (one thread per image row), lin_reward,
+    // and the fused observation write: f32 [1,64,64] image + 6 binary features
+    __shared__ uint64_t sh_bits[IMG];
+    {
         const int row = tid;
-        const uint64_t bits = raster_row(P, P.shapes[s_shape[n - 1]], s_pose[n - 1], row);
-        if (bits) {
-            P.block_bits[(size_t)e * IMG + row] |= bits;
-            const float *rw = P.reward_img + (size_t)e * IMG * IMG + row * IMG;
-            uint64_t bb = bits;
-            while (bb) {
-                const int j = __ffsll((long long)bb) - 1;
-                bb &= bb - 1;
-                lin += (double)rw[j];
+        uint64_t cur = P.block_bits[(size_t)e * IMG + row];
+        double lin = 0.0;
+        if (placed) {
+            const uint64_t bits = raster_row(P, P.shapes[s_shape[n - 1]], s_pose[n - 1], row);
+            if (bits) {
+                cur |= bits;
+                P.block_bits[(size_t)e * IMG + row] = cur;
+                const float *rw = P.reward_img + (size_t)e * IMG * IMG + row * IMG;
+                uint64_t bb = bits;
+                while (bb) {
+                    const int j = __ffsll((long long)bb) - 1;
+                    bb &= bb - 1;
+                    lin += (double)rw[j];
+                }
             }
         }
+        sh_bits[row] = cur;
         lin = warp_sum(lin);
         if (lane == 0) sh_lin[warp] = lin;
-        __syncthreads();
-        if (tid == 0) {
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (placed) {
             // successor_dqn.py:397-401
             const float s = (float)(sh_lin[0] + sh_lin[1]);
             float lr = 0.0f;
@@ -827,13 +846,29 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             if (stable_unfrozen) lr = s;
             out[e].lin_reward = lr;
         }
+        P.last_out[e] = out[e];
+        if (binary != nullptr) {
+            float *bf = binary + (size_t)e * 6;   // get_state_features, successor_dqn.py:53-60
+            bf[0] = (float)stable_frozen; bf[1] = 0.0f; bf[2] = 0.0f; bf[3] = 0.0f; bf[4] = 0.0f; bf[5] = 0.0f;
+        }
     }
-    if (tid == 0) P.last_out[e] = out[e];
+    if (block_img != nullptr) {
+        float4 *dst = reinterpret_cast<float4 *>(block_img + (size_t)e * IMG * IMG);
+#pragma unroll 4
+        for (int i = 0; i < IMG * IMG / 4 / 64; i++) {
+            const int q = i * 64 + tid;            // float4 index: row = q / 16, nibble = q % 16
+            const unsigned nib = (unsigned)(sh_bits[q >> 4] >> (4 * (q & 15))) & 0xfu;
+            __stcs(dst + q, make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f,
+                                        (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f));
+        }
+    }
 }
 
 void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
-                 bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes, cudaStream_t stream) {
-    step_kernel<<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_itf, d_nitf, variant);
+                 float *d_block_img, float *d_binary, bw_interface *d_itf, int32_t *d_nitf, int variant,
+                 int smem_bytes, cudaStream_t stream) {
+    step_kernel<<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf, d_nitf,
+                                                 variant);
 }
 
 cudaError_t configure_step(int smem_bytes) {

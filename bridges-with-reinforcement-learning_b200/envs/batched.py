@@ -71,6 +71,7 @@ class BatchedAssemblyGym:
         # issued through torch and the library's kernels are ordered without extra syncs
         with torch.cuda.device(self.device):
             cfg.stream = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+            cfg.use_caller_stream = 1          # 0/NULL is torch's (legacy default) stream, a valid choice
         self.handle = C.c_void_p()
         rc = self.lib.bw_create(C.byref(cfg), C.byref(self.handle))
         self._check(rc)

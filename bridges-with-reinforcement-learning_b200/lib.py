@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbridges_
 
 
 class bw_config(C.Structure):
-    _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("max_steps", C.c_int32), ("reserved0", C.c_int32),
+    _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("max_steps", C.c_int32), ("use_caller_stream", C.c_int32),
                 ("xlim", C.c_double * 2), ("ylim", C.c_double * 2),
                 ("floor_halfwidth", C.c_double), ("floor_depth", C.c_double),
                 ("mu", C.c_double), ("density", C.c_double), ("tmax", C.c_double), ("amin", C.c_double),
@@ -60,7 +60,7 @@ class bw_step_out(C.Structure):
                 ("distance_to_targets", C.c_double * BW_MAX_TARGETS),
                 ("reward", C.c_float), ("lin_reward", C.c_float),
                 ("n_blocks", C.c_int32), ("n_interfaces", C.c_int32), ("newton_iters", C.c_int32),
-                ("reserved0", C.c_int32),
+                ("solver_kflops", C.c_int32),
                 ("stable", C.c_uint8), ("stable_unfrozen", C.c_uint8), ("collision", C.c_uint8),
                 ("collision_block", C.c_uint8), ("collision_obstacle", C.c_uint8), ("collision_floor", C.c_uint8),
                 ("collision_boundary", C.c_uint8), ("terminated", C.c_uint8), ("truncated", C.c_uint8),
@@ -83,7 +83,7 @@ def np_dtypes():
     step_out = np.dtype([("residual", "<f8"), ("residual_unfrozen", "<f8"),
                          ("distance_to_targets", "<f8", (BW_MAX_TARGETS,)),
                          ("reward", "<f4"), ("lin_reward", "<f4"),
-                         ("n_blocks", "<i4"), ("n_interfaces", "<i4"), ("newton_iters", "<i4"), ("reserved0", "<i4"),
+                         ("n_blocks", "<i4"), ("n_interfaces", "<i4"), ("newton_iters", "<i4"), ("solver_kflops", "<i4"),
                          ("stable", "u1"), ("stable_unfrozen", "u1"), ("collision", "u1"), ("collision_block", "u1"),
                          ("collision_obstacle", "u1"), ("collision_floor", "u1"), ("collision_boundary", "u1"),
                          ("terminated", "u1"), ("truncated", "u1"), ("solver_status", "u1"), ("error", "u1"),
@@ -134,6 +134,7 @@ SIGNATURES = {
     "bw_set_static_mask": (C.c_int, [_H, _P]),
     "bw_set_timing": (C.c_int, [_H, C.c_int32]),
     "bw_last_step_kernel_ms": (C.c_int, [_H, _P]),
+    "bw_fp64_peak_gflops": (C.c_int, [_H, _P]),
     "bw_kernel_launches": (C.c_int64, [_H]),
 }
 

@@ -58,7 +58,8 @@ typedef struct {
     int32_t num_envs;
     int32_t device;          /* CUDA device ordinal */
     int32_t max_steps;       /* AssemblyGym(max_steps); 0 = None */
-    int32_t reserved0;
+    int32_t use_caller_stream; /* 1: enqueue on `stream` below (NULL = the legacy default stream);
+                                  0: the library creates its own non-blocking stream */
     double xlim[2];          /* raster / bounds window in x (default -3, 7) */
     double ylim[2];          /* raster / bounds window in z (default 0, 10) */
     double floor_halfwidth;  /* support Box half width: 0.5*(bounds[1][0]-bounds[0][0]) = 5 (assembly_env.py:290) */
@@ -68,7 +69,7 @@ typedef struct {
     double tmax;             /* interface coplanarity tolerance (compas_cra default 1e-6) */
     double amin;             /* minimum interface area, 0.001 (assembly_env.py:304) */
     double stable_tol;       /* verdict threshold on the relative equilibrium residual, default 1e-6 */
-    void *stream;            /* cudaStream_t to enqueue on; NULL = the library creates one */
+    void *stream;            /* cudaStream_t to enqueue on when use_caller_stream = 1 */
 } bw_config;
 
 /* One entry of the block library: what Shape.from_urdf (assembly_env.py:54-68) extracts,
@@ -127,7 +128,7 @@ typedef struct {
     int32_t n_blocks;
     int32_t n_interfaces;
     int32_t newton_iters;         /* Newton steps of both solves */
-    int32_t reserved0;
+    int32_t solver_kflops;        /* work estimate of both solves, in 1e3 flops */
     uint8_t stable;               /* obs['stable']: verdict with only the new block frozen */
     uint8_t stable_unfrozen;      /* stabilities_freezing()[1]: last block released */
     uint8_t collision;            /* constant 0 without PyBullet (assembly_env.py:310-312) */
@@ -234,12 +235,15 @@ int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf /*[E,BW_MAX
 int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask);
 
 /* ---- measurement helpers ------------------------------------------------------------- */
-/* bw_set_timing(h, 1) brackets every kernel of bw_step with CUDA events on the handle's
- * stream; bw_last_step_kernel_ms then returns (after synchronising) the elapsed ms of
- * [0] the step kernel (placement, interfaces, two solves, bookkeeping, raster update) and
- * [1] the observation kernel (bit raster -> f32 image + binary features; 0 if not launched) */
+/* bw_set_timing(h, 1) brackets the step kernel of bw_step with CUDA events on the handle's
+ * stream; bw_last_step_kernel_ms then returns (after synchronising) in h_ms2[0] the elapsed ms
+ * of that kernel (placement, interfaces, two solves, bookkeeping, raster update, f32
+ * observation write); h_ms2[1] is reserved (0) */
 int bw_set_timing(bw_handle *h, int32_t enabled);
 int bw_last_step_kernel_ms(bw_handle *h, float *h_ms2);
+/* sustained FP64 FMA throughput of the device (GFLOP/s), measured by a micro-benchmark:
+ * the denominator of the solver's compute roofline */
+int bw_fp64_peak_gflops(bw_handle *h, double *h_gflops);
 /* number of kernels launched by this handle so far */
 int64_t bw_kernel_launches(const bw_handle *h);
 
