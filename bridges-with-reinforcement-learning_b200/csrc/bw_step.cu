@@ -248,72 +248,68 @@ struct Solver {
         }
     }
 
-    // solve H d = rhs by Cholesky; rows owned by lanes (i, i + 32); result in d[]
+    // Solve H d = rhs by a left-looking Cholesky factorisation in the packed lower-triangular
+    // storage: lane i owns row i (and row i + 32 when m > 32).  Column j costs one dot product of
+    // the owned row with row j (a broadcast read), so the inner loop is LDS + LDS + DFMA with no
+    // stores; the loops are kept rolled on purpose -- the whole solver has to stay resident in the
+    // instruction cache, straight-line unrolled variants ran 3x slower.
     __device__ void chol_solve(double inv_rho) {
         const int i0 = lane, i1 = lane + 32;
-        double z0 = (i0 < m) ? rhs[i0] : 0.0;
-        double z1 = (i1 < m) ? rhs[i1] : 0.0;
+        const bool two = m > 32;
+        // lanes without a row read row 0 (results unused) so that every access stays inside H
+        double *row0 = H + tri(i0 < m ? i0 : 0);
+        double *row1 = H + tri(i1 < m ? i1 : 0);
         for (int j = 0; j < m; j++) {
-            double piv = H[tri(j) + j];
+            const double *rowj = H + tri(j);
+            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+            int p = 0;
+            if (!two) {
+                for (; p + 1 < j; p += 2) {
+                    a0 += row0[p] * rowj[p];
+                    a1 += row0[p + 1] * rowj[p + 1];
+                }
+                if (p < j) a0 += row0[p] * rowj[p];
+            } else {
+                for (; p < j; p++) {
+                    const double l = rowj[p];
+                    a0 += row0[p] * l;
+                    c0 += (i1 < m) ? row1[p] * l : 0.0;
+                }
+            }
+            const double s0 = ((i0 >= j && i0 < m) ? row0[j] : 0.0) - (a0 + a1);
+            const double s1 = (two && i1 < m) ? row1[j] - (c0 + c1) : 0.0;
+            double piv = __shfl_sync(FULL, (j < 32) ? s0 : s1, j & 31);
             if (!(piv > 1e-300)) piv = inv_rho;
-            double inv = rsqrt(piv);
-            double l0 = 0.0, l1 = 0.0;
-            if (i0 > j && i0 < m) { l0 = H[tri(i0) + j] * inv; H[tri(i0) + j] = l0; }
-            if (i1 > j && i1 < m) { l1 = H[tri(i1) + j] * inv; H[tri(i1) + j] = l1; }
+            const double inv = rsqrt(piv);
+            if (i0 > j && i0 < m) row0[j] = s0 * inv;
+            if (two && i1 > j && i1 < m) row1[j] = s1 * inv;
             if (lane == 0) invd[j] = inv;
-            double zj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * inv;
-            if (i0 == j) z0 = zj;
-            if (i1 == j) z1 = zj;
-            if (i0 > j) z0 -= l0 * zj;
-            if (i1 > j) z1 -= l1 * zj;
-            __syncwarp();
-            // trailing update, rows >= k of column k
-            int k = j + 1;
-            for (; k + 3 < m; k += 4) {
-                double lk0 = H[tri(k) + j], lk1 = H[tri(k + 1) + j], lk2 = H[tri(k + 2) + j], lk3 = H[tri(k + 3) + j];
-                if (i0 < m && i0 >= k) {
-                    double *row = H + tri(i0);
-                    double h0 = row[k], h1 = 0, h2 = 0, h3 = 0;
-                    bool b1 = i0 >= k + 1, b2 = i0 >= k + 2, b3 = i0 >= k + 3;
-                    if (b1) h1 = row[k + 1];
-                    if (b2) h2 = row[k + 2];
-                    if (b3) h3 = row[k + 3];
-                    row[k] = h0 - l0 * lk0;
-                    if (b1) row[k + 1] = h1 - l0 * lk1;
-                    if (b2) row[k + 2] = h2 - l0 * lk2;
-                    if (b3) row[k + 3] = h3 - l0 * lk3;
-                }
-                if (i1 < m && i1 >= k) {
-                    double *row = H + tri(i1);
-                    double h0 = row[k], h1 = 0, h2 = 0, h3 = 0;
-                    bool b1 = i1 >= k + 1, b2 = i1 >= k + 2, b3 = i1 >= k + 3;
-                    if (b1) h1 = row[k + 1];
-                    if (b2) h2 = row[k + 2];
-                    if (b3) h3 = row[k + 3];
-                    row[k] = h0 - l1 * lk0;
-                    if (b1) row[k + 1] = h1 - l1 * lk1;
-                    if (b2) row[k + 2] = h2 - l1 * lk2;
-                    if (b3) row[k + 3] = h3 - l1 * lk3;
-                }
-            }
-            for (; k < m; k++) {
-                double lkj = H[tri(k) + j];
-                if (i0 < m && i0 >= k) H[tri(i0) + k] -= l0 * lkj;
-                if (i1 < m && i1 >= k) H[tri(i1) + k] -= l1 * lkj;
-            }
             __syncwarp();
         }
-        // back substitution L^T d = z
+        // forward substitution L z = rhs, then back substitution L^T d = z
+        double z0 = (i0 < m) ? rhs[i0] : 0.0;
+        double z1 = (two && i1 < m) ? rhs[i1] : 0.0;
+        for (int j = 0; j < m; j++) {
+            const double zj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
+            if (i0 == j) z0 = zj;
+            else if (i0 > j && i0 < m) z0 -= row0[j] * zj;
+            if (two) {
+                if (i1 == j) z1 = zj;
+                else if (i1 > j && i1 < m) z1 -= row1[j] * zj;
+            }
+        }
         for (int j = m - 1; j >= 0; j--) {
-            double dj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
+            const double dj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
+            const double *rowj = H + tri(j);
             if (i0 == j) z0 = dj;
-            if (i1 == j) z1 = dj;
-            const double *row = H + tri(j);
-            if (i0 < j) z0 -= row[i0] * dj;
-            if (i1 < j) z1 -= row[i1] * dj;
+            else if (i0 < j) z0 -= rowj[i0] * dj;
+            if (two) {
+                if (i1 == j) z1 = dj;
+                else if (i1 < j) z1 -= rowj[i1] * dj;
+            }
         }
         if (i0 < m) d[i0] = z0;
-        if (i1 < m) d[i1] = z1;
+        if (two && i1 < m) d[i1] = z1;
         __syncwarp();
     }
 
@@ -331,14 +327,36 @@ struct Solver {
         return sqrt(warp_sum(acc));
     }
 
+    __device__ __forceinline__ double dphi(double t, double bd, double yd, double dd, double inv_rho) {
+        double fh = 0.0;
+        for (int c = lane; c < nc; c += 32) {
+            double fn, ft;
+            int tp;
+            project_cone(g[2 * c] + t * h[2 * c], g[2 * c + 1] + t * h[2 * c + 1], mu, inv_den, fn, ft, tp);
+            fh += fn * h[2 * c] + ft * h[2 * c + 1];
+        }
+        fh = warp_sum(fh);
+        flops += 20.0 * nc;
+        return bd - fh - (yd + t * dd) * inv_rho;
+    }
+
     // returns status: 0 feasible (r <= 1e-9), 1 stagnated at r* > 0, 2 not converged
     // work estimate (flops) of the last solve: per Newton step one Cholesky (m^3/3), two
     // triangular solves (2 m^2), the assembly of H (54 flops per contact column pair), two sparse
     // products with A (24 nc each) and per line-search evaluation one cone projection sweep
     double flops = 0.0;
+#ifdef BW_PROFILE
+    long long acc_t[6] = {0, 0, 0, 0, 0, 0};   // grad, assemble, cholesky, dots+h, line search, residual
+#define BW_ACC(i, t0) acc_t[i] += clock64() - (t0)
+#define BW_T0(name) const long long name = clock64()
+#else
+#define BW_ACC(i, t0)
+#define BW_T0(name)
+#endif
 
     __device__ int solve(double &r_out, int &iters_out) {
         for (int i = lane; i < m; i += 32) y[i] = 0.0;
+        for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
         __syncwarp();
         double rprev = -1.0, r = 1.0;
         int status = 2, iters = 0;
@@ -347,8 +365,7 @@ struct Solver {
             for (int i = lane; i < m; i += 32) yk[i] = y[i];
             __syncwarp();
             for (int it = 0; it < MAX_NEWTON; it++) {
-                at_times(y, g);
-                __syncwarp();
+                BW_T0(t_a);
                 project_all();
                 __syncwarp();
                 double acc = 0.0;
@@ -358,10 +375,16 @@ struct Solver {
                     acc += gr * gr;
                 }
                 double gn2 = warp_sum(acc);
+                BW_ACC(0, t_a);
                 if (gn2 <= 1e-20) break;
+                BW_T0(t_b);
                 assemble_H(inv_rho);
                 __syncwarp();
+                BW_ACC(1, t_b);
+                BW_T0(t_c);
                 chol_solve(inv_rho);
+                BW_ACC(2, t_c);
+                BW_T0(t_d);
                 at_times(d, h);
                 __syncwarp();
                 // dots for the line search
@@ -376,34 +399,42 @@ struct Solver {
                 }
                 dd = warp_sum(dd); bd = warp_sum(bd); yd = warp_sum(yd); gd = warp_sum(gd); yy = warp_sum(yy);
                 const double phi0 = gd;
+                BW_ACC(3, t_d);
                 if (!(phi0 > 1e-30)) break;
-                // derivative of the concave dual along d: phi'(t) = b.d - P_K(g + t h).h - (yd + t dd)/rho
+                BW_T0(t_e);
+                // derivative of the concave dual along d: phi'(t) = b.d - P_K(g + t h).h - (yd + t dd)/rho,
+                // piecewise linear and decreasing.  Accept t = 1 if still ascending there, otherwise
+                // bracket the root with a safeguarded regula falsi until |phi'| <= 0.1 phi'(0).
                 double t = 1.0;
-                double p;
-                for (int ls = 0; ls < 30; ls++) {
-                    double fh = 0.0;
-                    for (int c = lane; c < nc; c += 32) {
-                        double fn, ft;
-                        int tp;
-                        project_cone(g[2 * c] + t * h[2 * c], g[2 * c + 1] + t * h[2 * c + 1], mu, inv_den, fn, ft, tp);
-                        fh += fn * h[2 * c] + ft * h[2 * c + 1];
+                double p = dphi(t, bd, yd, dd, inv_rho);
+                if (p < -1e-12 * phi0) {
+                    double lo = 0.0, plo = phi0, hi = 1.0, phi = p;
+                    for (int ls = 0; ls < 20; ls++) {
+                        const double w = hi - lo;
+                        t = lo + w * plo / (plo - phi);
+                        t = fmin(fmax(t, lo + 0.1 * w), hi - 0.1 * w);
+                        p = dphi(t, bd, yd, dd, inv_rho);
+                        if (fabs(p) <= 0.1 * phi0) break;
+                        if (p > 0.0) { lo = t; plo = p; } else { hi = t; phi = p; }
                     }
-                    fh = warp_sum(fh);
-                    p = bd - fh - (yd + t * dd) * inv_rho;
-                    flops += 20.0 * nc;
-                    if (p >= -1e-12 * phi0) break;
-                    double ts = t * phi0 / (phi0 - p);
-                    t = fmin(fmax(ts, 0.05 * t), 0.95 * t);
+                    if (p < 0.0 && fabs(p) > 0.1 * phi0 && lo > 0.0) t = lo;
                 }
                 for (int i = lane; i < m; i += 32) y[i] += t * d[i];
+                for (int c = lane; c < 2 * nc; c += 32) g[c] += t * h[c];   // A^T (y + t d)
                 __syncwarp();
+                BW_ACC(4, t_e);
                 iters++;
                 flops += (double)m * m * m / 3.0 + 2.0 * m * m + 54.0 * 2.0 * nc + 48.0 * nc + 12.0 * m;
                 if (t * sqrt(dd) <= 1e-15 * fmax(1.0, sqrt(yy))) break;
             }
+            BW_T0(t_f);
             r = residual();
+            BW_ACC(5, t_f);
             if (r <= 1e-9) { status = 0; break; }
             if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
+            // a feasible system loses two orders of magnitude per stage (rho x 100); a residual that
+            // stays above half its previous value and far above the verdict threshold has stalled at r*
+            if (rprev >= 0.0 && r >= 0.5 * rprev && r > 1e-3) { status = 1; break; }
             rprev = r;
         }
         r_out = r;
@@ -440,8 +471,20 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     __shared__ double sh_res[2];
     __shared__ int sh_status[2], sh_iters[2], sh_stable[2];
     __shared__ double sh_flops[2];
+#ifdef BW_PROFILE
+    __shared__ long long sh_prof_solve[2];
+    __shared__ long long sh_prof_sub[2][6];
+    __shared__ long long sh_prof_book[4];
+#endif
     __shared__ double sh_lin[2];
 
+#ifdef BW_PROFILE
+    long long prof_t[8];
+    prof_t[0] = clock64();
+#define BW_STAMP(i) prof_t[i] = clock64()
+#else
+#define BW_STAMP(i)
+#endif
     const bw_action act = actions[e];
     const int n_old = P.n_blocks[e];
     if (tid < n_old) {
@@ -534,6 +577,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     }
     __syncthreads();
 
+    BW_STAMP(1);
     // ---------------- phase 2: interfaces (one candidate per body pair, lexicographic order)
     unsigned hitmask = 0;  // bit r = pair (r*64 + tid) has an interface
     for (int r = 0; r < 3; r++) {
@@ -656,6 +700,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     }
     __syncthreads();
 
+    BW_STAMP(2);
     // ---------------- phase 3: two equilibrium problems, one warp each
     uint32_t smask = P.static_mask[e];
     if (placed) {
@@ -717,6 +762,12 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             status = S.solve(res, iters);
             stable = (status != 2) && (res <= P.stable_tol);
         }
+#ifdef BW_PROFILE
+        if (lane == 0) {
+            sh_prof_solve[warp] = clock64() - prof_t[2];
+            for (int q = 0; q < 6; q++) sh_prof_sub[warp][q] = S.acc_t[q];
+        }
+#endif
         if (lane == 0) {
             sh_res[warp] = res; sh_status[warp] = status; sh_iters[warp] = iters; sh_stable[warp] = stable;
             sh_flops[warp] = S.flops;
@@ -732,13 +783,20 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     }
     __syncthreads();
 
+    BW_STAMP(4);
     // ---------------- phase 4: bookkeeping (thread 0)
     TaskDev *task = P.task + e;
     const int stable_frozen = sh_stable[0], stable_unfrozen = sh_stable[1];
     if (tid == 0) {
+#ifdef BW_PROFILE
+        const long long tb0 = clock64();
+#endif
         bw_step_out o;
         memset(&o, 0, sizeof(o));
         TaskDev tk = *task;
+#ifdef BW_PROFILE
+        sh_prof_book[0] = clock64() - tb0;
+#endif
         if (placed) {
             // _update_targets (gym_env.py:162-168): AABB test, removal while iterating
             const double *B = s_body + n * BODY_DOUBLES;
@@ -771,6 +829,9 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             P.shape_of[(size_t)e * NB + (n - 1)] = s_shape[n - 1];
             P.static_mask[e] = smask;
         }
+#ifdef BW_PROFILE
+        sh_prof_book[1] = clock64() - tb0;
+#endif
         // distance_to_targets (gym_env.py:154-160, geometry.py:89-105)
         for (int t = 0; t < tk.n_targets; t++) {
             double best = INFINITY;
@@ -790,6 +851,9 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             }
             o.distance_to_targets[t] = best;
         }
+#ifdef BW_PROFILE
+        sh_prof_book[2] = clock64() - tb0;
+#endif
         o.stable = (uint8_t)stable_frozen;
         o.stable_unfrozen = (uint8_t)stable_unfrozen;
         o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0));
@@ -811,6 +875,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         if (placed) P.done[e] = (uint8_t)(o.terminated | o.truncated);
     }
 
+    BW_STAMP(5);
     // ---------------- phase 5: raster update of the new block (one thread per image row), lin_reward,
     // and the fused observation write: f32 [1,64,64] image + 6 binary features
     __shared__ uint64_t sh_bits[IMG];
@@ -852,7 +917,31 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             bf[0] = (float)stable_frozen; bf[1] = 0.0f; bf[2] = 0.0f; bf[3] = 0.0f; bf[4] = 0.0f; bf[5] = 0.0f;
         }
     }
-    if (block_img != nullptr) {
+#ifdef BW_PROFILE
+    __syncthreads();
+    if (tid == 0) {   // cycle counts smuggled out through fields the profile run does not need
+        const long long t_end = clock64();
+        out[e].distance_to_targets[0] = (double)(prof_t[1] - prof_t[0]);   // load, placement, posed faces
+        out[e].distance_to_targets[1] = (double)(prof_t[2] - prof_t[1]);   // interfaces, contacts, adjacency
+        out[e].distance_to_targets[2] = (double)sh_prof_solve[0];          // solve, warp 0
+        out[e].distance_to_targets[3] = (double)sh_prof_solve[1];          // solve, warp 1
+        out[e].residual = (double)(prof_t[5] - prof_t[4]);                 // bookkeeping
+        out[e].residual_unfrozen = (double)(t_end - prof_t[5]);            // raster + lin_reward
+        out[e].reward = (float)(t_end - prof_t[0]);                        // total before the image write
+        // sub-phases of warp 1's solve and of the bookkeeping, packed as floats into the image buffer
+        if (block_img != nullptr) {
+            float *dbg = block_img + (size_t)e * IMG * IMG;
+            for (int q = 0; q < 6; q++) dbg[q] = (float)sh_prof_sub[1][q];
+            for (int q = 0; q < 3; q++) dbg[8 + q] = (float)sh_prof_book[q];
+        }
+    }
+#endif
+#ifdef BW_PROFILE
+    if (false)
+#else
+    if (block_img != nullptr)
+#endif
+    {
         float4 *dst = reinterpret_cast<float4 *>(block_img + (size_t)e * IMG * IMG);
 #pragma unroll 4
         for (int i = 0; i < IMG * IMG / 4 / 64; i++) {

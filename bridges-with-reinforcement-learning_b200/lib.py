@@ -16,7 +16,8 @@ BW_MAX_INTERFACES = 48
 BW_IMG = 64
 BW_ABI_VERSION = 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbridges_b200.so")
+LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                            "libbridges_b200.so")
 
 
 class bw_config(C.Structure):

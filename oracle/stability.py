@@ -296,12 +296,22 @@ def min_norm_forces(A, b, mu, schedule=RHO_SCHEDULE, max_newton=60):
 
             t = 1.0
             p = dphi(t)
-            for _ls in range(30):
-                if p >= -1e-12 * phi0:
-                    break
-                ts = t * phi0 / (phi0 - p)
-                t = min(max(ts, 0.05 * t), 0.95 * t)
-                p = dphi(t)
+            if p < -1e-12 * phi0:
+                # bracket the root of the piecewise-linear derivative (safeguarded regula falsi)
+                lo, plo, hi, phi = 0.0, phi0, 1.0, p
+                for _ls in range(20):
+                    w = hi - lo
+                    t = lo + w * plo / (plo - phi)
+                    t = min(max(t, lo + 0.1 * w), hi - 0.1 * w)
+                    p = dphi(t)
+                    if abs(p) <= 0.1 * phi0:
+                        break
+                    if p > 0.0:
+                        lo, plo = t, p
+                    else:
+                        hi, phi = t, p
+                if p < 0.0 and abs(p) > 0.1 * phi0 and lo > 0.0:
+                    t = lo
             y = y + t * d
             if t * math.sqrt(dd) <= 1e-15 * max(1.0, float(np.linalg.norm(y))):
                 break
@@ -312,6 +322,9 @@ def min_norm_forces(A, b, mu, schedule=RHO_SCHEDULE, max_newton=60):
             break
         if rprev is not None and abs(r - rprev) <= 1e-3 * r:
             status = "stagnated"
+            break
+        if rprev is not None and r >= 0.5 * rprev and r > 1e-3:
+            status = "stagnated"            # stalled far above the verdict threshold
             break
         rprev = r
     return f * nb, y * nb, r, status
