@@ -107,7 +107,7 @@ def cpu_env_rate(cores, budget_s, tower_height, max_steps, max_env_steps=10 ** 9
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = args.cpu_cores or os.cpu_count() or 1
     # one "step" of this arm = a bounded sample: every worker advances ~4 env steps
     per_step = 4 * cores
     total_env_steps = per_step * (args.steps + args.warmup)
@@ -201,6 +201,7 @@ def run_gpu(args, rank, local_rank, world):
     import torch.distributed as dist
     from bridges_b200 import lib as L
     from bridges_b200.envs.batched import BatchedAssemblyGym
+    from bridges_b200.sharding import max_over_ranks
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: bridges_b200 has no CPU fallback")
@@ -212,7 +213,7 @@ def run_gpu(args, rank, local_rank, world):
     # CPU baseline first (rank 0, N=1 only), before this process touches CUDA in earnest
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = args.cpu_cores or os.cpu_count() or 1
         t0 = time.perf_counter()
         rate, steps = cpu_env_rate(cores, args.cpu_budget, args.tower_height, args.max_steps)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -259,7 +260,8 @@ def run_gpu(args, rank, local_rank, world):
     wall0 = time.perf_counter()
     for i in range(K):
         acts = choose_actions(W + i)
-        flush.fill_(i & 0xff)                       # evict the 126 MB L2
+        if not args.no_flush:
+            flush.fill_(i & 0xff)                   # evict the 126 MB L2
         ev[i][0].record()
         env.step(acts, block_img=block_img, binary=binary)
         ev[i][1].record()
@@ -304,10 +306,7 @@ def run_gpu(args, rank, local_rank, world):
     d2h = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
 
     # ---- max over ranks
-    red = torch.tensor([t_dev, t_e2e, wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, wall = (float(x) for x in red.cpu())
+    t_dev, t_e2e, wall = max_over_ranks([t_dev, t_e2e, wall], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -360,6 +359,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline sampling")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-cores", type=int, default=0, help="CPU-arm worker processes (0 = all host cores)")
+    ap.add_argument("--no-flush", action="store_true", help="profiling only: skip the L2 flush between steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -433,8 +433,8 @@ struct Solver {
             if (r <= 1e-9) { status = 0; break; }
             if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
             // a feasible system loses two orders of magnitude per stage (rho x 100); a residual that
-            // stays above half its previous value and far above the verdict threshold has stalled at r*
-            if (rprev >= 0.0 && r >= 0.5 * rprev && r > 1e-3) { status = 1; break; }
+            // stays above 90% of its previous value and far above the verdict threshold has stalled at r*
+            if (rprev >= 0.0 && r >= 0.9 * rprev && r > 1e-3) { status = 1; break; }
             rprev = r;
         }
         r_out = r;

@@ -323,7 +323,7 @@ def min_norm_forces(A, b, mu, schedule=RHO_SCHEDULE, max_newton=60):
         if rprev is not None and abs(r - rprev) <= 1e-3 * r:
             status = "stagnated"
             break
-        if rprev is not None and r >= 0.5 * rprev and r > 1e-3:
+        if rprev is not None and r >= 0.9 * rprev and r > 1e-3:
             status = "stagnated"            # stalled far above the verdict threshold
             break
         rprev = r

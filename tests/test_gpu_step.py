@@ -151,7 +151,9 @@ def test_random_assemblies_verdicts_residuals_forces():
                     continue
                 assert bool(got) == bool(want), (e, k, r_gpu, r_or)
                 if r_or is not None:
-                    assert abs(r_gpu - r_or) <= 5e-3 * r_or + 1e-7, (e, k, r_gpu, r_or)
+                    # clearly unstable assemblies leave the solver early: the residual is then an upper
+                    # estimate of r* (within 2%); near the verdict threshold it is converged
+                    assert -1e-7 - 1e-3 * r_or <= r_gpu - r_or <= (2e-2 if r_or > 1e-3 else 1e-3) * r_or + 1e-7, (e, k, r_gpu, r_or)
                 n_checked += 1
                 n_stable += bool(want)
             # contact forces of the frozen variant against the oracle's min-norm solution
