@@ -1,0 +1,408 @@
+// K3: the rigid-block equilibrium solver, one warp per problem, everything in shared memory.
+//
+// Replaces `rbe_solve(assembly, mu, density, penalty=False)` as called by `is_stable_rbe`
+// (assembly_gym/assembly_gym/utils/stability.py:49-71).  Problem (2-D reduction):
+//     find f in K = prod {(fn, ft): |ft| <= mu fn}  with  A f = b,
+// three rows per free block.  Computed quantity: r = min_{f in K} ||A f - b|| (b normalised) and,
+// when r = 0, the minimum-norm f.  Method: proximal-point iteration on the
+// dual  d(y) = b.y - 1/2 ||P_K(A^T y)||^2  with rho = 1e2, 1e4, ...; every proximal sub-problem by
+// a semismooth Newton method:
+//     gradient   b - A P_K(A^T y) - (y - y_k)/rho
+//     Hessian    A J A^T + I/rho      (J = generalised Jacobian of the cone projection)
+//     direction  packed left-looking Cholesky, lane = row; the right-hand side rides along as one
+//                more row so that the forward substitution costs nothing
+//     step       bracketing search on the piecewise-linear derivative phi'(t)
+// Loops are deliberately kept rolled: the whole solver must stay resident in the instruction
+// cache (fully unrolled variants were 3x slower, profiles/README.md).
+#pragma once
+#include "bw_common.cuh"
+
+namespace bw {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NSCHED = 6;
+__constant__ double c_rho[NSCHED] = {1e2, 1e4, 1e6, 1e8, 1e8, 1e8};
+constexpr int MAX_NEWTON = 60;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ void warp_sum3(double &a, double &b, double &c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+        c += __shfl_xor_sync(FULL, c, o);
+    }
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// 1/sqrt(a) for a normal positive a: hardware approximation + one Newton step (~1e-13 relative),
+// ample for the Newton direction (the gradient, which fixes the solution, does not use it)
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    const double e = fma(-a * x, x, 1.0);
+    return fma(0.5 * x, e, x);
+}
+
+// projection of (gn, gt) onto the friction cone |ft| <= mu fn.
+// typ: 0 = polar cone (f = 0), 1 = interior, 2 = ray ft = +mu fn, 3 = ray ft = -mu fn
+__device__ __forceinline__ void project_cone(double gn, double gt, double mu, double inv_den, double &fn, double &ft,
+                                             int &typ) {
+    const double agt = fabs(gt);
+    if (agt <= mu * gn) {
+        fn = gn; ft = gt; typ = 1;
+    } else if (mu * agt <= -gn) {
+        fn = 0.0; ft = 0.0; typ = 0;
+    } else {
+        const double k = (gn + mu * agt) * inv_den;
+        fn = k;
+        if (gt > 0) { ft = mu * k; typ = 2; } else { ft = -mu * k; typ = 3; }
+    }
+}
+
+// TWO = false: at most 31 rows (10 free blocks + the right-hand side), one row per lane;
+// TWO = true: up to 49 rows, lanes also own row lane + 32.
+template <bool TWO>
+struct Solver {
+    // shared by the two problems of an environment, read-only here
+    const double *G;         // [nc][12]: per contact point the columns of A for body a (normal 0..2,
+                             //           tangent 3..5) and body b (6..8, 9..11); rows = Fx, Fz, torque/L0
+    const uint8_t *c_a, *c_b;   // bodies of a contact point (0 = floor)
+    const uint8_t *adj_ptr;     // [NBODY+1] CSR over bodies
+    const uint8_t *adj;         // contact | side << 7
+    // this problem
+    double *y, *yk, *d, *b, *g, *h, *f, *invd;
+    double *L;               // packed lower triangle, rows 0..m; row m carries the right-hand side
+    uint8_t *typ;
+    int8_t *rowbase;         // body -> first row or -1 (support)
+    uint8_t *freebody;       // free block index -> body
+    int m, nfree, nc, nitf, lane;
+    double mu, inv_den;
+    double flops;            // work estimate, see DESIGN.md section 6
+#ifdef BW_PROFILE
+    long long acc_t[6];      // grad, assemble, factor+solve, A^T d + dots, line search + update, residual
+#define BW_T0(name) const long long name = clock64()
+#define BW_ACC(i, t0) acc_t[i] += clock64() - (t0)
+#else
+#define BW_T0(name)
+#define BW_ACC(i, t0)
+#endif
+
+    // out = A^T v (lanes over contact points)
+    __device__ __forceinline__ void at_times(const double *v, double *out) const {
+        for (int c = lane; c < nc; c += 32) {
+            const double *Gc = G + c * 12;
+            const int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
+            double gn = 0.0, gt = 0.0;
+            if (ra >= 0) {
+                const double v0 = v[ra], v1 = v[ra + 1], v2 = v[ra + 2];
+                gn = Gc[0] * v0 + Gc[1] * v1 + Gc[2] * v2;
+                gt = Gc[3] * v0 + Gc[4] * v1 + Gc[5] * v2;
+            }
+            if (rb >= 0) {
+                const double v0 = v[rb], v1 = v[rb + 1], v2 = v[rb + 2];
+                gn += Gc[6] * v0 + Gc[7] * v1 + Gc[8] * v2;
+                gt += Gc[9] * v0 + Gc[10] * v1 + Gc[11] * v2;
+            }
+            out[2 * c] = gn;
+            out[2 * c + 1] = gt;
+        }
+    }
+
+    // f = P_K(g), typ
+    __device__ __forceinline__ void project_all() {
+        for (int c = lane; c < nc; c += 32) {
+            double fn, ft;
+            int t;
+            project_cone(g[2 * c], g[2 * c + 1], mu, inv_den, fn, ft, t);
+            f[2 * c] = fn;
+            f[2 * c + 1] = ft;
+            typ[c] = (uint8_t)t;
+        }
+    }
+
+    // (A f)_i
+    __device__ __forceinline__ double a_times_f_row(int i) const {
+        const int I = i / 3, k = i - 3 * I;
+        const int body = freebody[I];
+        double acc = 0.0;
+        for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
+            const int e = adj[q];
+            const int c = e & 0x7f;
+            const double *Gc = G + c * 12 + (e >> 7) * 6;
+            acc += Gc[k] * f[2 * c] + Gc[3 + k] * f[2 * c + 1];
+        }
+        return acc;
+    }
+
+    // H = A J A^T + I/rho into rows 0..m-1 of L.  Diagonal 3x3 tiles gather over the contacts of
+    // their block (lanes over free blocks); an off-diagonal tile belongs to exactly one interface
+    // (two contact points), so lanes over interfaces write it without accumulation conflicts.
+    __device__ void assemble_H(double inv_rho) {
+        const int nz = tri(m);
+        for (int q = lane; q < nz; q += 32) L[q] = 0.0;
+        __syncwarp();
+        const double isd = sqrt(inv_den);
+        if (lane < nfree) {
+            const int body = freebody[lane];
+            double a00 = inv_rho, a10 = 0, a11 = inv_rho, a20 = 0, a21 = 0, a22 = inv_rho;
+            for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
+                const int e = adj[q];
+                const int c = e & 0x7f;
+                const int tp = typ[c];
+                if (tp == 0) continue;
+                const double *Gi = G + c * 12 + (e >> 7) * 6;
+                double u0, u1, u2;
+                if (tp == 1) {
+                    u0 = Gi[3]; u1 = Gi[4]; u2 = Gi[5];
+                    a00 += u0 * u0; a10 += u1 * u0; a11 += u1 * u1; a20 += u2 * u0; a21 += u2 * u1; a22 += u2 * u2;
+                    u0 = Gi[0]; u1 = Gi[1]; u2 = Gi[2];
+                } else {
+                    const double sm = (tp == 2 ? mu : -mu);
+                    u0 = (Gi[0] + sm * Gi[3]) * isd; u1 = (Gi[1] + sm * Gi[4]) * isd; u2 = (Gi[2] + sm * Gi[5]) * isd;
+                }
+                a00 += u0 * u0; a10 += u1 * u0; a11 += u1 * u1; a20 += u2 * u0; a21 += u2 * u1; a22 += u2 * u2;
+            }
+            const int r0 = 3 * lane;
+            double *p = L + tri(r0) + r0;
+            p[0] = a00;
+            p += r0 + 1;
+            p[0] = a10; p[1] = a11;
+            p += r0 + 2;
+            p[0] = a20; p[1] = a21; p[2] = a22;
+        }
+        for (int k = lane; k < nitf; k += 32) {
+            const int c0 = 2 * k;
+            const int ra = rowbase[c_a[c0]], rb = rowbase[c_b[c0]];
+            if (ra < 0 || rb < 0) continue;
+            double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int c = c0 + q;
+                const int tp = typ[c];
+                if (tp == 0) continue;
+                const double *Ga = G + c * 12, *Gb = Ga + 6;
+                double u0, u1, u2, w0, w1, w2;
+                if (tp == 1) {
+                    u0 = Gb[3]; u1 = Gb[4]; u2 = Gb[5]; w0 = Ga[3]; w1 = Ga[4]; w2 = Ga[5];
+                    t00 += u0 * w0; t01 += u0 * w1; t02 += u0 * w2;
+                    t10 += u1 * w0; t11 += u1 * w1; t12 += u1 * w2;
+                    t20 += u2 * w0; t21 += u2 * w1; t22 += u2 * w2;
+                    u0 = Gb[0]; u1 = Gb[1]; u2 = Gb[2]; w0 = Ga[0]; w1 = Ga[1]; w2 = Ga[2];
+                } else {
+                    const double sm = (tp == 2 ? mu : -mu);
+                    u0 = (Gb[0] + sm * Gb[3]) * isd; u1 = (Gb[1] + sm * Gb[4]) * isd; u2 = (Gb[2] + sm * Gb[5]) * isd;
+                    w0 = (Ga[0] + sm * Ga[3]) * isd; w1 = (Ga[1] + sm * Ga[4]) * isd; w2 = (Ga[2] + sm * Ga[5]) * isd;
+                }
+                t00 += u0 * w0; t01 += u0 * w1; t02 += u0 * w2;
+                t10 += u1 * w0; t11 += u1 * w1; t12 += u1 * w2;
+                t20 += u2 * w0; t21 += u2 * w1; t22 += u2 * w2;
+            }
+            double *p = L + tri(rb) + ra;          // rb > ra: rows of the later block
+            p[0] = t00; p[1] = t01; p[2] = t02;
+            p += rb + 1;
+            p[0] = t10; p[1] = t11; p[2] = t12;
+            p += rb + 2;
+            p[0] = t20; p[1] = t21; p[2] = t22;
+        }
+        __syncwarp();
+    }
+
+    // Left-looking Cholesky of rows 0..m-1 with row m (the gradient) carried along, then the
+    // back substitution: d = H^-1 grad.
+    __device__ void factor_and_solve(double inv_rho) {
+        const int nrows = m + 1;
+        const int i0 = lane, i1 = lane + 32;
+        double *row0 = L + tri(i0 < nrows ? i0 : 0);       // idle lanes read row 0 (results unused)
+        double *row1 = L + tri((TWO && i1 < nrows) ? i1 : 0);
+        for (int j = 0; j < m; j++) {
+            const double *rowj = L + tri(j);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double c0 = 0.0, c1 = 0.0;
+            int p = 0;
+            for (; p + 3 < j; p += 4) {
+                const double l0 = rowj[p], l1 = rowj[p + 1], l2 = rowj[p + 2], l3 = rowj[p + 3];
+                a0 += row0[p] * l0; a1 += row0[p + 1] * l1; a2 += row0[p + 2] * l2; a3 += row0[p + 3] * l3;
+                if (TWO) { c0 += row1[p] * l0 + row1[p + 2] * l2; c1 += row1[p + 1] * l1 + row1[p + 3] * l3; }
+            }
+            for (; p < j; p++) {
+                const double l0 = rowj[p];
+                a0 += row0[p] * l0;
+                if (TWO) c0 += row1[p] * l0;
+            }
+            const double s0 = row0[j] - ((a0 + a1) + (a2 + a3));
+            const double s1 = TWO ? row1[j] - (c0 + c1) : 0.0;
+            double piv = __shfl_sync(FULL, (!TWO || j < 32) ? s0 : s1, j & 31);
+            if (!(piv > 1e-300)) piv = inv_rho;
+            const double inv = fast_rsqrt(piv);
+            if (i0 > j && i0 < nrows) row0[j] = s0 * inv;
+            if (TWO && i1 > j && i1 < nrows) row1[j] = s1 * inv;
+            if (lane == 0) invd[j] = inv;
+            __syncwarp();
+        }
+        // row m now holds z = L^-1 grad; back substitution L^T d = z
+        const double *rowm = L + tri(m);
+        double z0 = (i0 < m) ? rowm[i0] : 0.0;
+        double z1 = (TWO && i1 < m) ? rowm[i1] : 0.0;
+        for (int j = m - 1; j >= 0; j--) {
+            const double dj = __shfl_sync(FULL, (!TWO || j < 32) ? z0 : z1, j & 31) * invd[j];
+            const double *rowj = L + tri(j);
+            if (i0 == j) z0 = dj;
+            else if (i0 < j) z0 -= rowj[i0] * dj;
+            if (TWO) {
+                if (i1 == j) z1 = dj;
+                else if (i1 < j) z1 -= rowj[i1] * dj;
+            }
+        }
+        if (i0 < m) d[i0] = z0;
+        if (TWO && i1 < m) d[i1] = z1;
+        __syncwarp();
+    }
+
+    // ||b - A P_K(A^T y)|| (b is normalised); leaves g = A^T y, f = P_K(g)
+    __device__ double residual() {
+        at_times(y, g);
+        __syncwarp();
+        project_all();
+        __syncwarp();
+        double acc = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            const double r = b[i] - a_times_f_row(i);
+            acc += r * r;
+        }
+        return sqrt(warp_sum(acc));
+    }
+
+    // sum over contact points of P_K(g + t h) . h
+    __device__ __forceinline__ double fdoth(double t) {
+        double fh = 0.0;
+        for (int c = lane; c < nc; c += 32) {
+            double fn, ft;
+            int tp;
+            const double hn = h[2 * c], ht = h[2 * c + 1];
+            project_cone(g[2 * c] + t * hn, g[2 * c + 1] + t * ht, mu, inv_den, fn, ft, tp);
+            fh += fn * hn + ft * ht;
+        }
+        flops += 20.0 * nc;
+        return warp_sum(fh);
+    }
+
+    // returns status: 0 feasible (r <= 1e-9), 1 stalled at r* > 0, 2 not converged
+    __device__ int solve(double &r_out, int &iters_out) {
+        for (int i = lane; i < m; i += 32) y[i] = 0.0;
+        for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
+        __syncwarp();
+        flops = 0.0;
+#ifdef BW_PROFILE
+        for (int q = 0; q < 6; q++) acc_t[q] = 0;
+#endif
+        double *rhs = L + tri(m);
+        double rprev = -1.0, r = 1.0;
+        int status = 2, iters = 0;
+        for (int k = 0; k < NSCHED; k++) {
+            const double inv_rho = 1.0 / c_rho[k];
+            for (int i = lane; i < m; i += 32) yk[i] = y[i];
+            __syncwarp();
+            for (int it = 0; it < MAX_NEWTON; it++) {
+                BW_T0(t_a);
+                project_all();
+                __syncwarp();
+                double gn2 = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    const double gr = b[i] - a_times_f_row(i) - (y[i] - yk[i]) * inv_rho;
+                    d[i] = gr;                     // kept for the dot products below
+                    gn2 += gr * gr;
+                }
+                gn2 = warp_sum(gn2);
+                BW_ACC(0, t_a);
+                if (gn2 <= 1e-20) break;
+                BW_T0(t_b);
+                assemble_H(inv_rho);               // zero-fills rows 0..m-1, leaves row m alone
+                for (int i = lane; i < m; i += 32) rhs[i] = d[i];
+                double gd = 0.0;
+                // keep the gradient in registers: d[] is overwritten by the solve
+                const double gr0 = (lane < m) ? d[lane] : 0.0;
+                const double gr1 = (TWO && lane + 32 < m) ? d[lane + 32] : 0.0;
+                __syncwarp();
+                BW_ACC(1, t_b);
+                BW_T0(t_c);
+                factor_and_solve(inv_rho);
+                BW_ACC(2, t_c);
+                BW_T0(t_d);
+                at_times(d, h);
+                __syncwarp();
+                // phi'(t) = grad.d + f.h - P_K(g + t h).h - t d.d / rho   (piecewise linear, decreasing)
+                double dd = 0.0, fh0 = 0.0;
+                {
+                    const double d0 = (lane < m) ? d[lane] : 0.0;
+                    gd = gr0 * d0;
+                    dd = d0 * d0;
+                    if (TWO) {
+                        const double d1 = (lane + 32 < m) ? d[lane + 32] : 0.0;
+                        gd += gr1 * d1;
+                        dd += d1 * d1;
+                    }
+                    for (int c = lane; c < 2 * nc; c += 32) fh0 += f[c] * h[c];
+                }
+                warp_sum3(gd, dd, fh0);
+                BW_ACC(3, t_d);
+                BW_T0(t_e);
+                const double phi0 = gd;
+                if (!(phi0 > 1e-30)) break;
+                const double base = phi0 + fh0;
+                double t = 1.0;
+                double p = base - fdoth(1.0) - dd * inv_rho;
+                if (p < -1e-12 * phi0) {
+                    // bracket the root with a safeguarded regula falsi until |phi'| <= 0.1 phi'(0)
+                    double lo = 0.0, plo = phi0, hi = 1.0, phi = p;
+                    for (int ls = 0; ls < 20; ls++) {
+                        const double w = hi - lo;
+                        t = lo + w * plo / (plo - phi);
+                        t = fmin(fmax(t, lo + 0.1 * w), hi - 0.1 * w);
+                        p = base - fdoth(t) - t * dd * inv_rho;
+                        if (fabs(p) <= 0.1 * phi0) break;
+                        if (p > 0.0) { lo = t; plo = p; } else { hi = t; phi = p; }
+                    }
+                    if (p < 0.0 && fabs(p) > 0.1 * phi0 && lo > 0.0) t = lo;
+                }
+                double yy = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    const double yn = y[i] + t * d[i];
+                    y[i] = yn;
+                    yy = fmax(yy, fabs(yn));
+                }
+                for (int c = lane; c < 2 * nc; c += 32) g[c] += t * h[c];   // A^T (y + t d)
+                __syncwarp();
+                BW_ACC(4, t_e);
+                iters++;
+                flops += (double)m * m * m / 3.0 + 2.0 * m * m + 156.0 * nc + 12.0 * m;
+                // no representable progress any more (|t d| below the rounding of y)
+                const double ymax = warp_max(yy);
+                if (t * t * dd <= 1e-30 * fmax(1.0, ymax * ymax)) break;
+            }
+            BW_T0(t_f);
+            r = residual();
+            BW_ACC(5, t_f);
+            if (r <= 1e-9) { status = 0; break; }
+            if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
+            // a feasible system loses two orders of magnitude per stage (rho x 100); a residual that
+            // stays above 90% of its previous value and far above the verdict threshold has stalled at r*
+            if (rprev >= 0.0 && r >= 0.9 * rprev && r > 1e-3) { status = 1; break; }
+            rprev = r;
+        }
+        r_out = r;
+        iters_out = iters;
+        return status;
+    }
+};
+
+}  // namespace bw

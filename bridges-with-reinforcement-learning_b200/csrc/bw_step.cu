@@ -15,6 +15,7 @@
 // problem lives in the shared memory of its warp; reductions are warp shuffles.
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
+#include "bw_solver.cuh"
 
 namespace bw {
 
@@ -26,10 +27,6 @@ __constant__ uint8_t c_tri_i[NB * (NB + 1) / 2];
 __constant__ uint8_t c_tri_j[NB * (NB + 1) / 2];
 
 constexpr int NPAIR = NBODY * (NBODY - 1) / 2;  // 136
-constexpr int NSCHED = 6;
-__constant__ double c_rho[NSCHED] = {1e2, 1e4, 1e6, 1e8, 1e8, 1e8};
-constexpr int MAX_NEWTON = 60;
-constexpr unsigned FULL = 0xffffffffu;
 
 void upload_step_tables() {
     uint8_t pa[NPAIR], pb[NPAIR], ti[NB * (NB + 1) / 2], tj[NB * (NB + 1) / 2];
@@ -53,7 +50,7 @@ struct Layout {
 };
 
 struct ProbOff {  // offsets inside one problem block
-    int y, yk, rhs, d, b, g, h, f, invd, H, typ, rowbase, freebody, size;
+    int y, yk, d, b, g, h, f, invd, H, typ, rowbase, freebody, size;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -63,7 +60,6 @@ __host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
     int p = 0;
     o.y = p; p += MM * 8;
     o.yk = p; p += MM * 8;
-    o.rhs = p; p += MM * 8;
     o.d = p; p += MM * 8;
     o.b = p; p += MM * 8;
     o.invd = p; p += MM * 8;
@@ -85,7 +81,7 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf) {
     Layout L;
     L.MM = 3 * max_blocks;
     L.MC = 2 * max_itf;
-    L.HS = L.MM * (L.MM + 1) / 2;
+    L.HS = (L.MM + 1) * (L.MM + 2) / 2;      // packed rows 0..MM (the last one carries the right-hand side)
     int p = 0;
     L.pose = p; p += NB * (int)sizeof(Pose) + align16(NB);          // poses + shape ids
     L.body = p; p += NBODY * BODY_DOUBLES * 8;
@@ -107,343 +103,8 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf) {
 
 int step_smem_bytes(int max_blocks, int max_itf) { return make_layout(max_blocks, max_itf).total; }
 
-// ------------------------------------------------------------------ small device helpers
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
-
-// projection of (gn, gt) onto the friction cone |ft| <= mu fn.
-// typ: 0 = polar cone (f = 0), 1 = interior, 2 = ray ft = +mu fn, 3 = ray ft = -mu fn
-__device__ __forceinline__ void project_cone(double gn, double gt, double mu, double inv_den, double &fn, double &ft,
-                                             int &typ) {
-    double agt = fabs(gt);
-    if (agt <= mu * gn) {
-        fn = gn; ft = gt; typ = 1;
-    } else if (mu * agt <= -gn) {
-        fn = 0.0; ft = 0.0; typ = 0;
-    } else {
-        double k = (gn + mu * agt) * inv_den;
-        fn = k;
-        if (gt > 0) { ft = mu * k; typ = 2; } else { ft = -mu * k; typ = 3; }
-    }
-}
-
-struct Solver {
-    // shared, read-only during the solve
-    const double *G;         // [nc][12]
-    const uint8_t *c_a, *c_b;
-    const uint8_t *adj_ptr;  // [NBODY+1]
-    const uint8_t *adj;      // entries: contact | side << 7
-    // per problem
-    double *y, *yk, *rhs, *d, *b, *g, *h, *f, *invd, *H;
-    uint8_t *typ;
-    int8_t *rowbase;
-    uint8_t *freebody;
-    int m, nfree, nc, lane;
-    double mu, inv_den;
-
-    // g = A^T v for every contact point (lanes over contacts)
-    __device__ __forceinline__ void at_times(const double *v, double *out) const {
-        for (int c = lane; c < nc; c += 32) {
-            const double *Gc = G + c * 12;
-            int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
-            double gn = 0.0, gt = 0.0;
-            if (ra >= 0) {
-                double v0 = v[ra], v1 = v[ra + 1], v2 = v[ra + 2];
-                gn += Gc[0] * v0 + Gc[1] * v1 + Gc[2] * v2;
-                gt += Gc[3] * v0 + Gc[4] * v1 + Gc[5] * v2;
-            }
-            if (rb >= 0) {
-                double v0 = v[rb], v1 = v[rb + 1], v2 = v[rb + 2];
-                gn += Gc[6] * v0 + Gc[7] * v1 + Gc[8] * v2;
-                gt += Gc[9] * v0 + Gc[10] * v1 + Gc[11] * v2;
-            }
-            out[2 * c] = gn;
-            out[2 * c + 1] = gt;
-        }
-    }
-
-    // f = P_K(g), typ
-    __device__ __forceinline__ void project_all() {
-        for (int c = lane; c < nc; c += 32) {
-            double fn, ft;
-            int t;
-            project_cone(g[2 * c], g[2 * c + 1], mu, inv_den, fn, ft, t);
-            f[2 * c] = fn;
-            f[2 * c + 1] = ft;
-            typ[c] = (uint8_t)t;
-        }
-    }
-
-    // (A f)_i for row i
-    __device__ __forceinline__ double a_times_f_row(int i) const {
-        int I = i / 3, k = i - 3 * I;
-        int body = freebody[I];
-        double acc = 0.0;
-        for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
-            int e = adj[q];
-            int c = e & 0x7f, side = e >> 7;
-            const double *Gc = G + c * 12 + side * 6;
-            acc += Gc[k] * f[2 * c] + Gc[3 + k] * f[2 * c + 1];
-        }
-        return acc;
-    }
-
-    // H = A J A^T + I/rho (packed lower)
-    __device__ void assemble_H(double inv_rho) {
-        int ntile = (nfree * (nfree + 1)) >> 1;
-        const double isd = sqrt(inv_den);
-        for (int t = lane; t < ntile; t += 32) {
-            int I = c_tri_i[t], J = c_tri_j[t];
-            int bi = freebody[I], bj = freebody[J];
-            double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
-            for (int q = adj_ptr[bi]; q < adj_ptr[bi + 1]; q++) {
-                int e = adj[q];
-                int c = e & 0x7f, side = e >> 7;
-                int other = side ? c_a[c] : c_b[c];
-                int tp = typ[c];
-                if (tp == 0) continue;
-                const double *Gi = G + c * 12 + side * 6;
-                const double *Gj;
-                if (I == J) Gj = Gi;
-                else if (other == bj) Gj = G + c * 12 + (1 - side) * 6;
-                else continue;
-                if (tp == 1) {
-                    // both columns
-#pragma unroll
-                    for (int col = 0; col < 2; col++) {
-                        double u0 = Gi[3 * col], u1 = Gi[3 * col + 1], u2 = Gi[3 * col + 2];
-                        double w0 = Gj[3 * col], w1 = Gj[3 * col + 1], w2 = Gj[3 * col + 2];
-                        a00 += u0 * w0; a01 += u0 * w1; a02 += u0 * w2;
-                        a10 += u1 * w0; a11 += u1 * w1; a12 += u1 * w2;
-                        a20 += u2 * w0; a21 += u2 * w1; a22 += u2 * w2;
-                    }
-                } else {
-                    double sm = (tp == 2 ? mu : -mu);
-                    double u0 = (Gi[0] + sm * Gi[3]) * isd, u1 = (Gi[1] + sm * Gi[4]) * isd, u2 = (Gi[2] + sm * Gi[5]) * isd;
-                    double w0 = (Gj[0] + sm * Gj[3]) * isd, w1 = (Gj[1] + sm * Gj[4]) * isd, w2 = (Gj[2] + sm * Gj[5]) * isd;
-                    a00 += u0 * w0; a01 += u0 * w1; a02 += u0 * w2;
-                    a10 += u1 * w0; a11 += u1 * w1; a12 += u1 * w2;
-                    a20 += u2 * w0; a21 += u2 * w1; a22 += u2 * w2;
-                }
-            }
-            int r0 = 3 * I, c0 = 3 * J;
-            if (I == J) {
-                H[tri(r0) + c0] = a00 + inv_rho;
-                H[tri(r0 + 1) + c0] = a10; H[tri(r0 + 1) + c0 + 1] = a11 + inv_rho;
-                H[tri(r0 + 2) + c0] = a20; H[tri(r0 + 2) + c0 + 1] = a21; H[tri(r0 + 2) + c0 + 2] = a22 + inv_rho;
-            } else {
-                H[tri(r0) + c0] = a00; H[tri(r0) + c0 + 1] = a01; H[tri(r0) + c0 + 2] = a02;
-                H[tri(r0 + 1) + c0] = a10; H[tri(r0 + 1) + c0 + 1] = a11; H[tri(r0 + 1) + c0 + 2] = a12;
-                H[tri(r0 + 2) + c0] = a20; H[tri(r0 + 2) + c0 + 1] = a21; H[tri(r0 + 2) + c0 + 2] = a22;
-            }
-        }
-    }
-
-    // Solve H d = rhs by a left-looking Cholesky factorisation in the packed lower-triangular
-    // storage: lane i owns row i (and row i + 32 when m > 32).  Column j costs one dot product of
-    // the owned row with row j (a broadcast read), so the inner loop is LDS + LDS + DFMA with no
-    // stores; the loops are kept rolled on purpose -- the whole solver has to stay resident in the
-    // instruction cache, straight-line unrolled variants ran 3x slower.
-    __device__ void chol_solve(double inv_rho) {
-        const int i0 = lane, i1 = lane + 32;
-        const bool two = m > 32;
-        // lanes without a row read row 0 (results unused) so that every access stays inside H
-        double *row0 = H + tri(i0 < m ? i0 : 0);
-        double *row1 = H + tri(i1 < m ? i1 : 0);
-        for (int j = 0; j < m; j++) {
-            const double *rowj = H + tri(j);
-            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
-            int p = 0;
-            if (!two) {
-                for (; p + 1 < j; p += 2) {
-                    a0 += row0[p] * rowj[p];
-                    a1 += row0[p + 1] * rowj[p + 1];
-                }
-                if (p < j) a0 += row0[p] * rowj[p];
-            } else {
-                for (; p < j; p++) {
-                    const double l = rowj[p];
-                    a0 += row0[p] * l;
-                    c0 += (i1 < m) ? row1[p] * l : 0.0;
-                }
-            }
-            const double s0 = ((i0 >= j && i0 < m) ? row0[j] : 0.0) - (a0 + a1);
-            const double s1 = (two && i1 < m) ? row1[j] - (c0 + c1) : 0.0;
-            double piv = __shfl_sync(FULL, (j < 32) ? s0 : s1, j & 31);
-            if (!(piv > 1e-300)) piv = inv_rho;
-            const double inv = rsqrt(piv);
-            if (i0 > j && i0 < m) row0[j] = s0 * inv;
-            if (two && i1 > j && i1 < m) row1[j] = s1 * inv;
-            if (lane == 0) invd[j] = inv;
-            __syncwarp();
-        }
-        // forward substitution L z = rhs, then back substitution L^T d = z
-        double z0 = (i0 < m) ? rhs[i0] : 0.0;
-        double z1 = (two && i1 < m) ? rhs[i1] : 0.0;
-        for (int j = 0; j < m; j++) {
-            const double zj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
-            if (i0 == j) z0 = zj;
-            else if (i0 > j && i0 < m) z0 -= row0[j] * zj;
-            if (two) {
-                if (i1 == j) z1 = zj;
-                else if (i1 > j && i1 < m) z1 -= row1[j] * zj;
-            }
-        }
-        for (int j = m - 1; j >= 0; j--) {
-            const double dj = __shfl_sync(FULL, (j < 32) ? z0 : z1, j & 31) * invd[j];
-            const double *rowj = H + tri(j);
-            if (i0 == j) z0 = dj;
-            else if (i0 < j) z0 -= rowj[i0] * dj;
-            if (two) {
-                if (i1 == j) z1 = dj;
-                else if (i1 < j) z1 -= rowj[i1] * dj;
-            }
-        }
-        if (i0 < m) d[i0] = z0;
-        if (two && i1 < m) d[i1] = z1;
-        __syncwarp();
-    }
-
-    // relative residual ||b - A P_K(A^T y)|| (b is normalised)
-    __device__ double residual() {
-        at_times(y, g);
-        __syncwarp();
-        project_all();
-        __syncwarp();
-        double acc = 0.0;
-        for (int i = lane; i < m; i += 32) {
-            double r = b[i] - a_times_f_row(i);
-            acc += r * r;
-        }
-        return sqrt(warp_sum(acc));
-    }
-
-    __device__ __forceinline__ double dphi(double t, double bd, double yd, double dd, double inv_rho) {
-        double fh = 0.0;
-        for (int c = lane; c < nc; c += 32) {
-            double fn, ft;
-            int tp;
-            project_cone(g[2 * c] + t * h[2 * c], g[2 * c + 1] + t * h[2 * c + 1], mu, inv_den, fn, ft, tp);
-            fh += fn * h[2 * c] + ft * h[2 * c + 1];
-        }
-        fh = warp_sum(fh);
-        flops += 20.0 * nc;
-        return bd - fh - (yd + t * dd) * inv_rho;
-    }
-
-    // returns status: 0 feasible (r <= 1e-9), 1 stagnated at r* > 0, 2 not converged
-    // work estimate (flops) of the last solve: per Newton step one Cholesky (m^3/3), two
-    // triangular solves (2 m^2), the assembly of H (54 flops per contact column pair), two sparse
-    // products with A (24 nc each) and per line-search evaluation one cone projection sweep
-    double flops = 0.0;
-#ifdef BW_PROFILE
-    long long acc_t[6] = {0, 0, 0, 0, 0, 0};   // grad, assemble, cholesky, dots+h, line search, residual
-#define BW_ACC(i, t0) acc_t[i] += clock64() - (t0)
-#define BW_T0(name) const long long name = clock64()
-#else
-#define BW_ACC(i, t0)
-#define BW_T0(name)
-#endif
-
-    __device__ int solve(double &r_out, int &iters_out) {
-        for (int i = lane; i < m; i += 32) y[i] = 0.0;
-        for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
-        __syncwarp();
-        double rprev = -1.0, r = 1.0;
-        int status = 2, iters = 0;
-        for (int k = 0; k < NSCHED; k++) {
-            const double rho = c_rho[k], inv_rho = 1.0 / rho;
-            for (int i = lane; i < m; i += 32) yk[i] = y[i];
-            __syncwarp();
-            for (int it = 0; it < MAX_NEWTON; it++) {
-                BW_T0(t_a);
-                project_all();
-                __syncwarp();
-                double acc = 0.0;
-                for (int i = lane; i < m; i += 32) {
-                    double gr = b[i] - a_times_f_row(i) - (y[i] - yk[i]) * inv_rho;
-                    rhs[i] = gr;
-                    acc += gr * gr;
-                }
-                double gn2 = warp_sum(acc);
-                BW_ACC(0, t_a);
-                if (gn2 <= 1e-20) break;
-                BW_T0(t_b);
-                assemble_H(inv_rho);
-                __syncwarp();
-                BW_ACC(1, t_b);
-                BW_T0(t_c);
-                chol_solve(inv_rho);
-                BW_ACC(2, t_c);
-                BW_T0(t_d);
-                at_times(d, h);
-                __syncwarp();
-                // dots for the line search
-                double dd = 0.0, bd = 0.0, yd = 0.0, gd = 0.0, yy = 0.0;
-                for (int i = lane; i < m; i += 32) {
-                    double di = d[i];
-                    dd += di * di;
-                    bd += b[i] * di;
-                    yd += (y[i] - yk[i]) * di;
-                    gd += rhs[i] * di;
-                    yy += y[i] * y[i];
-                }
-                dd = warp_sum(dd); bd = warp_sum(bd); yd = warp_sum(yd); gd = warp_sum(gd); yy = warp_sum(yy);
-                const double phi0 = gd;
-                BW_ACC(3, t_d);
-                if (!(phi0 > 1e-30)) break;
-                BW_T0(t_e);
-                // derivative of the concave dual along d: phi'(t) = b.d - P_K(g + t h).h - (yd + t dd)/rho,
-                // piecewise linear and decreasing.  Accept t = 1 if still ascending there, otherwise
-                // bracket the root with a safeguarded regula falsi until |phi'| <= 0.1 phi'(0).
-                double t = 1.0;
-                double p = dphi(t, bd, yd, dd, inv_rho);
-                if (p < -1e-12 * phi0) {
-                    double lo = 0.0, plo = phi0, hi = 1.0, phi = p;
-                    for (int ls = 0; ls < 20; ls++) {
-                        const double w = hi - lo;
-                        t = lo + w * plo / (plo - phi);
-                        t = fmin(fmax(t, lo + 0.1 * w), hi - 0.1 * w);
-                        p = dphi(t, bd, yd, dd, inv_rho);
-                        if (fabs(p) <= 0.1 * phi0) break;
-                        if (p > 0.0) { lo = t; plo = p; } else { hi = t; phi = p; }
-                    }
-                    if (p < 0.0 && fabs(p) > 0.1 * phi0 && lo > 0.0) t = lo;
-                }
-                for (int i = lane; i < m; i += 32) y[i] += t * d[i];
-                for (int c = lane; c < 2 * nc; c += 32) g[c] += t * h[c];   // A^T (y + t d)
-                __syncwarp();
-                BW_ACC(4, t_e);
-                iters++;
-                flops += (double)m * m * m / 3.0 + 2.0 * m * m + 54.0 * 2.0 * nc + 48.0 * nc + 12.0 * m;
-                if (t * sqrt(dd) <= 1e-15 * fmax(1.0, sqrt(yy))) break;
-            }
-            BW_T0(t_f);
-            r = residual();
-            BW_ACC(5, t_f);
-            if (r <= 1e-9) { status = 0; break; }
-            if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
-            // a feasible system loses two orders of magnitude per stage (rho x 100); a residual that
-            // stays above 90% of its previous value and far above the verdict threshold has stalled at r*
-            if (rprev >= 0.0 && r >= 0.9 * rprev && r > 1e-3) { status = 1; break; }
-            rprev = r;
-        }
-        r_out = r;
-        iters_out = iters;
-        return status;
-    }
-};
-
 // ------------------------------------------------------------------ the kernel
+template <bool TWO>
 __global__ void __launch_bounds__(64)
 step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
             bw_step_out *__restrict__ out, float *__restrict__ block_img, float *__restrict__ binary,
@@ -711,23 +372,24 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         const uint32_t vmask = (warp == 0) ? smask : (n > 0 ? (smask & ~(1u << (n - 1))) : smask);
         const ProbOff po = prob_layout(L.MM, L.MC, L.HS);
         unsigned char *pb = smem + L.prob[warp];
-        Solver S;
+        Solver<TWO> S;
         S.G = s_G; S.c_a = s_ca; S.c_b = s_cb; S.adj_ptr = s_adj_ptr; S.adj = s_adj;
         S.y = reinterpret_cast<double *>(pb + po.y);
         S.yk = reinterpret_cast<double *>(pb + po.yk);
-        S.rhs = reinterpret_cast<double *>(pb + po.rhs);
         S.d = reinterpret_cast<double *>(pb + po.d);
         S.b = reinterpret_cast<double *>(pb + po.b);
         S.g = reinterpret_cast<double *>(pb + po.g);
         S.h = reinterpret_cast<double *>(pb + po.h);
         S.f = reinterpret_cast<double *>(pb + po.f);
         S.invd = reinterpret_cast<double *>(pb + po.invd);
-        S.H = reinterpret_cast<double *>(pb + po.H);
+        S.L = reinterpret_cast<double *>(pb + po.H);
         S.typ = pb + po.typ;
         S.rowbase = reinterpret_cast<int8_t *>(pb + po.rowbase);
         S.freebody = pb + po.freebody;
         S.lane = lane;
         S.nc = nc;
+        S.nitf = overflow ? 0 : nitf;
+        S.flops = 0.0;
         S.mu = P.mu[e];
         S.inv_den = 1.0 / (1.0 + S.mu * S.mu);
         // free blocks -> rows
@@ -765,7 +427,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
 #ifdef BW_PROFILE
         if (lane == 0) {
             sh_prof_solve[warp] = clock64() - prof_t[2];
-            for (int q = 0; q < 6; q++) sh_prof_sub[warp][q] = S.acc_t[q];
+            for (int q = 0; q < 6; q++) sh_prof_sub[warp][q] = (nitf > 0 && nfree > 0 && !overflow) ? S.acc_t[q] : 0;
         }
 #endif
         if (lane == 0) {
@@ -956,12 +618,19 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
 void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
                  float *d_block_img, float *d_binary, bw_interface *d_itf, int32_t *d_nitf, int variant,
                  int smem_bytes, cudaStream_t stream) {
-    step_kernel<<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf, d_nitf,
-                                                 variant);
+    // 3 rows per free block + the right-hand side row: one row per lane up to 10 blocks
+    if (3 * P.max_blocks + 1 <= 32)
+        step_kernel<false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf,
+                                                            d_nitf, variant);
+    else
+        step_kernel<true><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf,
+                                                           d_nitf, variant);
 }
 
 cudaError_t configure_step(int smem_bytes) {
-    return cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
 }  // namespace bw
