@@ -283,30 +283,42 @@ def run_gpu(args, rank, local_rank, world):
     fp64 = C.c_double(0.0)
     lib.bw_fp64_peak_gflops(h, C.byref(fp64))
 
-    # ---- end-to-end loop: host actions in, host results (records, images, binary) out
+    # ---- end-to-end loops through the host entry point bw_step_host: pinned host actions in,
+    # host results out.  (a) headline: step records + the raster as the reference's `_get_obs` /
+    # `render_blocks_2d` deliver it (one byte per pixel, bool) + binary features;
+    # (b) the same with the float32 [E,1,64,64] tensor of get_state_features copied to the host too.
     h_act = torch.empty(E * dt["action"].itemsize, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(E * dt["step_out"].itemsize, dtype=torch.uint8).pin_memory()
+    h_u8 = torch.empty((E, 64, 64), dtype=torch.uint8).pin_memory()
     h_img = torch.empty((E, 1, 64, 64), dtype=torch.float32).pin_memory()
     h_bin = torch.empty((E, 6), dtype=torch.float32).pin_memory()
     Ke = min(K, args.e2e_steps)
-    barrier()
-    t_e2e = 0.0
-    for i in range(Ke):
-        acts = choose_actions(W + K + i)
-        h_act.copy_(acts)                           # the policy's actions arrive on the host
-        flush.fill_(i & 0xff)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rc = lib.bw_step_host(h, h_act.data_ptr(), None, h_out.data_ptr(), h_img.data_ptr(), h_bin.data_ptr())
-        t_e2e += time.perf_counter() - t0
-        L.check(lib, h, rc)
-        env.reset_done()
-    barrier()
+
+    def e2e_loop(obs, seed0):
+        barrier()
+        total = 0.0
+        for i in range(Ke):
+            acts = choose_actions(seed0 + i)
+            h_act.copy_(acts)                       # the policy's actions arrive on the host
+            if not args.no_flush:
+                flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = lib.bw_step_host(h, h_act.data_ptr(), None, h_out.data_ptr(), C.byref(obs))
+            total += time.perf_counter() - t0
+            L.check(lib, h, rc)
+            env.reset_done()
+        barrier()
+        return total
+
+    t_e2e = e2e_loop(L.bw_obs_out(None, h_u8.data_ptr(), h_bin.data_ptr()), W + K)
+    t_e2e_f32 = e2e_loop(L.bw_obs_out(h_img.data_ptr(), None, h_bin.data_ptr()), W + K + Ke)
     h2d = E * dt["action"].itemsize
-    d2h = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
+    d2h = E * (dt["step_out"].itemsize + 64 * 64 + 6 * 4)
+    d2h_f32 = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
 
     # ---- max over ranks
-    t_dev, t_e2e, wall = max_over_ranks([t_dev, t_e2e, wall], device=dev)
+    t_dev, t_e2e, t_e2e_f32, wall = max_over_ranks([t_dev, t_e2e, t_e2e_f32, wall], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,7 +334,9 @@ def run_gpu(args, rank, local_rank, world):
         "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
         "clocks": clocks,
         "e2e": {"value": world * E * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "api": "bw_step_host (pinned host actions in; step records, f32 images, binary out)"},
+                "steps": Ke, "api": "bw_step_host: pinned host actions in; step records + u8 raster [E,64,64] "
+                                    "(render_blocks_2d's bool image) + binary features out",
+                "with_f32_images": {"value": world * E * Ke / t_e2e_f32, "unit": UNIT, "d2h_bytes_per_step": d2h_f32}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,

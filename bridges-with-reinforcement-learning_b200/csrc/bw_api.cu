@@ -35,6 +35,7 @@ struct bw_handle {
     bw_task *d_tasks = nullptr;
     float *d_img[3] = {nullptr, nullptr, nullptr};
     float *d_binary = nullptr;
+    uint8_t *d_img_u8 = nullptr;
     bw_interface *d_itf = nullptr;
     int32_t *d_nitf = nullptr;
     double *d_ground = nullptr, *d_offsets = nullptr;
@@ -368,8 +369,8 @@ int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
     h->launches++;
     if (d_tasks != nullptr) {
         // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
-        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, nullptr, nullptr, nullptr, nullptr, 0, h->smem_step,
-                    h->stream);
+        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr}, nullptr, nullptr,
+                    0, h->smem_step, h->stream);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -401,15 +402,16 @@ int bw_reset_done(bw_handle *h) {
     return BW_OK;
 }
 
-int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out, float *d_block_img,
-            float *d_binary) {
+int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
+            const bw_obs_out *obs) {
     if (!h || !d_actions || !d_out) return BW_ERR_INVALID;
     if (int rc = need_shapes(h)) return rc;
     CU(cudaSetDevice(h->cfg.device));
     if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
     // one kernel: placement, interfaces, both solves, bookkeeping, raster update and the
-    // f32 observation write
-    launch_step(h->P, d_actions, d_mask, d_out, d_block_img, d_binary, nullptr, nullptr, 0, h->smem_step, h->stream);
+    // observation write
+    launch_step(h->P, d_actions, d_mask, d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr}, nullptr, nullptr, 0,
+                h->smem_step, h->stream);
     h->launches++;
     if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
     CU(cudaGetLastError());
@@ -431,24 +433,35 @@ static int ensure_img(bw_handle *h, int which) {
 }
 
 int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
-                 float *h_block_img, float *h_binary) {
+                 const bw_obs_out *obs) {
     if (!h || !h_actions || !h_out) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
-    const int E = h->P.E;
+    const size_t E = (size_t)h->P.E;
     CU(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
     if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
-    if (h_block_img)
+    bw_obs_out dev = {nullptr, nullptr, nullptr};
+    if (obs && obs->block_img_f32) {
         if (int rc = ensure_img(h, 0)) return rc;
-    if (h_binary && !h->d_binary) CU(dev_alloc(h, &h->d_binary, (size_t)E * 6, false));
-    int rc = bw_step(h, h->d_actions, h_mask ? h->d_mask : nullptr, h->d_out, h_block_img ? h->d_img[0] : nullptr,
-                     h_binary ? h->d_binary : nullptr);
+        dev.block_img_f32 = h->d_img[0];
+    }
+    if (obs && obs->block_img_u8) {
+        if (!h->d_img_u8) CU(dev_alloc(h, &h->d_img_u8, E * IMG * IMG, false));
+        dev.block_img_u8 = h->d_img_u8;
+    }
+    if (obs && obs->binary) {
+        if (!h->d_binary) CU(dev_alloc(h, &h->d_binary, E * 6, false));
+        dev.binary = h->d_binary;
+    }
+    int rc = bw_step(h, h->d_actions, h_mask ? h->d_mask : nullptr, h->d_out, &dev);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_out, h->d_out, sizeof(bw_step_out) * E, cudaMemcpyDeviceToHost, h->stream));
-    if (h_block_img)
-        CU(cudaMemcpyAsync(h_block_img, h->d_img[0], sizeof(float) * (size_t)E * IMG * IMG, cudaMemcpyDeviceToHost,
+    if (dev.block_img_f32)
+        CU(cudaMemcpyAsync(obs->block_img_f32, dev.block_img_f32, sizeof(float) * E * IMG * IMG, cudaMemcpyDeviceToHost,
                            h->stream));
-    if (h_binary)
-        CU(cudaMemcpyAsync(h_binary, h->d_binary, sizeof(float) * (size_t)E * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (dev.block_img_u8)
+        CU(cudaMemcpyAsync(obs->block_img_u8, dev.block_img_u8, E * IMG * IMG, cudaMemcpyDeviceToHost, h->stream));
+    if (dev.binary)
+        CU(cudaMemcpyAsync(obs->binary, dev.binary, sizeof(float) * E * 6, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -656,8 +669,8 @@ int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h
     CU(cudaMemsetAsync(h->d_itf, 0, sizeof(bw_interface) * E * BW_MAX_INTERFACES, h->stream));
     // the state did not change since the last step: re-evaluating it reproduces the same
     // interfaces and dual iterates, this time with the read-back enabled
-    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, nullptr, nullptr, h->d_itf, h->d_nitf, variant,
-                h->smem_step, h->stream);
+    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr}, h->d_itf, h->d_nitf,
+                variant, h->smem_step, h->stream);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_itf, h->d_itf, sizeof(bw_interface) * E * BW_MAX_INTERFACES, cudaMemcpyDeviceToHost, h->stream));

@@ -9,8 +9,8 @@ void upload_step_tables();
 int step_smem_bytes(int max_blocks, int max_itf);
 cudaError_t configure_step(int smem_bytes);
 void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
-                 float *d_block_img, float *d_binary, bw_interface *d_itf, int32_t *d_nitf, int variant,
-                 int smem_bytes, cudaStream_t stream);
+                 const bw_obs_out &obs, bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes,
+                 cudaStream_t stream);
 double measure_fp64_gflops(cudaStream_t stream);
 
 // bw_obs.cu

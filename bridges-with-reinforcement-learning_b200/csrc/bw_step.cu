@@ -107,8 +107,10 @@ int step_smem_bytes(int max_blocks, int max_itf) { return make_layout(max_blocks
 template <bool TWO>
 __global__ void __launch_bounds__(64)
 step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
-            bw_step_out *__restrict__ out, float *__restrict__ block_img, float *__restrict__ binary,
-            bw_interface *__restrict__ save_itf, int32_t *__restrict__ save_nitf, int save_variant) {
+            bw_step_out *__restrict__ out, bw_obs_out obs, bw_interface *__restrict__ save_itf,
+            int32_t *__restrict__ save_nitf, int save_variant) {
+    float *__restrict__ block_img = obs.block_img_f32;
+    float *__restrict__ binary = obs.binary;
     extern __shared__ __align__(16) unsigned char smem[];
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
@@ -613,18 +615,30 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
                                         (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f));
         }
     }
+    if (obs.block_img_u8 != nullptr) {
+        uint4 *dst = reinterpret_cast<uint4 *>(obs.block_img_u8 + (size_t)e * IMG * IMG);
+#pragma unroll
+        for (int i = 0; i < IMG * IMG / 16 / 64; i++) {
+            const int q = i * 64 + tid;            // uint4 index: row = q / 4, 16-pixel segment = q % 4
+            const unsigned seg = (unsigned)(sh_bits[q >> 2] >> (16 * (q & 3))) & 0xffffu;
+            uint4 v;
+            v.x = (seg & 1u) | ((seg & 2u) << 7) | ((seg & 4u) << 14) | ((seg & 8u) << 21);
+            v.y = ((seg >> 4) & 1u) | (((seg >> 4) & 2u) << 7) | (((seg >> 4) & 4u) << 14) | (((seg >> 4) & 8u) << 21);
+            v.z = ((seg >> 8) & 1u) | (((seg >> 8) & 2u) << 7) | (((seg >> 8) & 4u) << 14) | (((seg >> 8) & 8u) << 21);
+            v.w = ((seg >> 12) & 1u) | (((seg >> 12) & 2u) << 7) | (((seg >> 12) & 4u) << 14) | (((seg >> 12) & 8u) << 21);
+            __stcs(dst + q, v);
+        }
+    }
 }
 
 void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
-                 float *d_block_img, float *d_binary, bw_interface *d_itf, int32_t *d_nitf, int variant,
-                 int smem_bytes, cudaStream_t stream) {
+                 const bw_obs_out &obs, bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes,
+                 cudaStream_t stream) {
     // 3 rows per free block + the right-hand side row: one row per lane up to 10 blocks
     if (3 * P.max_blocks + 1 <= 32)
-        step_kernel<false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf,
-                                                            d_nitf, variant);
+        step_kernel<false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
     else
-        step_kernel<true><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, d_block_img, d_binary, d_itf,
-                                                           d_nitf, variant);
+        step_kernel<true><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
 }
 
 cudaError_t configure_step(int smem_bytes) {

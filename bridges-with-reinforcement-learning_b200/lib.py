@@ -69,6 +69,10 @@ class bw_step_out(C.Structure):
                 ("reserved1", C.c_uint8 * 4)]
 
 
+class bw_obs_out(C.Structure):
+    _fields_ = [("block_img_f32", C.c_void_p), ("block_img_u8", C.c_void_p), ("binary", C.c_void_p)]
+
+
 class bw_interface(C.Structure):
     _fields_ = [("body_a", C.c_int32), ("body_b", C.c_int32), ("face_a", C.c_int32), ("face_b", C.c_int32),
                 ("nx", C.c_double), ("nz", C.c_double),
@@ -119,8 +123,8 @@ SIGNATURES = {
     "bw_reset": (C.c_int, [_H, _P, _P]),
     "bw_reset_host": (C.c_int, [_H, _P, _P]),
     "bw_reset_done": (C.c_int, [_H]),
-    "bw_step": (C.c_int, [_H, _P, _P, _P, _P, _P]),
-    "bw_step_host": (C.c_int, [_H, _P, _P, _P, _P, _P]),
+    "bw_step": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
+    "bw_step_host": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
     "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_observe_host": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_enumerate_actions": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -141,6 +141,15 @@ typedef struct {
     uint8_t reserved1[4];
 } bw_step_out;
 
+/* Optional observation outputs of a step; any pointer may be NULL.  The raster is
+ * render_blocks_2d(obs['blocks']) (rendering.py:105-113, a bool image) either as the float32
+ * tensor get_state_features makes of it (successor_dqn.py:63) or as one byte per pixel. */
+typedef struct {
+    float *block_img_f32;   /* [E,1,64,64] */
+    uint8_t *block_img_u8;  /* [E,64,64], 0/1 */
+    float *binary;          /* [E,6] = (stable, collision, collision_block, _obstacle, _floor, _boundary) */
+} bw_obs_out;
+
 /* One contact interface with its two contact points and their forces (bw_get_forces) */
 typedef struct {
     int32_t body_a, body_b;       /* -1 = floor; a < b */
@@ -181,13 +190,12 @@ int bw_reset_host(bw_handle *h, const bw_task *h_tasks, const uint8_t *h_mask);
 int bw_reset_done(bw_handle *h);
 
 /* ---- step: AssemblyGym.step (gym_env.py:218-253) + stabilities_freezing (:325-333) ------
- * d_actions[E], d_mask (NULL = all), d_out[E].  Optional observation outputs (may be NULL):
- * d_block_img [E,1,64,64] f32 = get_state_features image (successor_dqn.py:47-64),
- * d_binary [E,6] f32 = (stable, collision, collision_block, _obstacle, _floor, _boundary). */
+ * d_actions[E], d_mask (NULL = all), d_out[E]; `obs` (may be NULL) holds DEVICE pointers for
+ * bw_step and HOST pointers for bw_step_host (get_state_features, successor_dqn.py:47-64). */
 int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
-            float *d_block_img, float *d_binary);
+            const bw_obs_out *obs);
 int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
-                 float *h_block_img, float *h_binary);
+                 const bw_obs_out *obs);
 
 /* ---- observations: _get_obs + get_state_features / get_task_features ----------------
  * any pointer may be NULL.  Images are [E,1,64,64] f32, row 0 = top (rendering.py:105-113). */

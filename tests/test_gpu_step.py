@@ -182,3 +182,34 @@ def test_random_assemblies_verdicts_residuals_forces():
         assert np.array_equal(env.bits_to_bool(bits[e]), render_blocks_2d(ob, H.XLIM, H.YLIM, H.IMG))
     assert n_checked > 1000 and n_stable > 100 and n_forces > 30
     assert n_band <= 0.01 * n_checked            # size of the excluded band
+
+
+def test_host_entry_point_and_observation_formats():
+    """bw_step_host (host buffers in/out) against the device path: records, u8 raster, f32 image, binary."""
+    import ctypes as C
+    from bridges_b200 import lib as L
+    actions = [(-1, 0, 0, 2, -0.45, 0.0), (0, 0, 0, 1, 0.0, 0.0), (1, 3, 0, 1, 0.0, 0.0)]
+    task = dict(obstacles=[(0.6, 0, 0.3)], targets=[(0.6, 0, 0.9)])
+    a = _gpu_env(3, [H.URDF["trapezoid"]])
+    b = _gpu_env(3, [H.URDF["trapezoid"]])
+    a.reset(task)
+    b.reset(task)
+    E = 3
+    for act in actions:
+        arr = a.actions_array([act] * E)
+        h_out = np.zeros(E, dtype=a.dt["step_out"])
+        h_u8 = np.zeros((E, 64, 64), dtype=np.uint8)
+        h_f32 = np.zeros((E, 1, 64, 64), dtype=np.float32)
+        h_bin = np.zeros((E, 6), dtype=np.float32)
+        obs = L.bw_obs_out(h_f32.ctypes.data, h_u8.ctypes.data, h_bin.ctypes.data)
+        L.check(a.lib, a.handle, a.lib.bw_step_host(a.handle, arr.ctypes.data, None, h_out.ctypes.data, C.byref(obs)))
+        b.step([act] * E)
+        ref = b.read_out()
+        for name in ("stable", "stable_unfrozen", "reward", "lin_reward", "terminated", "n_blocks", "n_interfaces",
+                     "residual", "residual_unfrozen"):
+            assert np.array_equal(h_out[name], ref[name]), name
+        bits, _ = b.raster_bits()
+        want = b.bits_to_bool(bits)
+        assert np.array_equal(h_u8.astype(bool), want) and set(np.unique(h_u8)) <= {0, 1}
+        assert np.array_equal(h_f32[:, 0], want.astype(np.float32))
+        assert np.array_equal(h_bin[:, 0], ref["stable"].astype(np.float32)) and not h_bin[:, 1:].any()
