@@ -99,6 +99,7 @@ struct Solver {
 
     // out = A^T v (lanes over contact points)
     __device__ __forceinline__ void at_times(const double *v, double *out) const {
+#pragma unroll 1
         for (int c = lane; c < nc; c += 32) {
             const double *Gc = G + c * 12;
             const int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
@@ -120,6 +121,7 @@ struct Solver {
 
     // f = P_K(g), typ
     __device__ __forceinline__ void project_all() {
+#pragma unroll 1
         for (int c = lane; c < nc; c += 32) {
             double fn, ft;
             int t;
@@ -135,6 +137,7 @@ struct Solver {
         const int I = i / 3, k = i - 3 * I;
         const int body = freebody[I];
         double acc = 0.0;
+#pragma unroll 1
         for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
             const int e = adj[q];
             const int c = e & 0x7f;
@@ -149,12 +152,14 @@ struct Solver {
     // (two contact points), so lanes over interfaces write it without accumulation conflicts.
     __device__ void assemble_H(double inv_rho) {
         const int nz = tri(m);
+#pragma unroll 1
         for (int q = lane; q < nz; q += 32) L[q] = 0.0;
         __syncwarp();
         const double isd = sqrt(inv_den);
         if (lane < nfree) {
             const int body = freebody[lane];
             double a00 = inv_rho, a10 = 0, a11 = inv_rho, a20 = 0, a21 = 0, a22 = inv_rho;
+#pragma unroll 1
             for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
                 const int e = adj[q];
                 const int c = e & 0x7f;
@@ -180,6 +185,7 @@ struct Solver {
             p += r0 + 2;
             p[0] = a20; p[1] = a21; p[2] = a22;
         }
+#pragma unroll 1
         for (int k = lane; k < nitf; k += 32) {
             const int c0 = 2 * k;
             const int ra = rowbase[c_a[c0]], rb = rowbase[c_b[c0]];
@@ -224,16 +230,20 @@ struct Solver {
         const int i0 = lane, i1 = lane + 32;
         double *row0 = L + tri(i0 < nrows ? i0 : 0);       // idle lanes read row 0 (results unused)
         double *row1 = L + tri((TWO && i1 < nrows) ? i1 : 0);
+#pragma unroll 1
         for (int j = 0; j < m; j++) {
             const double *rowj = L + tri(j);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             double c0 = 0.0, c1 = 0.0;
             int p = 0;
+            // the compiler would unroll these loops 16-fold and pay the set-up on every (short) column
+#pragma unroll 1
             for (; p + 3 < j; p += 4) {
                 const double l0 = rowj[p], l1 = rowj[p + 1], l2 = rowj[p + 2], l3 = rowj[p + 3];
                 a0 += row0[p] * l0; a1 += row0[p + 1] * l1; a2 += row0[p + 2] * l2; a3 += row0[p + 3] * l3;
                 if (TWO) { c0 += row1[p] * l0 + row1[p + 2] * l2; c1 += row1[p + 1] * l1 + row1[p + 3] * l3; }
             }
+#pragma unroll 1
             for (; p < j; p++) {
                 const double l0 = rowj[p];
                 a0 += row0[p] * l0;
@@ -253,6 +263,7 @@ struct Solver {
         const double *rowm = L + tri(m);
         double z0 = (i0 < m) ? rowm[i0] : 0.0;
         double z1 = (TWO && i1 < m) ? rowm[i1] : 0.0;
+#pragma unroll 1
         for (int j = m - 1; j >= 0; j--) {
             const double dj = __shfl_sync(FULL, (!TWO || j < 32) ? z0 : z1, j & 31) * invd[j];
             const double *rowj = L + tri(j);
@@ -275,6 +286,7 @@ struct Solver {
         project_all();
         __syncwarp();
         double acc = 0.0;
+#pragma unroll 1
         for (int i = lane; i < m; i += 32) {
             const double r = b[i] - a_times_f_row(i);
             acc += r * r;
@@ -285,6 +297,7 @@ struct Solver {
     // sum over contact points of P_K(g + t h) . h
     __device__ __forceinline__ double fdoth(double t) {
         double fh = 0.0;
+#pragma unroll 1
         for (int c = lane; c < nc; c += 32) {
             double fn, ft;
             int tp;
@@ -298,7 +311,9 @@ struct Solver {
 
     // returns status: 0 feasible (r <= 1e-9), 1 stalled at r* > 0, 2 not converged
     __device__ int solve(double &r_out, int &iters_out) {
+#pragma unroll 1
         for (int i = lane; i < m; i += 32) y[i] = 0.0;
+#pragma unroll 1
         for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
         __syncwarp();
         flops = 0.0;
@@ -308,15 +323,19 @@ struct Solver {
         double *rhs = L + tri(m);
         double rprev = -1.0, r = 1.0;
         int status = 2, iters = 0;
+#pragma unroll 1
         for (int k = 0; k < NSCHED; k++) {
             const double inv_rho = 1.0 / c_rho[k];
+#pragma unroll 1
             for (int i = lane; i < m; i += 32) yk[i] = y[i];
             __syncwarp();
+#pragma unroll 1
             for (int it = 0; it < MAX_NEWTON; it++) {
                 BW_T0(t_a);
                 project_all();
                 __syncwarp();
                 double gn2 = 0.0;
+#pragma unroll 1
                 for (int i = lane; i < m; i += 32) {
                     const double gr = b[i] - a_times_f_row(i) - (y[i] - yk[i]) * inv_rho;
                     d[i] = gr;                     // kept for the dot products below
@@ -327,6 +346,7 @@ struct Solver {
                 if (gn2 <= 1e-20) break;
                 BW_T0(t_b);
                 assemble_H(inv_rho);               // zero-fills rows 0..m-1, leaves row m alone
+#pragma unroll 1
                 for (int i = lane; i < m; i += 32) rhs[i] = d[i];
                 double gd = 0.0;
                 // keep the gradient in registers: d[] is overwritten by the solve
@@ -351,6 +371,7 @@ struct Solver {
                         gd += gr1 * d1;
                         dd += d1 * d1;
                     }
+#pragma unroll 1
                     for (int c = lane; c < 2 * nc; c += 32) fh0 += f[c] * h[c];
                 }
                 warp_sum3(gd, dd, fh0);
@@ -364,6 +385,7 @@ struct Solver {
                 if (p < -1e-12 * phi0) {
                     // bracket the root with a safeguarded regula falsi until |phi'| <= 0.1 phi'(0)
                     double lo = 0.0, plo = phi0, hi = 1.0, phi = p;
+#pragma unroll 1
                     for (int ls = 0; ls < 20; ls++) {
                         const double w = hi - lo;
                         t = lo + w * plo / (plo - phi);
@@ -375,11 +397,13 @@ struct Solver {
                     if (p < 0.0 && fabs(p) > 0.1 * phi0 && lo > 0.0) t = lo;
                 }
                 double yy = 0.0;
+#pragma unroll 1
                 for (int i = lane; i < m; i += 32) {
                     const double yn = y[i] + t * d[i];
                     y[i] = yn;
                     yy = fmax(yy, fabs(yn));
                 }
+#pragma unroll 1
                 for (int c = lane; c < 2 * nc; c += 32) g[c] += t * h[c];   // A^T (y + t d)
                 __syncwarp();
                 BW_ACC(4, t_e);

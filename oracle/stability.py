@@ -238,7 +238,7 @@ def equilibrium_residual(A, b, mu):
     w = R.T @ resid                          # must be <= 0 on x = 0 and == 0 on x > 0
     scale = max(1.0, float(np.abs(R).max())) * nb
     free = x > 1e-12 * max(1.0, float(np.abs(x).max()))
-    if np.any(w[~free] > 1e-8 * scale) or np.any(np.abs(w[free]) > 1e-8 * scale):
+    if np.any(w[~free] > 1e-6 * scale) or np.any(np.abs(w[free]) > 1e-6 * scale):
         raise RuntimeError("BVLS did not reach a KKT point")
     return float(np.linalg.norm(resid)) / nb
 

@@ -116,20 +116,22 @@ def test_targets_quirk_max_steps_and_invalid_actions():
     assert list(env.read_out()["error"]) == [2, 2]      # max_steps = 2 blocks is the capacity
 
 
-def test_random_assemblies_verdicts_residuals_forces():
+@pytest.mark.parametrize("N,max_blocks,max_steps,seed", [(160, 12, None, 2024), (96, 10, 10, 7)])
+def test_random_assemblies_verdicts_residuals_forces(N, max_blocks, max_steps, seed):
+    """max_steps=None sizes the kernel for 16 blocks (two matrix rows per lane), max_steps=10 selects the
+    one-row-per-lane solver instantiation: both are checked."""
     from oracle import stability as ost
     from oracle import synth
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(seed)
     shapes = synth.library()
-    N = 160
-    plans = [synth.random_assembly(rng, shapes, max_blocks=12) for _ in range(N)]
+    plans = [synth.random_assembly(rng, shapes, max_blocks=max_blocks) for _ in range(N)]
     mus = [synth.MUS[i % 3] for i in range(N)]
-    env = _gpu_env(N, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"])
+    env = _gpu_env(N, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"], max_steps=max_steps)
     env.set_mu(mus)
     env.reset(dict())
     oenvs = [H.oracle_env(["trapezoid", "hexagon", "cube1"], mu=mus[i]) for i in range(N)]
     from oracle.gym_env import Action as OAction
-    n_band = n_checked = n_stable = n_forces = 0
+    n_band = n_checked = n_stable = n_forces = n_residuals = 0
     for k in range(max(len(p) for p in plans)):
         acts = [(p[k].target_block, p[k].target_face, p[k].shape, p[k].face, p[k].offset_x, p[k].offset_y)
                 if k < len(p) else None for p in plans]
@@ -150,10 +152,11 @@ def test_random_assemblies_verdicts_residuals_forces():
                     n_band += 1
                     continue
                 assert bool(got) == bool(want), (e, k, r_gpu, r_or)
-                if r_or is not None:
+                if r_or is not None and not np.isnan(r_gpu):
                     # clearly unstable assemblies leave the solver early: the residual is then an upper
                     # estimate of r* (within 2%); near the verdict threshold it is converged
                     assert -1e-7 - 1e-3 * r_or <= r_gpu - r_or <= (2e-2 if r_or > 1e-3 else 1e-3) * r_or + 1e-7, (e, k, r_gpu, r_or)
+                    n_residuals += 1
                 n_checked += 1
                 n_stable += bool(want)
             # contact forces of the frozen variant against the oracle's min-norm solution
@@ -180,7 +183,7 @@ def test_random_assemblies_verdicts_residuals_forces():
             b = blocks[e][i]
             assert (b["x"], b["z"], b["c"], b["s"]) == blk.pose
         assert np.array_equal(env.bits_to_bool(bits[e]), render_blocks_2d(ob, H.XLIM, H.YLIM, H.IMG))
-    assert n_checked > 1000 and n_stable > 100 and n_forces > 30
+    assert n_checked > 500 and n_stable > 50 and n_forces > 15 and n_residuals > 300
     assert n_band <= 0.01 * n_checked            # size of the excluded band
 
 
@@ -205,9 +208,11 @@ def test_host_entry_point_and_observation_formats():
         L.check(a.lib, a.handle, a.lib.bw_step_host(a.handle, arr.ctypes.data, None, h_out.ctypes.data, C.byref(obs)))
         b.step([act] * E)
         ref = b.read_out()
-        for name in ("stable", "stable_unfrozen", "reward", "lin_reward", "terminated", "n_blocks", "n_interfaces",
-                     "residual", "residual_unfrozen"):
+        for name in ("stable", "stable_unfrozen", "reward", "lin_reward", "terminated", "n_blocks", "n_interfaces"):
             assert np.array_equal(h_out[name], ref[name]), name
+        for name in ("residual", "residual_unfrozen"):     # NaN = verdict implied by the sibling solve
+            both = ~np.isnan(h_out[name]) & ~np.isnan(ref[name])
+            assert np.array_equal(h_out[name][both], ref[name][both]), name
         bits, _ = b.raster_bits()
         want = b.bits_to_bool(bits)
         assert np.array_equal(h_u8.astype(bool), want) and set(np.unique(h_u8)) <= {0, 1}
