@@ -570,6 +570,15 @@ int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits, uint64_t *h_obstacl
     return BW_OK;
 }
 
+int bw_copy_raster_bits(bw_handle *h, uint64_t *d_block_bits, uint64_t *d_obstacle_bits) {
+    if (!h) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t bytes = sizeof(uint64_t) * (size_t)h->P.E * IMG;
+    if (d_block_bits) CU(cudaMemcpyAsync(d_block_bits, h->P.block_bits, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (d_obstacle_bits) CU(cudaMemcpyAsync(d_obstacle_bits, h->P.obst_bits, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return BW_OK;
+}
+
 int bw_get_target_state(bw_handle *h, int8_t *h_remaining, int8_t *h_reached, int32_t *h_counts) {
     if (!h || !h_remaining || !h_reached || !h_counts) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));

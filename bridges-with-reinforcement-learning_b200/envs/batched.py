@@ -225,6 +225,15 @@ class BatchedAssemblyGym:
         self._check(self.lib.bw_get_raster_bits(self.handle, blk.ctypes.data, obs.ctypes.data))
         return blk, obs
 
+    def raster_bits_device(self, obstacles=False):
+        """Bit rasters as an int64 CUDA tensor [E, 64] (device-to-device copy on the handle's stream)."""
+        out = torch.empty((self.num_envs, L.BW_IMG), dtype=torch.int64, device=self.device)
+        if obstacles:
+            self._check(self.lib.bw_copy_raster_bits(self.handle, None, out.data_ptr()))
+        else:
+            self._check(self.lib.bw_copy_raster_bits(self.handle, out.data_ptr(), None))
+        return out
+
     @staticmethod
     def bits_to_bool(bits):
         """[..., 64] uint64 rows -> [..., 64, 64] bool (row 0 = top, bit x = column x)."""

@@ -132,6 +132,7 @@ SIGNATURES = {
     "bw_select_random": (C.c_int, [_H, _P, _P, _P, C.c_int32, C.c_uint64, _P, _P]),
     "bw_get_state": (C.c_int, [_H, _P, _P]),
     "bw_get_raster_bits": (C.c_int, [_H, _P, _P]),
+    "bw_copy_raster_bits": (C.c_int, [_H, _P, _P]),
     "bw_get_forces": (C.c_int, [_H, C.c_int32, _P, _P]),
     "bw_get_target_state": (C.c_int, [_H, _P, _P, _P]),
     "bw_query_placement_host": (C.c_int, [_H, _P, _P, _P, _P, _P]),

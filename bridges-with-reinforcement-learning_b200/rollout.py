@@ -1,0 +1,130 @@
+"""Lock-step rollouts and a device-resident replay memory.
+
+Batched counterpart of `rollout_episode` (robotoddler/training/successor_dqn.py:365-475) and
+`ReplayBuffer` (robotoddler/utils/replay_memory.py:10-43): every environment of a
+`BatchedAssemblyGym` advances once per iteration, finished episodes are reset in place, and the
+transitions stay on the GPU with their rasters bit-packed (512 B instead of 16 KB per image).
+Across GPUs the only communication is the gather of freshly collected transitions into every
+rank's replay memory (`torch.distributed.all_gather_into_tensor`, NCCL over NVLink on the GPU box,
+gloo in the CPU tests); the environment step itself never communicates.
+"""
+import torch
+import torch.distributed as dist
+
+IMG = 64
+# one transition = these fields (successor_dqn.py:27-44, minus the per-candidate next-state tensors,
+# which are re-derived from next_block_bits by the candidate kernel when a batch is sampled)
+FIELDS = (("block_bits", torch.int64, (IMG,)), ("action_bits", torch.int64, (IMG,)),
+          ("next_block_bits", torch.int64, (IMG,)), ("binary", torch.float32, (6,)),
+          ("next_binary", torch.float32, (6,)), ("reward", torch.float32, ()), ("lin_reward", torch.float32, ()),
+          ("done", torch.bool, ()), ("env", torch.int32, ()))
+
+
+def empty_batch(n, device):
+    return {name: torch.zeros((n,) + shape, dtype=dtype, device=device) for name, dtype, shape in FIELDS}
+
+
+def gather_transitions(batch, group=None):
+    """Concatenate the per-rank batches of equal length on every rank (collective)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return batch
+    world = dist.get_world_size(group)
+    out = {}
+    for name, t in batch.items():
+        src = t.to(torch.uint8) if t.dtype == torch.bool else t
+        dst = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
+        out[name] = dst.to(torch.bool) if t.dtype == torch.bool else dst
+    return out
+
+
+class DeviceReplayBuffer:
+    """Ring buffer of transitions in device memory (`push` / `sample`, replay_memory.py:10-43)."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.data = empty_batch(self.capacity, self.device)
+        self.size = 0
+        self.head = 0
+
+    def __len__(self):
+        return self.size
+
+    def push(self, batch, valid=None):
+        """Append the rows of `batch` (optionally only those with `valid`)."""
+        if valid is not None:
+            idx = torch.nonzero(valid, as_tuple=False).flatten()
+            batch = {k: v.index_select(0, idx) for k, v in batch.items()}
+        n = next(iter(batch.values())).shape[0]
+        if n == 0:
+            return
+        if n > self.capacity:
+            batch = {k: v[-self.capacity:] for k, v in batch.items()}
+            n = self.capacity
+        pos = (torch.arange(n, device=self.device) + self.head) % self.capacity
+        for name, t in batch.items():
+            self.data[name].index_copy_(0, pos, t.to(self.device))
+        self.head = (self.head + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch_size, generator=None):
+        idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=generator)
+        return {name: t.index_select(0, idx) for name, t in self.data.items()}
+
+
+def random_policy(seed=0):
+    """Uniformly random valid candidate (the synthetic policy of the benchmarks)."""
+    state = {"step": 0}
+
+    def policy(env, cand):
+        actions, index = env.select_random(seed * 1000003 + state["step"] * 7919, cand)
+        state["step"] += 1
+        return actions, index
+    return policy
+
+
+def rollout_lockstep(env, policy, n_steps, x_discr_ground, offset_values=(0.0,), amax=128, replay=None,
+                     gather=True):
+    """Advance every environment `n_steps` times.
+
+    policy(env, cand) -> (uint8 CUDA tensor holding bw_action[E], int32 index tensor [E] into the
+    candidates, -1 = no valid candidate).  Returns the last gathered batch; with `replay` the
+    (gathered) transitions are pushed as they are produced.
+    """
+    E, dev = env.num_envs, env.device
+    binary = torch.zeros((E, 6), dtype=torch.float32, device=dev)
+    binary[:, 0] = 1.0                                          # empty scene: stable
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    env_ids = torch.arange(E, dtype=torch.int32, device=dev) + rank * E
+    last = None
+    fresh = torch.tensor([1.0, 0, 0, 0, 0, 0], device=dev).expand(E, 6)
+    for _ in range(n_steps):
+        cand = env.enumerate_actions(x_discr_ground, offset_values, amax=amax, with_bits=True)
+        actions, index = policy(env, cand)
+        has_action = index >= 0
+        before = env.raster_bits_device()
+        sel = cand["bits"][torch.arange(E, device=dev), index.clamp(min=0).long()]
+        sel = torch.where(has_action[:, None], sel, torch.zeros_like(sel))
+        next_binary = torch.empty_like(binary)
+        out_dev = env.step(actions, binary=next_binary)
+        after = env.raster_bits_device()
+        out = env.read_out(out_dev)
+        done = torch.from_numpy((out["terminated"] | out["truncated"]).astype(bool)).to(dev) | ~has_action
+        batch = dict(block_bits=before, action_bits=sel, next_block_bits=after, binary=binary.clone(),
+                     next_binary=next_binary, reward=torch.from_numpy(out["reward"].copy()).to(dev),
+                     lin_reward=torch.from_numpy(out["lin_reward"].copy()).to(dev), done=done, env=env_ids)
+        keep = has_action                                   # envs without a valid candidate yield no transition
+        if gather:
+            full = gather_transitions(dict(batch, keep=keep))
+            keep = full.pop("keep")
+            batch = full
+        if replay is not None:
+            replay.push(batch, valid=keep)
+        last = (batch, keep)
+        env.reset_done()
+        # environments that could not move end their episode too (rollout_episode, successor_dqn.py:409-411)
+        if bool((~has_action).any()):
+            env.reset(None, mask=(~has_action).to(torch.uint8).cpu().numpy())
+        binary = torch.where(done[:, None], fresh, next_binary)
+    return last

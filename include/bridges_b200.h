@@ -221,6 +221,8 @@ int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_val
 /* ---- state read-back (adapters, checkpointing, tests) ------------------------------ */
 int bw_get_state(bw_handle *h, bw_block *h_blocks /*[E,BW_MAX_BLOCKS]*/, int32_t *h_n_blocks /*[E]*/);
 int bw_get_raster_bits(bw_handle *h, uint64_t *h_block_bits /*[E,64]*/, uint64_t *h_obstacle_bits /*[E,64]*/);
+/* the same into caller-owned DEVICE buffers (device-to-device, asynchronous on the handle's stream) */
+int bw_copy_raster_bits(bw_handle *h, uint64_t *d_block_bits /*[E,64]*/, uint64_t *d_obstacle_bits /*[E,64]*/);
 /* targets_remaining / targets_reached of AssemblyGym (gym_env.py:162-168) as indices into the
  * task's target list, in list order; h_counts[e] = {n_remaining, n_reached} */
 int bw_get_target_state(bw_handle *h, int8_t *h_remaining /*[E,BW_MAX_TARGETS]*/,

@@ -218,3 +218,33 @@ def test_host_entry_point_and_observation_formats():
         assert np.array_equal(h_u8.astype(bool), want) and set(np.unique(h_u8)) <= {0, 1}
         assert np.array_equal(h_f32[:, 0], want.astype(np.float32))
         assert np.array_equal(h_bin[:, 0], ref["stable"].astype(np.float32)) and not h_bin[:, 1:].any()
+
+
+def test_masks_empty_scene_and_capacity():
+    env = _gpu_env(4, [H.URDF["cube"]])
+    env.reset(dict())
+    # empty scene: stable by the edge-less rule, infinite distances are only defined with targets
+    env.evaluate()
+    out = env.read_out()
+    assert list(out["stable"]) == [1, 1, 1, 1] and list(out["n_blocks"]) == [0, 0, 0, 0]
+    # masked step: envs 1 and 3 advance, 0 and 2 are untouched
+    env.step([(-1, 0, 0, 0, 0.0, 0.0)] * 4, mask=[0, 1, 0, 1])
+    _, n = env.get_state()
+    assert list(n) == [0, 1, 0, 1]
+    bits, _ = env.raster_bits()
+    assert not bits[0].any() and bits[1].any()
+    # masked reset keeps the others
+    env.reset(dict(), mask=[0, 1, 0, 0])
+    _, n = env.get_state()
+    assert list(n) == [0, 0, 0, 1]
+    # a 16-cube tower reaches BW_MAX_BLOCKS; the 17th placement is refused with error 2
+    env.reset(dict())
+    for k in range(16):
+        env.step([(k - 1, 3 if k else 0, 0, 0, 0.0, 0.0)] * 4)
+        out = env.read_out()
+        assert list(out["error"]) == [0] * 4 and list(out["n_blocks"]) == [k + 1] * 4
+        assert list(out["stable"]) == [1] * 4 and list(out["stable_unfrozen"]) == [1] * 4   # a straight tower
+    env.step([(15, 3, 0, 0, 0.0, 0.0)] * 4)
+    assert list(env.read_out()["error"]) == [2] * 4
+    _, n = env.get_state()
+    assert list(n) == [16] * 4
