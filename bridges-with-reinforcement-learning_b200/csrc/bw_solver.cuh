@@ -224,54 +224,107 @@ struct Solver {
     }
 
     // Left-looking Cholesky of rows 0..m-1 with row m (the gradient) carried along, then the
-    // back substitution: d = H^-1 grad.
+    // back substitution: d = H^-1 grad.  The factorisation advances one 3x3 block column (= one free
+    // block) at a time: every lane accumulates the three dot products of its row with the three rows
+    // of the block (one own load feeds three FMAs), the 3x3 diagonal block is factorised redundantly
+    // by all lanes from six shuffled values, and each lane finishes its three entries with a 3x3
+    // triangular solve.  m is a multiple of 3, so the right-hand-side row m lies below every block.
     __device__ void factor_and_solve(double inv_rho) {
         const int nrows = m + 1;
         const int i0 = lane, i1 = lane + 32;
         double *row0 = L + tri(i0 < nrows ? i0 : 0);       // idle lanes read row 0 (results unused)
         double *row1 = L + tri((TWO && i1 < nrows) ? i1 : 0);
 #pragma unroll 1
-        for (int j = 0; j < m; j++) {
-            const double *rowj = L + tri(j);
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            double c0 = 0.0, c1 = 0.0;
-            int p = 0;
-            // the compiler would unroll these loops 16-fold and pay the set-up on every (short) column
+        for (int c0 = 0; c0 < m; c0 += 3) {
+            const double *rA = L + tri(c0), *rB = L + tri(c0 + 1), *rC = L + tri(c0 + 2);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+            // c0 is a multiple of 3: three columns per trip, all twelve loads issued before the FMAs
 #pragma unroll 1
-            for (; p + 3 < j; p += 4) {
-                const double l0 = rowj[p], l1 = rowj[p + 1], l2 = rowj[p + 2], l3 = rowj[p + 3];
-                a0 += row0[p] * l0; a1 += row0[p + 1] * l1; a2 += row0[p + 2] * l2; a3 += row0[p + 3] * l3;
-                if (TWO) { c0 += row1[p] * l0 + row1[p + 2] * l2; c1 += row1[p + 1] * l1 + row1[p + 3] * l3; }
+            for (int p = 0; p < c0; p += 3) {
+                const double la0 = rA[p], lb0 = rB[p], lc0 = rC[p];
+                const double la1 = rA[p + 1], lb1 = rB[p + 1], lc1 = rC[p + 1];
+                const double la2 = rA[p + 2], lb2 = rB[p + 2], lc2 = rC[p + 2];
+                const double o0 = row0[p], o1 = row0[p + 1], o2 = row0[p + 2];
+                a0 += o0 * la0; a1 += o0 * lb0; a2 += o0 * lc0;
+                a0 += o1 * la1; a1 += o1 * lb1; a2 += o1 * lc1;
+                a0 += o2 * la2; a1 += o2 * lb2; a2 += o2 * lc2;
+                if (TWO) {
+                    const double q0 = row1[p], q1 = row1[p + 1], q2 = row1[p + 2];
+                    b0 += q0 * la0; b1 += q0 * lb0; b2 += q0 * lc0;
+                    b0 += q1 * la1; b1 += q1 * lb1; b2 += q1 * lc1;
+                    b0 += q2 * la2; b1 += q2 * lb2; b2 += q2 * lc2;
+                }
             }
-#pragma unroll 1
-            for (; p < j; p++) {
-                const double l0 = rowj[p];
-                a0 += row0[p] * l0;
-                if (TWO) c0 += row1[p] * l0;
-            }
-            const double s0 = row0[j] - ((a0 + a1) + (a2 + a3));
-            const double s1 = TWO ? row1[j] - (c0 + c1) : 0.0;
-            double piv = __shfl_sync(FULL, (!TWO || j < 32) ? s0 : s1, j & 31);
+            // t = H[i][c0..c0+2] - partial dots (entries right of the diagonal are never used)
+            const double t0 = row0[c0] - a0, t1 = row0[c0 + 1] - a1, t2 = row0[c0 + 2] - a2;
+            double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+            if (TWO) { u0 = row1[c0] - b0; u1 = row1[c0 + 1] - b1; u2 = row1[c0 + 2] - b2; }
+            // the diagonal block: rows c0, c0+1, c0+2
+            const int ra = c0, rb = c0 + 1, rc = c0 + 2;
+            const double d00 = __shfl_sync(FULL, (!TWO || ra < 32) ? t0 : u0, ra & 31);
+            const double d10 = __shfl_sync(FULL, (!TWO || rb < 32) ? t0 : u0, rb & 31);
+            const double d11 = __shfl_sync(FULL, (!TWO || rb < 32) ? t1 : u1, rb & 31);
+            const double d20 = __shfl_sync(FULL, (!TWO || rc < 32) ? t0 : u0, rc & 31);
+            const double d21 = __shfl_sync(FULL, (!TWO || rc < 32) ? t1 : u1, rc & 31);
+            const double d22 = __shfl_sync(FULL, (!TWO || rc < 32) ? t2 : u2, rc & 31);
+            double piv = d00;
             if (!(piv > 1e-300)) piv = inv_rho;
-            const double inv = fast_rsqrt(piv);
-            if (i0 > j && i0 < nrows) row0[j] = s0 * inv;
-            if (TWO && i1 > j && i1 < nrows) row1[j] = s1 * inv;
-            if (lane == 0) invd[j] = inv;
+            const double i00 = fast_rsqrt(piv);
+            const double l10 = d10 * i00, l20 = d20 * i00;
+            piv = d11 - l10 * l10;
+            if (!(piv > 1e-300)) piv = inv_rho;
+            const double i11 = fast_rsqrt(piv);
+            const double l21 = (d21 - l20 * l10) * i11;
+            piv = d22 - l20 * l20 - l21 * l21;
+            if (!(piv > 1e-300)) piv = inv_rho;
+            const double i22 = fast_rsqrt(piv);
+            // x L_d^T = t for this lane's row(s)
+            {
+                const double x0 = t0 * i00;
+                const double x1 = (t1 - x0 * l10) * i11;
+                const double x2 = (t2 - x0 * l20 - x1 * l21) * i22;
+                if (i0 < nrows) {
+                    if (i0 > ra) row0[ra] = x0;
+                    if (i0 > rb) row0[rb] = x1;
+                    if (i0 > rc) row0[rc] = x2;
+                }
+            }
+            if (TWO && i1 < nrows) {
+                const double x0 = u0 * i00;
+                const double x1 = (u1 - x0 * l10) * i11;
+                const double x2 = (u2 - x0 * l20 - x1 * l21) * i22;
+                if (i1 > ra) row1[ra] = x0;
+                if (i1 > rb) row1[rb] = x1;
+                if (i1 > rc) row1[rc] = x2;
+            }
+            if (lane == 0) { invd[ra] = i00; invd[rb] = i11; invd[rc] = i22; }
             __syncwarp();
         }
-        // row m now holds z = L^-1 grad; back substitution L^T d = z
+        // row m now holds z = L^-1 grad; back substitution L^T d = z, one 3x3 block per trip
         const double *rowm = L + tri(m);
         double z0 = (i0 < m) ? rowm[i0] : 0.0;
         double z1 = (TWO && i1 < m) ? rowm[i1] : 0.0;
 #pragma unroll 1
-        for (int j = m - 1; j >= 0; j--) {
-            const double dj = __shfl_sync(FULL, (!TWO || j < 32) ? z0 : z1, j & 31) * invd[j];
-            const double *rowj = L + tri(j);
-            if (i0 == j) z0 = dj;
-            else if (i0 < j) z0 -= rowj[i0] * dj;
+        for (int c0 = m - 3; c0 >= 0; c0 -= 3) {
+            const int ra = c0, rb = c0 + 1, rc = c0 + 2;
+            const double *rA = L + tri(ra), *rB = L + tri(rb), *rC = L + tri(rc);
+            const double za = __shfl_sync(FULL, (!TWO || ra < 32) ? z0 : z1, ra & 31);
+            const double zb = __shfl_sync(FULL, (!TWO || rb < 32) ? z0 : z1, rb & 31);
+            const double zc = __shfl_sync(FULL, (!TWO || rc < 32) ? z0 : z1, rc & 31);
+            const double l10 = rB[ra], l20 = rC[ra], l21 = rC[rb];
+            // L_d^T (da, db, dc) = (za, zb, zc)
+            const double dc = zc * invd[rc];
+            const double db = (zb - l21 * dc) * invd[rb];
+            const double da = (za - l10 * db - l20 * dc) * invd[ra];
+            if (i0 == ra) z0 = da;
+            else if (i0 == rb) z0 = db;
+            else if (i0 == rc) z0 = dc;
+            else if (i0 < ra) z0 -= rA[i0] * da + rB[i0] * db + rC[i0] * dc;
             if (TWO) {
-                if (i1 == j) z1 = dj;
-                else if (i1 < j) z1 -= rowj[i1] * dj;
+                if (i1 == ra) z1 = da;
+                else if (i1 == rb) z1 = db;
+                else if (i1 == rc) z1 = dc;
+                else if (i1 < ra) z1 -= rA[i1] * da + rB[i1] * db + rC[i1] * dc;
             }
         }
         if (i0 < m) d[i0] = z0;
