@@ -156,34 +156,36 @@ struct Solver {
         for (int q = lane; q < nz; q += 32) L[q] = 0.0;
         __syncwarp();
         const double isd = sqrt(inv_den);
-        if (lane < nfree) {
-            const int body = freebody[lane];
-            double a00 = inv_rho, a10 = 0, a11 = inv_rho, a20 = 0, a21 = 0, a22 = inv_rho;
+        // diagonal tiles: three lanes per free block, lane (I, r) accumulates row r of the lower tile
 #pragma unroll 1
-            for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
-                const int e = adj[q];
+        for (int q = lane; q < m; q += 32) {
+            const int I = q / 3, r = q - 3 * I;
+            const int body = freebody[I];
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0;         // entries (r, 0..r)
+#pragma unroll 1
+            for (int a = adj_ptr[body]; a < adj_ptr[body + 1]; a++) {
+                const int e = adj[a];
                 const int c = e & 0x7f;
                 const int tp = typ[c];
                 if (tp == 0) continue;
                 const double *Gi = G + c * 12 + (e >> 7) * 6;
-                double u0, u1, u2;
                 if (tp == 1) {
-                    u0 = Gi[3]; u1 = Gi[4]; u2 = Gi[5];
-                    a00 += u0 * u0; a10 += u1 * u0; a11 += u1 * u1; a20 += u2 * u0; a21 += u2 * u1; a22 += u2 * u2;
-                    u0 = Gi[0]; u1 = Gi[1]; u2 = Gi[2];
+                    const double ur = Gi[r], vr = Gi[3 + r];
+                    e0 += ur * Gi[0] + vr * Gi[3];
+                    e1 += ur * Gi[1] + vr * Gi[4];
+                    e2 += ur * Gi[2] + vr * Gi[5];
                 } else {
                     const double sm = (tp == 2 ? mu : -mu);
-                    u0 = (Gi[0] + sm * Gi[3]) * isd; u1 = (Gi[1] + sm * Gi[4]) * isd; u2 = (Gi[2] + sm * Gi[5]) * isd;
+                    const double ur = (Gi[r] + sm * Gi[3 + r]) * inv_den;     // isd^2 = 1/(1+mu^2)
+                    e0 += ur * (Gi[0] + sm * Gi[3]);
+                    e1 += ur * (Gi[1] + sm * Gi[4]);
+                    e2 += ur * (Gi[2] + sm * Gi[5]);
                 }
-                a00 += u0 * u0; a10 += u1 * u0; a11 += u1 * u1; a20 += u2 * u0; a21 += u2 * u1; a22 += u2 * u2;
             }
-            const int r0 = 3 * lane;
-            double *p = L + tri(r0) + r0;
-            p[0] = a00;
-            p += r0 + 1;
-            p[0] = a10; p[1] = a11;
-            p += r0 + 2;
-            p[0] = a20; p[1] = a21; p[2] = a22;
+            double *p = L + tri(q) + 3 * I;
+            p[0] = e0 + (r == 0 ? inv_rho : 0.0);
+            if (r >= 1) p[1] = e1 + (r == 1 ? inv_rho : 0.0);
+            if (r == 2) p[2] = e2 + inv_rho;
         }
 #pragma unroll 1
         for (int k = lane; k < nitf; k += 32) {
