@@ -12,21 +12,31 @@
 
 namespace bw {
 
-constexpr unsigned FULLM = 0xffffffffu;
-constexpr int ENUM_WARPS = 4;
+constexpr int ENUM_THREADS = 128;
+constexpr int ENUM_CHUNK = 64;        // candidates posed per pass (shared-memory tables)
 
-__global__ void __launch_bounds__(32 * ENUM_WARPS)
+// Two phases per chunk of candidates.  A: one THREAD per candidate does everything that is uniform
+// for the candidate (placement, bounds test, posed half-planes, pixel window) -- FP64 work that must
+// not be replicated over the lanes of a warp.  B: one thread per (candidate, image row inside its
+// window) evaluates the row's bit mask and the overlap with the block / obstacle rasters.
+__global__ void __launch_bounds__(ENUM_THREADS, 8)
 enumerate_kernel(Params P, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                  int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
                  int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits) {
     const int e = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     __shared__ Pose s_pose[NB];
     __shared__ uint8_t s_shape[NB];
     __shared__ uint64_t s_block[IMG], s_obst[IMG];
     __shared__ uint8_t s_free_b[NB * NF], s_free_f[NB * NF];
     __shared__ uint8_t s_grp_s[BW_MAX_SHAPES * NF], s_grp_f[BW_MAX_SHAPES * NF];
     __shared__ int s_nfree, s_ngrp;
+    // per-chunk candidate tables
+    __shared__ double c_nx[ENUM_CHUNK][NF], c_nz[ENUM_CHUNK][NF], c_cx[ENUM_CHUNK][NF], c_cz[ENUM_CHUNK][NF],
+        c_inx[ENUM_CHUNK][NF];
+    __shared__ int8_t c_nf[ENUM_CHUNK], c_jlo[ENUM_CHUNK], c_jhi[ENUM_CHUNK], c_ilo[ENUM_CHUNK], c_bad[ENUM_CHUNK];
+    __shared__ int c_rowstart[ENUM_CHUNK + 1];
+    __shared__ int c_overlap[ENUM_CHUNK];
 
     const int n = P.n_blocks[e];
     if (tid < n) {
@@ -65,13 +75,14 @@ enumerate_kernel(Params P, const double *__restrict__ ground, int n_ground, cons
     const double eps = 1e-6;
     const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
 
-    for (int a = warp; a < amax; a += ENUM_WARPS) {
-        bw_action act;
-        act.target_block = -1; act.target_face = 0; act.shape = -1; act.face = 0;
-        act.offset_x = 0.0; act.offset_y = 0.0; act.frozen = 0; act.reserved0 = 0;
-        bool ok = false;
-        uint64_t bits0 = 0, bits1 = 0;
-        if (a < count) {
+    // only the first `count` slots are meaningful (n_cand); the rest of the caller's buffers is left alone
+    for (int base = 0; base < count; base += ENUM_CHUNK) {
+        const int nchunk = min(ENUM_CHUNK, count - base);
+        // ---- phase A: thread per candidate
+        if (tid < nchunk) {
+            const int a = base + tid;
+            bw_action act;
+            act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
             const int g = a / per_group, w = a - g * per_group;
             act.shape = s_grp_s[g];
             act.face = s_grp_f[g];
@@ -83,46 +94,71 @@ enumerate_kernel(Params P, const double *__restrict__ ground, int n_ground, cons
                 act.target_face = s_free_f[k];
                 act.offset_x = offsets[oi];
             }
+            cand[(size_t)e * amax + a] = act;
             Pose ps;
             const int err = place_block(P, s_pose, s_shape, n, act, ps);
-            if (err == 0) {
+            int rows = 0;
+            bool bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
+            if (!bad) {
                 const ShapeDev &sh = P.shapes[act.shape];
                 // collision_on_action: any vertex outside the window (gym_env.py:304-323)
-                bool outside = false;
                 for (int v = 0; v < sh.n_verts; v++) {
                     double vx, vz;
                     rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
                     vx = dadd(vx, ps.x);
                     vz = dadd(vz, ps.z);
-                    if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) outside = true;
+                    if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
                 }
-                bits0 = raster_row(P, sh, ps, lane);
-                bits1 = raster_row(P, sh, ps, lane + 32);
-                const bool overlap = ((bits0 & (s_block[lane] | s_obst[lane])) != 0) ||
-                                     ((bits1 & (s_block[lane + 32] | s_obst[lane + 32])) != 0);
-                ok = !outside && !__any_sync(FULLM, overlap);
-            } else {
-                // a full environment (err 2) offers no placement; keep the candidate, mark invalid
-                ok = false;
+                PosedShape o;
+                pose_shape(P, sh, ps, o);
+                for (int k = 0; k < NF; k++) {
+                    c_nx[tid][k] = o.nx[k]; c_nz[tid][k] = o.nz[k]; c_cx[tid][k] = o.cx[k]; c_cz[tid][k] = o.cz[k];
+                    c_inx[tid][k] = o.inv_nx[k];
+                }
+                c_nf[tid] = (int8_t)o.n_faces;
+                c_jlo[tid] = (int8_t)o.j_lo; c_jhi[tid] = (int8_t)o.j_hi; c_ilo[tid] = (int8_t)o.i_lo;
+                if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
             }
+            c_bad[tid] = bad ? 1 : 0;
+            c_overlap[tid] = 0;
+            c_rowstart[tid + 1] = rows;
         }
-        const size_t o = (size_t)e * amax + a;
-        if (lane == 0) {
-            cand[o] = act;
-            valid[o] = ok ? 1 : 0;
+        if (action_bits != nullptr) {   // rows outside the windows are zero
+            uint64_t *dst = action_bits + ((size_t)e * amax + base) * IMG;
+            for (int q = tid; q < nchunk * IMG; q += ENUM_THREADS) dst[q] = 0;
         }
-        if (action_bits != nullptr) {
-            action_bits[o * IMG + lane] = bits0;
-            action_bits[o * IMG + lane + 32] = bits1;
+        __syncthreads();
+        if (tid == 0) {
+            c_rowstart[0] = 0;
+            for (int t = 0; t < nchunk; t++) c_rowstart[t + 1] += c_rowstart[t];
         }
+        __syncthreads();
+        // ---- phase B: thread per (candidate, row of its window)
+        const int npairs = c_rowstart[nchunk];
+        for (int q = tid; q < npairs; q += ENUM_THREADS) {
+            int lo = 0, hi = nchunk - 1;            // largest t with rowstart[t] <= q
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
+            }
+            const int t = lo;
+            const int row = c_ilo[t] + (q - c_rowstart[t]);
+            const uint64_t bits = raster_row_posed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
+                                                   c_jhi[t], row);
+            if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
+            if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
+        }
+        __syncthreads();
+        if (tid < nchunk) valid[(size_t)e * amax + base + tid] = (!c_bad[tid] && !c_overlap[tid]) ? 1 : 0;
+        __syncthreads();
     }
 }
 
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       cudaStream_t stream) {
-    enumerate_kernel<<<P.E, 32 * ENUM_WARPS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                          d_valid, d_n_cand, d_action_bits);
+    enumerate_kernel<<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
+                                                       d_valid, d_n_cand, d_action_bits);
 }
 
 // create_block + collision_on_action for one hypothetical action per env (state untouched)

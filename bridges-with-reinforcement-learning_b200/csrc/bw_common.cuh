@@ -142,36 +142,79 @@ __device__ inline void posed_aabb(const ShapeDev &sh, const Pose &ps, double &xm
 // ---------------------------------------------------------------- raster (K4)
 // Bits of image row `row` covered by shape `sh` posed at `ps`: contains_2d
 // (assembly_env.py:126-137) at the pixel nodes of render_blocks_2d (rendering.py:105-113).
-// Half-plane value (px-cx)*nx + (pz-cz)*nz with individually rounded operations, `<= 0`.
-// Only a conservative index window around the bounding box is visited.
-__device__ inline uint64_t raster_row(const Params &P, const ShapeDev &sh, const Pose &ps, int row) {
+// A pixel is inside iff every half-plane value v = (px-cx)*nx + (pz-cz)*nz, evaluated with
+// individually rounded operations, is <= 0.  Along a row v is weakly monotone in the column index
+// (rounded subtraction, multiplication by a constant and addition all preserve order), so each face
+// admits an interval of columns; its end is located by an estimate of the crossing and then fixed
+// with the exact test, which makes the result identical to testing all 64 pixels one by one.
+__device__ __forceinline__ bool pixel_in_halfplane(double px, double cx, double nx, double vz) {
+    return dadd(dmul(dsub(px, cx), nx), vz) <= 0.0;
+}
+
+// posed half-planes + pixel window of one block: everything about a block the raster needs
+struct PosedShape {
+    double nx[NF], nz[NF], cx[NF], cz[NF], inv_nx[NF];
+    int n_faces;
+    int j_lo, j_hi, i_lo, i_hi;     // conservative window of pixel columns / rows (may be empty)
+};
+
+__device__ inline void pose_shape(const Params &P, const ShapeDev &sh, const Pose &ps, PosedShape &o) {
     double xmin, xmax, zmin, zmax;
     posed_aabb(sh, ps, xmin, xmax, zmin, zmax);
-    int j_lo = (int)floor((xmin - P.xlim0) * P.inv_step_x) - 1;
-    int j_hi = (int)ceil((xmax - P.xlim0) * P.inv_step_x) + 1;
-    const int i_lo = (int)floor((P.ylim1 - zmax) * P.inv_step_y) - 1;
-    const int i_hi = (int)ceil((P.ylim1 - zmin) * P.inv_step_y) + 1;
-    j_lo = max(j_lo, 0);
-    j_hi = min(j_hi, IMG - 1);
-    if (row < i_lo || row > i_hi || j_hi < j_lo) return 0;
-    const double pz = P.ys[row];
-    uint64_t bits = (j_hi - j_lo + 1 >= 64) ? ~0ull : (((1ull << (j_hi - j_lo + 1)) - 1) << j_lo);
-    for (int k = 0; k < sh.n_faces; k++) {
-        double nx, nz, ax, az;
-        rot(ps.c, ps.s, sh.face_nx[k], sh.face_nz[k], nx, nz);
-        rot(ps.c, ps.s, sh.face_cx[k], sh.face_cz[k], ax, az);
-        const double cx = dadd(ax, ps.x), cz = dadd(az, ps.z);
-        const double vz = dmul(dsub(pz, cz), nz);
-        uint64_t keep = 0;
-        for (int j = j_lo; j <= j_hi; j++) {
-            if (!((bits >> j) & 1ull)) continue;
-            const double v = dadd(dmul(dsub(P.xs[j], cx), nx), vz);
-            if (v <= 0.0) keep |= 1ull << j;
+    o.j_lo = max((int)floor((xmin - P.xlim0) * P.inv_step_x) - 1, 0);
+    o.j_hi = min((int)ceil((xmax - P.xlim0) * P.inv_step_x) + 1, IMG - 1);
+    o.i_lo = max((int)floor((P.ylim1 - zmax) * P.inv_step_y) - 1, 0);
+    o.i_hi = min((int)ceil((P.ylim1 - zmin) * P.inv_step_y) + 1, IMG - 1);
+    o.n_faces = sh.n_faces;
+    for (int k = 0; k < NF; k++) {
+        if (k < sh.n_faces) {
+            double ax, az;
+            rot(ps.c, ps.s, sh.face_nx[k], sh.face_nz[k], o.nx[k], o.nz[k]);
+            rot(ps.c, ps.s, sh.face_cx[k], sh.face_cz[k], ax, az);
+            o.cx[k] = dadd(ax, ps.x);
+            o.cz[k] = dadd(az, ps.z);
+            o.inv_nx[k] = (o.nx[k] != 0.0) ? 1.0 / o.nx[k] : 0.0;
         }
-        bits &= keep;
-        if (!bits) break;
     }
-    return bits;
+}
+
+// bits of image row `row` for a posed shape given by arrays (which may live in shared memory)
+__device__ inline uint64_t raster_row_posed(const Params &P, int n_faces, const double *nx, const double *nz,
+                                            const double *cx, const double *cz, const double *inv_nx, int j_lo,
+                                            int j_hi, int row) {
+    const double pz = P.ys[row];
+    int lo = j_lo, hi = j_hi;                 // surviving column interval [lo, hi]
+    for (int k = 0; k < n_faces && lo <= hi; k++) {
+        const double fnx = nx[k], fcx = cx[k];
+        const double vz = dmul(dsub(pz, cz[k]), nz[k]);
+        if (fnx == 0.0) {                     // the value does not depend on the column
+            if (!pixel_in_halfplane(P.xs[lo], fcx, fnx, vz)) hi = lo - 1;
+            continue;
+        }
+        // estimated crossing column of v(px) = 0 (only an estimate: the exact test below decides)
+        const double g = (fcx - vz * inv_nx[k] - P.xlim0) * P.inv_step_x;
+        if (fnx > 0.0) {                      // v increases with the column: inside = [lo, b]
+            int b = (g >= (double)hi) ? hi : (g < (double)lo ? lo - 1 : (int)floor(g));
+            while (b < hi && pixel_in_halfplane(P.xs[b + 1], fcx, fnx, vz)) b++;
+            while (b >= lo && !pixel_in_halfplane(P.xs[b], fcx, fnx, vz)) b--;
+            hi = b;
+        } else {                              // v decreases with the column: inside = [b, hi]
+            int b = (g <= (double)lo) ? lo : (g > (double)hi ? hi + 1 : (int)ceil(g));
+            while (b > lo && pixel_in_halfplane(P.xs[b - 1], fcx, fnx, vz)) b--;
+            while (b <= hi && !pixel_in_halfplane(P.xs[b], fcx, fnx, vz)) b++;
+            lo = b;
+        }
+    }
+    if (lo > hi) return 0;
+    const int w = hi - lo + 1;
+    return (w >= 64) ? ~0ull : (((1ull << w) - 1) << lo);
+}
+
+__device__ inline uint64_t raster_row(const Params &P, const ShapeDev &sh, const Pose &ps, int row) {
+    PosedShape o;
+    pose_shape(P, sh, ps, o);
+    if (row < o.i_lo || row > o.i_hi || o.j_hi < o.j_lo) return 0;
+    return raster_row_posed(P, o.n_faces, o.nx, o.nz, o.cx, o.cz, o.inv_nx, o.j_lo, o.j_hi, row);
 }
 
 }  // namespace bw
