@@ -195,6 +195,52 @@ def profiled_traffic():
     return None
 
 
+def run_sweep(args, rank, local_rank, world, dev):
+    """BASELINE.json configs[3]: 65,536 random assemblies (1..15 blocks, shapes trapezoid / hexagon /
+    cube1, mu cycled over 0.3 / 0.8 / 2.0), sharded contiguously over the ranks; the timed unit is
+    one stability check of every assembly (interfaces + both equilibrium verdicts), no placement."""
+    import numpy as np
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    from bridges_b200.sharding import max_over_ranks, shard_range
+    total = args.sweep_assemblies
+    lo, hi = shard_range(total, rank, world)
+    n = hi - lo
+    env = BatchedAssemblyGym(n, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"], max_steps=None,
+                             device=local_rank)
+    ids = np.arange(lo, hi)
+    env.set_mu(np.array([0.3, 0.8, 2.0])[ids % 3])
+    env.reset(dict())
+    rng = np.random.default_rng(0)
+    target = rng.integers(1, 16, size=total)[lo:hi]                 # n_blocks ~ U{1..15}
+    for k in range(15):
+        env.enumerate_actions(np.linspace(-2.0, 4.0, 13), (0.0, 0.25, -0.25), amax=1024, with_bits=False)
+        acts, _ = env.select_random(seed=12345 + k)
+        env.step(acts, mask=(target > k).astype(np.uint8))
+    env.sync()
+    K = args.sweep_steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for _ in range(3):
+        env.evaluate()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record()
+        env.evaluate()
+        b.record()
+    torch.cuda.synchronize()
+    t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    out = env.read_out()
+    (t,) = max_over_ranks([t], device=dev)
+    stats = dict(mean_blocks=float(out["n_blocks"].mean()), stable_frac=float(out["stable"].mean()),
+                 stable_unfrozen_frac=float(out["stable_unfrozen"].mean()),
+                 mean_newton_iters=float(out["newton_iters"].mean()),
+                 not_converged=int((out["solver_status"] != 0).sum()))
+    env.close()
+    return {"metric": "assembly stability checks/sec (two verdicts each)", "value": total * K / t,
+            "unit": "assemblies/s", "assemblies": total, "steps": K, "ms_per_pass": 1e3 * t / K, "scaling": "strong",
+            "rank0_stats": stats}
+
+
 def run_gpu(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -233,9 +279,18 @@ def run_gpu(args, rank, local_rank, world):
     amax = 128
     lib.bw_set_timing(h, 0)
 
-    def choose_actions(step_id):
-        env.enumerate_actions(X_GROUND, (0.0,), amax=amax, with_bits=False)
-        return env.select_random(seed=args.seed * 1000003 + step_id * 7919 + rank)[0]
+    cand_ev = []
+
+    def choose_actions(step_id, timed=False):
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        env.enumerate_actions(X_GROUND, (0.0,), amax=amax, with_bits=True)
+        acts = env.select_random(seed=args.seed * 1000003 + step_id * 7919 + rank)[0]
+        if timed:
+            b.record()
+            cand_ev.append((a, b))
+        return acts
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,7 +314,7 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     wall0 = time.perf_counter()
     for i in range(K):
-        acts = choose_actions(W + i)
+        acts = choose_actions(W + i, timed=True)
         if not args.no_flush:
             flush.fill_(i & 0xff)                   # evict the 126 MB L2
         ev[i][0].record()
@@ -274,6 +329,7 @@ def run_gpu(args, rank, local_rank, world):
     launches = env.kernel_launches() - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = sum(step_ms) * 1e-3
+    t_cand = sum(a.elapsed_time(b) for a, b in cand_ev) * 1e-3
 
     # ---- statistics of the sampled steps (algorithmic bytes / flops per launch)
     outs = np.concatenate([s.cpu().numpy().view(dt["step_out"]) for s in stats])
@@ -318,7 +374,8 @@ def run_gpu(args, rank, local_rank, world):
     d2h_f32 = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
 
     # ---- max over ranks
-    t_dev, t_e2e, t_e2e_f32, wall = max_over_ranks([t_dev, t_e2e, t_e2e_f32, wall], device=dev)
+    sweep = run_sweep(args, rank, local_rank, world, dev) if args.sweep else None
+    t_dev, t_e2e, t_e2e_f32, wall, t_cand = max_over_ranks([t_dev, t_e2e, t_e2e_f32, wall, t_cand], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,8 +408,14 @@ def run_gpu(args, rank, local_rank, world):
                       "mean_newton_iters_per_step": float(outs["newton_iters"].mean()),
                       "stable_frac": float(outs["stable"].mean()), "terminated_frac": float(outs["terminated"].mean()),
                       "solver_not_converged": int((outs["solver_status"] != 0).sum())},
+        "with_candidate_stage": {"value": world * E * K / (t_dev + t_cand), "unit": UNIT,
+                                 "candidate_ms_per_step": 1e3 * t_cand / K,
+                                 "note": "step + enumerate/filter kernel (candidates with bit rasters and validity "
+                                         "mask, robotoddler/utils/actions.py:7-82) + random selection"},
         "wall_s_timed_region": wall,
     }
+    if sweep is not None:
+        line["sweep"] = sweep
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
@@ -375,6 +438,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0, help="CPU-arm worker processes (0 = all host cores)")
     ap.add_argument("--no-flush", action="store_true", help="profiling only: skip the L2 flush between steps")
+    ap.add_argument("--sweep", action="store_true", help="also run the 65,536-assembly stability sweep (configs[3])")
+    ap.add_argument("--sweep-assemblies", type=int, default=65536)
+    ap.add_argument("--sweep-steps", type=int, default=10)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

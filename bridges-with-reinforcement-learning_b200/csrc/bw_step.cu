@@ -424,6 +424,8 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             stable = 1;
         } else {
             status = S.solve(res, iters);
+            // out of stages with a residual already under the verdict threshold: converged within the margin
+            if (status == 2 && res <= P.stable_tol) status = 0;
             stable = (status != 2) && (res <= P.stable_tol);
         }
 #ifdef BW_PROFILE
