@@ -19,8 +19,7 @@ struct bw_handle {
     bool own_stream = false;
     bool shapes_loaded = false;
     bool timing = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ev_obs = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     int smem_step = 0;
     int64_t launches = 0;
     char err[512] = {0};

@@ -35,8 +35,9 @@ def library():
             Shape(urdf_file="shapes/cube1.urdf", name="cube")]
 
 
-def random_assembly(rng, shapes, max_blocks=15, xlim=(-3.0, 7.0), ylim=(0.0, 10.0), tries=40):
-    """Returns the list of Actions of one random valid rollout (no stability filter)."""
+def random_assembly(rng, shapes, max_blocks=15, xlim=(-3.0, 7.0), ylim=(0.0, 10.0), tries=40, scale=1.0):
+    """Returns the list of Actions of one random valid rollout (no stability filter).
+    `scale` shrinks the offsets for the small shapes of the library (block.urdf, small_cube.urdf, ...)."""
     env = AssemblyGym(shapes=shapes, targets=[], obstacles=[], reward_fct=sparse_reward, restrict_2d=True,
                       assembly_env=AssemblyEnv(stability=None))
     n_blocks = int(rng.integers(1, max_blocks + 1))
@@ -47,17 +48,17 @@ def random_assembly(rng, shapes, max_blocks=15, xlim=(-3.0, 7.0), ylim=(0.0, 10.
             shape = int(rng.integers(len(shapes)))
             face = int(rng.integers(shapes[shape].num_faces_2d))
             if k == 0 or rng.random() < 0.2:
-                action = Action(-1, 0, shape, face, float(rng.uniform(-2.0, 4.0)), 0.0)
+                action = Action(-1, 0, shape, face, float(rng.uniform(-2.0, 4.0)) * scale, 0.0)
             else:
                 tb = int(rng.integers(k))
                 tf = int(rng.integers(env.assembly_env.blocks[tb].num_faces_2d))
                 if (tb, tf) in occupied:
                     continue
-                action = Action(tb, tf, shape, face, float(rng.choice([0.0, 0.25, -0.25])), 0.0)
+                action = Action(tb, tf, shape, face, float(rng.choice([0.0, 0.25, -0.25])) * scale, 0.0)
             if env.collision_on_action(action, xlim, ylim):
                 continue
             block = env.create_block(action)
-            if any(sat_overlap(block.polygon_2d, other.polygon_2d) for other in env.assembly_env.blocks):
+            if any(sat_overlap(block.polygon_2d, other.polygon_2d, eps=1e-7 * scale) for other in env.assembly_env.blocks):
                 continue
             env.assembly_env.blocks.append(block)
             if action.target_block >= 0:

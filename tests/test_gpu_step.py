@@ -248,3 +248,51 @@ def test_masks_empty_scene_and_capacity():
     assert list(env.read_out()["error"]) == [2] * 4
     _, n = env.get_state()
     assert list(n) == [16] * 4
+
+
+def test_small_shapes_and_densities():
+    """The 0.05-scale part of the block library (block.urdf, small_cube.urdf, t_block.urdf, v_block.urdf):
+    weights ~1e-4 and lever arms ~0.05 exercise the normalisation of the equilibrium system."""
+    from oracle import synth
+    from oracle.assembly_env import AssemblyEnv as OEnv
+    from oracle.assembly_env import Shape as OShape
+    from oracle.gym_env import Action as OAction
+    from oracle.gym_env import AssemblyGym as OGym
+    from oracle.gym_env import sparse_reward as o_reward
+    names = ["block", "small_cube", "t_block", "v_block"]
+    urdfs = [f"shapes/{n}.urdf" for n in names]
+    rng = np.random.default_rng(99)
+    N = 64
+    oshapes = [OShape(urdf_file=u, name=n) for u, n in zip(urdfs, names)]
+    plans = [synth.random_assembly(rng, oshapes, max_blocks=8, scale=0.08) for _ in range(N)]
+    density = 2.5
+    env = _gpu_env(N, urdfs, density=density)
+    mus = [synth.MUS[i % 3] for i in range(N)]
+    env.set_mu(mus)
+    env.reset(dict())
+    oenvs = [OGym(shapes=oshapes, obstacles=[], targets=[], reward_fct=o_reward, restrict_2d=True,
+                  assembly_env=OEnv(mu=mus[i], density=density)) for i in range(N)]
+    n_checked = n_stable = n_itf = 0
+    for k in range(max(len(p) for p in plans)):
+        acts = [(p[k].target_block, p[k].target_face, p[k].shape, p[k].face, p[k].offset_x, p[k].offset_y)
+                if k < len(p) else None for p in plans]
+        env.step(acts)
+        out = env.read_out()
+        blocks, _ = env.get_state()
+        for e in range(N):
+            if acts[e] is None:
+                continue
+            oenvs[e].step(OAction(*acts[e]))
+            frozen, unfrozen = oenvs[e].stabilities_freezing()
+            r_frozen, r_unfrozen = H.residuals(oenvs[e])
+            ob = oenvs[e].assembly_env.blocks
+            assert (blocks[e][len(ob) - 1]["x"], blocks[e][len(ob) - 1]["z"]) == ob[-1].pose[:2]
+            assert out[e]["n_interfaces"] == len(oenvs[e].assembly_env.cra_assembly.interfaces)
+            n_itf += out[e]["n_interfaces"]
+            for got, want, r_or in ((out[e]["stable"], frozen, r_frozen), (out[e]["stable_unfrozen"], unfrozen, r_unfrozen)):
+                if r_or is not None and BAND[0] < r_or < BAND[1]:
+                    continue
+                assert bool(got) == bool(want), (e, k, r_or)
+                n_checked += 1
+                n_stable += bool(want)
+    assert n_checked > 300 and n_stable > 30 and n_itf > 300
