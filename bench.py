@@ -234,7 +234,7 @@ def run_sweep(args, rank, local_rank, world, dev):
     stats = dict(mean_blocks=float(out["n_blocks"].mean()), stable_frac=float(out["stable"].mean()),
                  stable_unfrozen_frac=float(out["stable_unfrozen"].mean()),
                  mean_newton_iters=float(out["newton_iters"].mean()),
-                 not_converged=int((out["solver_status"] != 0).sum()))
+                 not_converged=int(((out["solver_status"] & 3) != 0).sum()))
     env.close()
     return {"metric": "assembly stability checks/sec (two verdicts each)", "value": total * K / t,
             "unit": "assemblies/s", "assemblies": total, "steps": K, "ms_per_pass": 1e3 * t / K, "scaling": "strong",
@@ -407,7 +407,8 @@ def run_gpu(args, rank, local_rank, world):
         "env_stats": {"mean_blocks": float(outs["n_blocks"].mean()), "mean_interfaces": float(outs["n_interfaces"].mean()),
                       "mean_newton_iters_per_step": float(outs["newton_iters"].mean()),
                       "stable_frac": float(outs["stable"].mean()), "terminated_frac": float(outs["terminated"].mean()),
-                      "solver_not_converged": int((outs["solver_status"] != 0).sum())},
+                      "solver_not_converged": int(((outs["solver_status"] & 3) != 0).sum()),
+                      "verdicts_implied_frac": float(((outs["solver_status"] & 4) != 0).mean() + ((outs["solver_status"] & 8) != 0).mean()) / 2},
         "with_candidate_stage": {"value": world * E * K / (t_dev + t_cand), "unit": UNIT,
                                  "candidate_ms_per_step": 1e3 * t_cand / K,
                                  "note": "step + enumerate/filter kernel (candidates with bit rasters and validity "

@@ -237,6 +237,7 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     CU(dev_alloc(h, &P.mu, E, false));
     CU(dev_alloc(h, &P.done, E));
     CU(dev_alloc(h, &P.last_out, E));
+    CU(dev_alloc(h, &P.su_valid, E));
     {
         std::vector<double> mu(E, cfg->mu);
         CU(cudaMemcpyAsync(P.mu, mu.data(), sizeof(double) * E, cudaMemcpyHostToDevice, h->stream));
@@ -336,6 +337,8 @@ int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask) {
     if (!h || !h_mask) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(h->P.static_mask, h_mask, sizeof(uint32_t) * h->P.E, cudaMemcpyHostToDevice, h->stream));
+    // the verdicts of the last step no longer describe these supports
+    CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }

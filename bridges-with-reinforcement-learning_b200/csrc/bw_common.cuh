@@ -82,6 +82,7 @@ struct Params {
     double *mu;                // [E]
     uint8_t *done;             // [E] last step returned terminated | truncated
     bw_step_out *last_out;     // [E] copy of the last step result (binary features of observe)
+    uint8_t *su_valid;         // [E] last_out[e].stable_unfrozen describes the current blocks and supports
 };
 
 // ---------------------------------------------------------------- placement (K1)

@@ -78,6 +78,7 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
         o.stable_unfrozen = 1;
         for (int i = 0; i < BW_MAX_TARGETS; i++) o.distance_to_targets[i] = INFINITY;
         P.last_out[e] = o;
+        P.su_valid[e] = (s_n == 0);       // pre-placed blocks: the evaluation that follows sets it
     }
     if (tid < NB) P.face_occ[(size_t)e * NB + tid] = 0;
     __syncthreads();

@@ -29,6 +29,13 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+__device__ __forceinline__ void warp_sum2(double &a, double &b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+    }
+}
 __device__ __forceinline__ void warp_sum3(double &a, double &b, double &c) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -87,6 +94,11 @@ struct Solver {
     uint8_t *freebody;       // free block index -> body
     int m, nfree, nc, nitf, lane;
     double mu, inv_den;
+    double r_exit;           // a residual <= r_exit ends the solve as feasible (1e-9 when the forces are
+                             // wanted, else the verdict threshold: the verdict cannot change below it)
+    const volatile int *sibling;   // verdict of the other solve of this environment (-1 = still running)
+    int implied_by;          // sibling verdict that decides this solve too (-1: never)
+    bool exit_anytime;       // false when the min-norm forces are wanted (needs the converged dual iterate)
     double flops;            // work estimate, see DESIGN.md section 6
 #ifdef BW_PROFILE
     long long acc_t[6];      // grad, assemble, factor+solve, A^T d + dots, line search + update, residual
@@ -364,7 +376,8 @@ struct Solver {
         return warp_sum(fh);
     }
 
-    // returns status: 0 feasible (r <= 1e-9), 1 stalled at r* > 0, 2 not converged
+    // returns status: 0 feasible (r <= r_exit), 1 stalled at r* > 0, 2 not converged,
+    // 3 verdict implied by the sibling solve (released-block equilibrium => frozen-block equilibrium)
     __device__ int solve(double &r_out, int &iters_out) {
 #pragma unroll 1
         for (int i = lane; i < m; i += 32) y[i] = 0.0;
@@ -384,21 +397,28 @@ struct Solver {
 #pragma unroll 1
             for (int i = lane; i < m; i += 32) yk[i] = y[i];
             __syncwarp();
+            bool have_r = false;
 #pragma unroll 1
             for (int it = 0; it < MAX_NEWTON; it++) {
+                if (implied_by >= 0 && *sibling == implied_by) { status = 3; break; }
                 BW_T0(t_a);
                 project_all();
                 __syncwarp();
-                double gn2 = 0.0;
+                // gradient of the proximal sub-problem and, for free, the equilibrium residual b - A f
+                double gn2 = 0.0, rr2 = 0.0;
 #pragma unroll 1
                 for (int i = lane; i < m; i += 32) {
-                    const double gr = b[i] - a_times_f_row(i) - (y[i] - yk[i]) * inv_rho;
+                    const double px = (y[i] - yk[i]) * inv_rho;
+                    const double rs = b[i] - a_times_f_row(i);
+                    const double gr = rs - px;
                     d[i] = gr;                     // kept for the dot products below
                     gn2 += gr * gr;
+                    rr2 += rs * rs;
                 }
-                gn2 = warp_sum(gn2);
+                warp_sum2(gn2, rr2);
                 BW_ACC(0, t_a);
-                if (gn2 <= 1e-20) break;
+                // f is in K, so ||b - A f|| bounds r* from above at every iterate
+                if (gn2 <= 1e-20 || (exit_anytime && rr2 <= r_exit * r_exit)) { r = sqrt(rr2); have_r = true; break; }
                 BW_T0(t_b);
                 assemble_H(inv_rho);               // zero-fills rows 0..m-1, leaves row m alone
 #pragma unroll 1
@@ -468,10 +488,13 @@ struct Solver {
                 const double ymax = warp_max(yy);
                 if (t * t * dd <= 1e-30 * fmax(1.0, ymax * ymax)) break;
             }
-            BW_T0(t_f);
-            r = residual();
-            BW_ACC(5, t_f);
-            if (r <= 1e-9) { status = 0; break; }
+            if (status == 3) break;
+            if (!have_r) {                         // left the Newton loop without a fresh gradient pass
+                BW_T0(t_f);
+                r = residual();
+                BW_ACC(5, t_f);
+            }
+            if (r <= r_exit) { status = 0; break; }
             if (rprev >= 0.0 && fabs(r - rprev) <= 1e-3 * r) { status = 1; break; }
             // a feasible system loses two orders of magnitude per stage (rho x 100); a residual that
             // stays above 90% of its previous value and far above the verdict threshold has stalled at r*

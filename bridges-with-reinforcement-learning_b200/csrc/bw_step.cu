@@ -13,6 +13,7 @@
 // solved in its dual (3 unknowns per free block) by a proximal-point iteration whose
 // sub-problems are solved by a semismooth Newton method.  Each
 // problem lives in the shared memory of its warp; reductions are warp shuffles.
+#include <cstdlib>
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
 #include "bw_solver.cuh"
@@ -40,6 +41,21 @@ void upload_step_tables() {
     cudaMemcpyToSymbol(c_pair_b, pb, sizeof(pb));
     cudaMemcpyToSymbol(c_tri_i, ti, sizeof(ti));
     cudaMemcpyToSymbol(c_tri_j, tj, sizeof(tj));
+    // tuning hook (tools/ only): BW_RHO_SCHEDULE="1e2,1e4,..." overrides the proximal schedule
+    if (const char *env = getenv("BW_RHO_SCHEDULE")) {
+        double rho[NSCHED];
+        int k = 0;
+        char *end = nullptr;
+        for (const char *q = env; k < NSCHED && *q; q = (*end == ',') ? end + 1 : end) {
+            rho[k] = strtod(q, &end);
+            if (end == q) break;
+            k++;
+        }
+        if (k > 0) {
+            for (; k < NSCHED; k++) rho[k] = rho[k - 1];
+            cudaMemcpyToSymbol(c_rho, rho, sizeof(rho));
+        }
+    }
 }
 
 // ------------------------------------------------------------------ shared memory layout
@@ -133,6 +149,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     __shared__ double sh_L0;
     __shared__ double sh_res[2];
     __shared__ int sh_status[2], sh_iters[2], sh_stable[2];
+    __shared__ volatile int sh_verdict[2];   // published as soon as a solve ends; -1 = running
     __shared__ double sh_flops[2];
 #ifdef BW_PROFILE
     __shared__ long long sh_prof_solve[2];
@@ -154,7 +171,12 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         s_pose[tid] = P.pose[(size_t)e * NB + tid];
         s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
     }
-    if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; }
+    if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; }
+    // stabilities_freezing()[1] of the previous step (all of today's free blocks were free and in
+    // equilibrium): the frozen solve of this step has the same rows plus contacts to a new support,
+    // so that equilibrium still holds -- no solve needed
+    const bool prev_released_ok = P.su_valid[e] != 0 && P.last_out[e].stable_unfrozen != 0;
+    const double prev_released_res = P.last_out[e].residual_unfrozen;
     __syncthreads();
 
     // ---------------- phase 1: placement (thread 0)
@@ -394,6 +416,12 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         S.flops = 0.0;
         S.mu = P.mu[e];
         S.inv_den = 1.0 / (1.0 + S.mu * S.mu);
+        const bool want_forces = (save_itf != nullptr && warp == save_variant);
+        S.r_exit = want_forces ? 1e-9 : fmin(P.stable_tol, 1e-6);
+        S.exit_anytime = !want_forces;
+        // released-block equilibrium => frozen-block equilibrium; no frozen equilibrium => no released one
+        S.sibling = &sh_verdict[warp ^ 1];
+        S.implied_by = want_forces ? -1 : (warp == 0 ? 1 : 0);
         // free blocks -> rows
         const bool is_free = (lane < n) && !((vmask >> lane) & 1u);
         const unsigned fb = __ballot_sync(FULL, is_free);
@@ -422,12 +450,16 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             res = stable ? 0.0 : 1.0;
         } else if (nfree == 0) {
             stable = 1;
+        } else if (warp == 0 && placed && prev_released_ok && !want_forces) {
+            stable = 1; status = 4; res = prev_released_res;
         } else {
             status = S.solve(res, iters);
             // out of stages with a residual already under the verdict threshold: converged within the margin
             if (status == 2 && res <= P.stable_tol) status = 0;
-            stable = (status != 2) && (res <= P.stable_tol);
+            if (status == 3) { stable = S.implied_by; res = nan(""); }
+            else stable = (status != 2) && (res <= P.stable_tol);
         }
+        if (lane == 0) { sh_verdict[warp] = stable; __threadfence_block(); }
 #ifdef BW_PROFILE
         if (lane == 0) {
             sh_prof_solve[warp] = clock64() - prof_t[2];
@@ -522,7 +554,8 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
 #endif
         o.stable = (uint8_t)stable_frozen;
         o.stable_unfrozen = (uint8_t)stable_unfrozen;
-        o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0));
+        o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0) |
+                                    (sh_status[0] >= 3 ? 4 : 0) | (sh_status[1] >= 3 ? 8 : 0));
         o.residual = sh_res[0];
         o.residual_unfrozen = sh_res[1];
         o.newton_iters = sh_iters[0] + sh_iters[1];
@@ -578,6 +611,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
             out[e].lin_reward = lr;
         }
         P.last_out[e] = out[e];
+        P.su_valid[e] = 1;
         if (binary != nullptr) {
             float *bf = binary + (size_t)e * 6;   // get_state_features, successor_dqn.py:53-60
             bf[0] = (float)stable_frozen; bf[1] = 0.0f; bf[2] = 0.0f; bf[3] = 0.0f; bf[4] = 0.0f; bf[5] = 0.0f;

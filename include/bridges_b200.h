@@ -135,7 +135,10 @@ typedef struct {
     uint8_t collision_block, collision_obstacle, collision_floor, collision_boundary;
     uint8_t terminated;           /* gym_env.py:141-144 */
     uint8_t truncated;            /* max_steps reached */
-    uint8_t solver_status;        /* bit0 / bit1: frozen / unfrozen solve did not converge (stable=None) */
+    uint8_t solver_status;        /* bit0 / bit1: frozen / unfrozen solve did not converge (stable=None);
+                                     bit2 / bit3: frozen / unfrozen verdict implied without (finishing) its own solve
+                                     (released-block equilibrium implies frozen-block equilibrium, within a step and
+                                     from the previous step's released verdict): residual is NaN or the implying one */
     uint8_t error;                /* 1 = invalid action indices, 2 = capacity exceeded */
     uint8_t n_targets_reached;
     uint8_t reserved1[4];
