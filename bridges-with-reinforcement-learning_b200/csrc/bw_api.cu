@@ -155,6 +155,10 @@ void bw_config_default(bw_config *cfg) {
     cfg->amin = 1e-3;
     cfg->stable_tol = 1e-6;
     cfg->stream = nullptr;
+    cfg->collision_mode = 0;
+    cfg->collision_tol = 0.005;
+    cfg->bounds_lo[0] = -3.0; cfg->bounds_lo[1] = -3.0; cfg->bounds_lo[2] = -1.0;
+    cfg->bounds_hi[0] = 7.0; cfg->bounds_hi[1] = 7.0; cfg->bounds_hi[2] = 9.0;
 }
 
 const char *bw_last_error(const bw_handle *h) { return h ? h->err : "null handle"; }
@@ -222,8 +226,13 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     CU(cudaMemcpyAsync(h->d_ys, ys, sizeof(ys), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));   // xs/ys live on this stack frame
     P.xs = h->d_xs; P.ys = h->d_ys;
-    CU(dev_alloc(h, &h->d_shapes, BW_MAX_SHAPES));
+    CU(dev_alloc(h, &h->d_shapes, BW_MAX_SHAPES + 1));    // the last entry is the obstacle / target marker
     P.shapes = h->d_shapes;
+    P.marker = h->d_shapes + BW_MAX_SHAPES;
+    if (cfg->collision_mode != 0 && cfg->collision_mode != 1) return fail(h, BW_ERR_INVALID, "collision_mode must be 0 or 1");
+    P.collision_mode = cfg->collision_mode;
+    P.collision_tol = cfg->collision_tol;
+    for (int k = 0; k < 3; k++) { P.bounds_lo[k] = cfg->bounds_lo[k]; P.bounds_hi[k] = cfg->bounds_hi[k]; }
 
     CU(dev_alloc(h, &P.n_blocks, E));
     CU(dev_alloc(h, &P.pose, (size_t)E * NB));
@@ -273,8 +282,12 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
         ShapeDev marker;
         default_marker(marker);
         upload_obs_tables(k, &marker);
+        CU(cudaMemcpyAsync(h->d_shapes + BW_MAX_SHAPES, &marker, sizeof(ShapeDev), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
     }
-    h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf);
+    // the step kernel keeps the block library in shared memory: sized for the largest library here,
+    // re-sized for the actual one by bw_load_shapes
+    h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf, BW_MAX_SHAPES);
     CU(configure_step(h->smem_step));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
@@ -299,6 +312,7 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     CU(cudaMemcpyAsync(h->d_shapes, dev, sizeof(ShapeDev) * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->P.n_shapes = n;
+    h->smem_step = step_smem_bytes(h->P.max_blocks, h->P.max_itf, n);
     h->shapes_loaded = true;
     return BW_OK;
 }
@@ -311,6 +325,8 @@ int bw_set_marker_shape(bw_handle *h, const bw_shape_desc *h_shape) {
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
     upload_obs_tables(nullptr, &d);
+    CU(cudaMemcpyAsync(h->d_shapes + BW_MAX_SHAPES, &d, sizeof(ShapeDev), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return BW_OK;
 }

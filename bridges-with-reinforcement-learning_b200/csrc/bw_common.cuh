@@ -69,6 +69,10 @@ struct Params {
     const double *xs;          // [IMG] pixel x coordinates (numpy linspace semantics)
     const double *ys;          // [IMG] pixel z coordinates, row 0 = top
     const ShapeDev *shapes;    // [n_shapes]
+    const ShapeDev *marker;    // the 0.6 cube of obstacles / target markers (cube06.urdf)
+    int32_t collision_mode;    // 0: flags constant False; 1: polygon penetration (assembly_env.py:346-391)
+    double collision_tol;
+    double bounds_lo[3], bounds_hi[3];
     // state
     int32_t *n_blocks;         // [E]
     Pose *pose;                // [E][NB]
@@ -140,6 +144,56 @@ __device__ inline void posed_aabb(const ShapeDev &sh, const Pose &ps, double &xm
     }
 }
 
+// ---------------------------------------------------------------- collision (K1, collision_mode = 1)
+// _check_collision (assembly_env.py:346-391): "contact distance < -tol" as the exact penetration of
+// two convex polygons.  sep = max over the faces of both polygons of the min over the other polygon's
+// vertices of (v - c).n; collision iff sep < -tol, i.e. iff the min of EVERY face is below -tol.
+// A FaceView is a posed face table: normals, centres and the two end points of every face (the end
+// points of all faces are the polygon's vertices), `stride` doubles apart, translated by (tx, tz).
+struct FaceView {
+    const double *nx, *nz, *cx, *cz, *e0x, *e0z, *e1x, *e1z;
+    int stride, nf;
+    double tx, tz;
+};
+
+// true iff every face of `a` sees all vertices of `b` deeper than `tol` behind it
+__device__ inline bool faces_all_penetrated(const FaceView &a, const FaceView &b, double tol) {
+    for (int f = 0; f < a.nf; f++) {
+        const int i = f * a.stride;
+        const double nx = a.nx[i], nz = a.nz[i];
+        const double cx = dadd(a.cx[i], a.tx), cz = dadd(a.cz[i], a.tz);
+        double smin = INFINITY;
+        for (int g = 0; g < b.nf; g++) {
+            const int j = g * b.stride;
+            const double v0 = dadd(dmul(dsub(dadd(b.e0x[j], b.tx), cx), nx), dmul(dsub(dadd(b.e0z[j], b.tz), cz), nz));
+            const double v1 = dadd(dmul(dsub(dadd(b.e1x[j], b.tx), cx), nx), dmul(dsub(dadd(b.e1z[j], b.tz), cz), nz));
+            smin = fmin(smin, fmin(v0, v1));
+        }
+        if (!(smin < -tol)) return false;      // a separating (or merely touching) axis
+    }
+    return true;
+}
+
+__device__ inline bool polygons_collide(const FaceView &a, const FaceView &b, double tol) {
+    return faces_all_penetrated(a, b, tol) && faces_all_penetrated(b, a, tol);
+}
+
+__device__ inline FaceView face_view_posed(const double *faces8, int nf) {   // [nf][8] = nx nz cx cz e0x e0z e1x e1z
+    FaceView v;
+    v.nx = faces8; v.nz = faces8 + 1; v.cx = faces8 + 2; v.cz = faces8 + 3;
+    v.e0x = faces8 + 4; v.e0z = faces8 + 5; v.e1x = faces8 + 6; v.e1z = faces8 + 7;
+    v.stride = 8; v.nf = nf; v.tx = 0.0; v.tz = 0.0;
+    return v;
+}
+
+__device__ inline FaceView face_view_shape(const ShapeDev &sh, double tx, double tz) {   // unrotated shape at (tx, tz)
+    FaceView v;
+    v.nx = sh.face_nx; v.nz = sh.face_nz; v.cx = sh.face_cx; v.cz = sh.face_cz;
+    v.e0x = sh.end0_x; v.e0z = sh.end0_z; v.e1x = sh.end1_x; v.e1z = sh.end1_z;
+    v.stride = 1; v.nf = sh.n_faces; v.tx = tx; v.tz = tz;
+    return v;
+}
+
 // ---------------------------------------------------------------- raster (K4)
 // Bits of image row `row` covered by shape `sh` posed at `ps`: contains_2d
 // (assembly_env.py:126-137) at the pixel nodes of render_blocks_2d (rendering.py:105-113).
@@ -180,14 +234,15 @@ __device__ inline void pose_shape(const Params &P, const ShapeDev &sh, const Pos
 }
 
 // bits of image row `row` for a posed shape given by arrays (which may live in shared memory)
+// `stride` = distance (in doubles) between consecutive faces in nx / nz / cx / cz (inv_nx is dense).
 __device__ inline uint64_t raster_row_posed(const Params &P, int n_faces, const double *nx, const double *nz,
                                             const double *cx, const double *cz, const double *inv_nx, int j_lo,
-                                            int j_hi, int row) {
+                                            int j_hi, int row, int stride = 1) {
     const double pz = P.ys[row];
     int lo = j_lo, hi = j_hi;                 // surviving column interval [lo, hi]
     for (int k = 0; k < n_faces && lo <= hi; k++) {
-        const double fnx = nx[k], fcx = cx[k];
-        const double vz = dmul(dsub(pz, cz[k]), nz[k]);
+        const double fnx = nx[k * stride], fcx = cx[k * stride];
+        const double vz = dmul(dsub(pz, cz[k * stride]), nz[k * stride]);
         if (fnx == 0.0) {                     // the value does not depend on the column
             if (!pixel_in_halfplane(P.xs[lo], fcx, fnx, vz)) hi = lo - 1;
             continue;

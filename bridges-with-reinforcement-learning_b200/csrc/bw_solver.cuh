@@ -149,7 +149,7 @@ struct Solver {
         const int I = i / 3, k = i - 3 * I;
         const int body = freebody[I];
         double acc = 0.0;
-#pragma unroll 1
+#pragma unroll 2
         for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
             const int e = adj[q];
             const int c = e & 0x7f;
@@ -174,7 +174,7 @@ struct Solver {
             const int I = q / 3, r = q - 3 * I;
             const int body = freebody[I];
             double e0 = 0.0, e1 = 0.0, e2 = 0.0;         // entries (r, 0..r)
-#pragma unroll 1
+#pragma unroll 2
             for (int a = adj_ptr[body]; a < adj_ptr[body + 1]; a++) {
                 const int e = adj[a];
                 const int c = e & 0x7f;
@@ -253,7 +253,7 @@ struct Solver {
             const double *rA = L + tri(c0), *rB = L + tri(c0 + 1), *rC = L + tri(c0 + 2);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
             // c0 is a multiple of 3: three columns per trip, all twelve loads issued before the FMAs
-#pragma unroll 1
+#pragma unroll 2
             for (int p = 0; p < c0; p += 3) {
                 const double la0 = rA[p], lb0 = rB[p], lc0 = rC[p];
                 const double la1 = rA[p + 1], lb1 = rB[p + 1], lc1 = rC[p + 1];

@@ -61,7 +61,7 @@ void upload_step_tables() {
 // ------------------------------------------------------------------ shared memory layout
 struct Layout {
     // offsets in bytes from the start of dynamic shared memory
-    int pose, body, faces, pairs, contacts_G, contacts_ab, adj, prob[2], total;
+    int pose, body, faces, pairs, contacts_G, contacts_ab, adj, prob[2], shapes, grid, total;
     int MM, MC, HS;
 };
 
@@ -93,7 +93,7 @@ __host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
 constexpr int BODY_DOUBLES = 8;   // comx, comz, weight, depth, xmin, xmax, zmin, zmax
 constexpr int FACE_DOUBLES = 8;   // nx, nz, cx, cz, e0x, e0z, e1x, e1z
 
-__host__ __device__ inline Layout make_layout(int max_blocks, int max_itf) {
+__host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n_shapes) {
     Layout L;
     L.MM = 3 * max_blocks;
     L.MC = 2 * max_itf;
@@ -113,16 +113,20 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf) {
     L.pairs = L.faces + NBODY * NF * FACE_DOUBLES * 8;
     int scratch_end = L.pairs + NPAIR * 16 + align16(NPAIR * 2);
     if (scratch_end > p) p = scratch_end;
+    p = align16(p);
+    // block library and pixel nodes: read many times per step, kept next to the problem data
+    L.shapes = p; p += align16(n_shapes * (int)sizeof(ShapeDev));
+    L.grid = p; p += 2 * IMG * 8;
     L.total = align16(p);
     return L;
 }
 
-int step_smem_bytes(int max_blocks, int max_itf) { return make_layout(max_blocks, max_itf).total; }
+int step_smem_bytes(int max_blocks, int max_itf, int n_shapes) { return make_layout(max_blocks, max_itf, n_shapes).total; }
 
 // ------------------------------------------------------------------ the kernel
 template <bool TWO>
 __global__ void __launch_bounds__(64)
-step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
+step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
             bw_step_out *__restrict__ out, bw_obs_out obs, bw_interface *__restrict__ save_itf,
             int32_t *__restrict__ save_nitf, int save_variant) {
     float *__restrict__ block_img = obs.block_img_f32;
@@ -131,7 +135,22 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Layout L = make_layout(P.max_blocks, P.max_itf);
+    const Layout L = make_layout(PG.max_blocks, PG.max_itf, PG.n_shapes);
+    // P = the handle's parameters with the block library and the pixel nodes redirected to the
+    // shared-memory copies made below (every helper of bw_common.cuh reads them through P)
+    Params P = PG;
+    P.shapes = reinterpret_cast<const ShapeDev *>(smem + L.shapes);
+    P.xs = reinterpret_cast<const double *>(smem + L.grid);
+    P.ys = P.xs + IMG;
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(smem + L.shapes);
+        const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
+        for (int q = tid; q < words; q += 64) dst[q] = src[q];
+        double *g = reinterpret_cast<double *>(smem + L.grid);
+        g[tid] = PG.xs[tid];
+        g[IMG + tid] = PG.ys[tid];
+    }
 
     Pose *s_pose = reinterpret_cast<Pose *>(smem + L.pose);
     uint8_t *s_shape = smem + L.pose + NB * sizeof(Pose);
@@ -154,9 +173,13 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
 #ifdef BW_PROFILE
     __shared__ long long sh_prof_solve[2];
     __shared__ long long sh_prof_sub[2][6];
-    __shared__ long long sh_prof_book[4];
 #endif
     __shared__ double sh_lin[2];
+    __shared__ uint64_t sh_bits[IMG];      // raster of all blocks after this step
+    __shared__ uint64_t sh_newbits[IMG];   // raster of the new block alone
+    __shared__ double s_inv_nx[NF];        // 1 / n_x of the new block's posed faces (raster crossing estimate)
+    __shared__ double sh_dist[BW_MAX_TARGETS];
+    __shared__ int sh_coll[4];             // collision with: blocks, obstacles, floor, bounds
 
 #ifdef BW_PROFILE
     long long prof_t[8];
@@ -167,11 +190,13 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
 #endif
     const bw_action act = actions[e];
     const int n_old = P.n_blocks[e];
+    const uint64_t old_bits = P.block_bits[(size_t)e * IMG + tid];   // image row tid, used after the placement
     if (tid < n_old) {
         s_pose[tid] = P.pose[(size_t)e * NB + tid];
         s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
     }
     if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; }
+    if (tid < 4) sh_coll[tid] = 0;
     // stabilities_freezing()[1] of the previous step (all of today's free blocks were free and in
     // equilibrium): the frozen solve of this step has the same rows plus contacts to a new support,
     // so that equilibrium still holds -- no solve needed
@@ -257,10 +282,61 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
                 F[4] = dadd(ax, ps.x); F[5] = dadd(az, ps.z);
                 rot(ps.c, ps.s, sh.end1_x[fc], sh.end1_z[fc], ax, az);
                 F[6] = dadd(ax, ps.x); F[7] = dadd(az, ps.z);
+                if (placed && bdy == n) s_inv_nx[fc] = (F[0] != 0.0) ? 1.0 / F[0] : 0.0;
             }
         }
     }
     __syncthreads();
+
+    // ---------------- collision flags of the last block (_check_collision assembly_env.py:346-391):
+    // lanes of warp 0 = the other blocks, lanes of warp 1 = the obstacles, floor and bounds
+    if (P.collision_mode != 0 && n >= 1) {
+        const double tol = P.collision_tol;
+        const double *BN = s_body + n * BODY_DOUBLES;      // xmin xmax zmin zmax at [4..7]
+        const FaceView last = face_view_posed(s_face + (size_t)n * NF * FACE_DOUBLES, P.shapes[s_shape[n - 1]].n_faces);
+        if (tid < n - 1) {
+            const double *BO = s_body + (tid + 1) * BODY_DOUBLES;
+            if (BO[4] <= BN[5] && BN[4] <= BO[5] && BO[6] <= BN[7] && BN[6] <= BO[7]) {     // disjoint boxes cannot penetrate
+                const FaceView other = face_view_posed(s_face + (size_t)(tid + 1) * NF * FACE_DOUBLES,
+                                                       P.shapes[s_shape[tid]].n_faces);
+                if (polygons_collide(other, last, tol)) sh_coll[0] = 1;
+            }
+        } else if (tid >= 32 && tid < 32 + BW_MAX_OBSTACLES) {
+            const TaskDev *tk = P.task + e;
+            if (tid - 32 < tk->n_obstacles) {
+                const FaceView obst = face_view_shape(*P.marker, tk->obstacle_xz[tid - 32][0], tk->obstacle_xz[tid - 32][1]);
+                if (polygons_collide(obst, last, tol)) sh_coll[1] = 1;
+            }
+        } else if (tid == 32 + BW_MAX_OBSTACLES) {
+            if (BN[6] < -tol) sh_coll[2] = 1;              // deepest vertex below the floor plane z = 0
+            const Pose ps = s_pose[n - 1];                 // bounds test on the block position (x, 0, z)
+            if (ps.x < P.bounds_lo[0] || ps.x > P.bounds_hi[0] || 0.0 < P.bounds_lo[1] || 0.0 > P.bounds_hi[1] ||
+                ps.z < P.bounds_lo[2] || ps.z > P.bounds_hi[2])
+                sh_coll[3] = 1;
+        }
+    }
+
+    // ---------------- raster update of the new block (render_blocks_2d rendering.py:105-113), one thread
+    // per image row, from the posed faces above (same arithmetic as pose_shape / raster_row)
+    int i_lo = 0, i_hi = -1;
+    {
+        uint64_t bits = 0;
+        if (placed) {
+            const double *B = s_body + n * BODY_DOUBLES;
+            const int j_lo = max((int)floor((B[4] - P.xlim0) * P.inv_step_x) - 1, 0);
+            const int j_hi = min((int)ceil((B[5] - P.xlim0) * P.inv_step_x) + 1, IMG - 1);
+            i_lo = max((int)floor((P.ylim1 - B[7]) * P.inv_step_y) - 1, 0);
+            i_hi = min((int)ceil((P.ylim1 - B[6]) * P.inv_step_y) + 1, IMG - 1);
+            if (tid >= i_lo && tid <= i_hi && j_hi >= j_lo) {
+                const double *F = s_face + (size_t)n * NF * FACE_DOUBLES;
+                bits = raster_row_posed(P, P.shapes[s_shape[n - 1]].n_faces, F, F + 1, F + 2, F + 3, s_inv_nx, j_lo, j_hi,
+                                        tid, FACE_DOUBLES);
+            }
+            if (bits) P.block_bits[(size_t)e * IMG + tid] = old_bits | bits;
+        }
+        sh_newbits[tid] = bits;
+        sh_bits[tid] = old_bits | bits;
+    }
 
     BW_STAMP(1);
     // ---------------- phase 2: interfaces (one candidate per body pair, lexicographic order)
@@ -318,6 +394,18 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     }
     __syncthreads();
     const double invL0 = 1.0 / fmax(sh_L0, 1e-300);
+    // sum of reward_img over the new block's pixels (lin_reward, successor_dqn.py:397-401): a warp
+    // per image row, coalesced; the loads overlap the contact assembly below
+    double lin = 0.0;
+    if (placed) {
+        const float *rw = PG.reward_img + (size_t)e * IMG * IMG;
+#pragma unroll 2
+        for (int r = i_lo + warp; r <= i_hi; r += 2) {
+            const uint64_t bb = sh_newbits[r];
+            if ((bb >> lane) & 1ull) lin += (double)rw[r * IMG + lane];
+            if ((bb >> (lane + 32)) & 1ull) lin += (double)rw[r * IMG + lane + 32];
+        }
+    }
     int nitf = 0;
     for (int r = 0; r < 3; r++) nitf += sh_cnt[r][0] + sh_cnt[r][1];
     const bool overflow = nitf > P.max_itf;
@@ -482,62 +570,30 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
     __syncthreads();
 
     BW_STAMP(4);
-    // ---------------- phase 4: bookkeeping (thread 0)
+    // ---------------- phase 4: bookkeeping.  Warp 1: distance_to_targets (lane = block); thread 0:
+    // targets, block graph, state write; then thread 0 composes the step record.
     TaskDev *task = P.task + e;
     const int stable_frozen = sh_stable[0], stable_unfrozen = sh_stable[1];
-    if (tid == 0) {
-#ifdef BW_PROFILE
-        const long long tb0 = clock64();
-#endif
-        bw_step_out o;
-        memset(&o, 0, sizeof(o));
-        TaskDev tk = *task;
-#ifdef BW_PROFILE
-        sh_prof_book[0] = clock64() - tb0;
-#endif
-        if (placed) {
-            // _update_targets (gym_env.py:162-168): AABB test, removal while iterating
-            const double *B = s_body + n * BODY_DOUBLES;
-            const double tol = 1e-6;
-            int idx = 0;
-            while (idx < tk.n_remaining) {
-                const int t = tk.remaining[idx];
-                idx++;
-                const double px = tk.target_xz[t][0], pz = tk.target_xz[t][1];
-                if (dsub(B[4], tol) <= px && px <= dadd(B[5], tol) && dsub(B[6], tol) <= pz && pz <= dadd(B[7], tol) &&
-                    -0.5 * B[3] - tol <= 0.0 && 0.0 <= 0.5 * B[3] + tol) {
-                    tk.reached[tk.n_reached++] = (int8_t)t;
-                    // list.remove(target): first entry with equal coordinates
-                    int k = 0;
-                    for (; k < tk.n_remaining; k++) {
-                        const int u = tk.remaining[k];
-                        if (tk.target_xz[u][0] == px && tk.target_xz[u][1] == pz) break;
-                    }
-                    for (int q = k; q + 1 < tk.n_remaining; q++) tk.remaining[q] = tk.remaining[q + 1];
-                    tk.n_remaining--;
-                }
-            }
-            // block_graph occupancy (gym_env.py:224-232)
-            uint8_t *occ = P.face_occ + (size_t)e * NB;
-            if (act.target_block >= 0) occ[act.target_block] |= (uint8_t)(1u << act.target_face);
-            occ[n - 1] = (uint8_t)(1u << act.face);
-            *task = tk;
-            P.n_blocks[e] = n;
-            P.pose[(size_t)e * NB + (n - 1)] = s_pose[n - 1];
-            P.shape_of[(size_t)e * NB + (n - 1)] = s_shape[n - 1];
-            P.static_mask[e] = smask;
-        }
-#ifdef BW_PROFILE
-        sh_prof_book[1] = clock64() - tb0;
-#endif
-        // distance_to_targets (gym_env.py:154-160, geometry.py:89-105)
-        for (int t = 0; t < tk.n_targets; t++) {
-            double best = INFINITY;
-            const double px = tk.target_xz[t][0], pz = tk.target_xz[t][1];
-            for (int j = 1; j <= n; j++) {
-                const double *B = s_body + j * BODY_DOUBLES;
+    __shared__ TaskDev sh_task;
+    if (tid == 0) sh_task = *task;
+    if (warp == 1) {
+        lin = warp_sum(lin);
+        if (lane == 0) sh_lin[1] = lin;
+    } else {
+        lin = warp_sum(lin);
+        if (lane == 0) sh_lin[0] = lin;
+    }
+    __syncthreads();
+    if (warp == 1) {
+        // distance_to_targets (gym_env.py:154-160, geometry.py:89-105): min over blocks of the
+        // point-to-bounding-box distance
+        const int nt = sh_task.n_targets;
+        for (int t = 0; t < nt; t++) {
+            double dist = INFINITY;
+            if (lane < n) {
+                const double px = sh_task.target_xz[t][0], pz = sh_task.target_xz[t][1];
+                const double *B = s_body + (lane + 1) * BODY_DOUBLES;
                 const double tol = 1e-6;
-                double dist;
                 if (dsub(B[4], tol) <= px && px <= dadd(B[5], tol) && dsub(B[6], tol) <= pz && pz <= dadd(B[7], tol)) {
                     dist = 0.0;
                 } else {
@@ -545,13 +601,52 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
                     const double dx = dsub(px, qx), dz = dsub(pz, qz);
                     dist = sqrt(dadd(dmul(dx, dx), dmul(dz, dz)));
                 }
-                best = fmin(best, dist);
             }
-            o.distance_to_targets[t] = best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dist = fmin(dist, __shfl_xor_sync(FULL, dist, o));
+            if (lane == 0) sh_dist[t] = dist;
         }
-#ifdef BW_PROFILE
-        sh_prof_book[2] = clock64() - tb0;
-#endif
+    } else if (tid == 0 && placed) {
+        TaskDev tk = sh_task;
+        // _update_targets (gym_env.py:162-168): AABB test, removal while iterating
+        const double *B = s_body + n * BODY_DOUBLES;
+        const double tol = 1e-6;
+        int idx = 0;
+        while (idx < tk.n_remaining) {
+            const int t = tk.remaining[idx];
+            idx++;
+            const double px = tk.target_xz[t][0], pz = tk.target_xz[t][1];
+            if (dsub(B[4], tol) <= px && px <= dadd(B[5], tol) && dsub(B[6], tol) <= pz && pz <= dadd(B[7], tol) &&
+                -0.5 * B[3] - tol <= 0.0 && 0.0 <= 0.5 * B[3] + tol) {
+                tk.reached[tk.n_reached++] = (int8_t)t;
+                // list.remove(target): first entry with equal coordinates
+                int k = 0;
+                for (; k < tk.n_remaining; k++) {
+                    const int u = tk.remaining[k];
+                    if (tk.target_xz[u][0] == px && tk.target_xz[u][1] == pz) break;
+                }
+                for (int q = k; q + 1 < tk.n_remaining; q++) tk.remaining[q] = tk.remaining[q + 1];
+                tk.n_remaining--;
+            }
+        }
+        // block_graph occupancy (gym_env.py:224-232)
+        uint8_t *occ = P.face_occ + (size_t)e * NB;
+        if (act.target_block >= 0) occ[act.target_block] |= (uint8_t)(1u << act.target_face);
+        occ[n - 1] = (uint8_t)(1u << act.face);
+        *task = tk;
+        sh_task = tk;
+        P.n_blocks[e] = n;
+        P.pose[(size_t)e * NB + (n - 1)] = s_pose[n - 1];
+        P.shape_of[(size_t)e * NB + (n - 1)] = s_shape[n - 1];
+        P.static_mask[e] = smask;
+    }
+    __syncthreads();
+    BW_STAMP(5);
+    if (tid == 0) {
+        bw_step_out o;
+        memset(&o, 0, sizeof(o));
+        const int n_reached = sh_task.n_reached;
+        for (int t = 0; t < sh_task.n_targets; t++) o.distance_to_targets[t] = sh_dist[t];
         o.stable = (uint8_t)stable_frozen;
         o.stable_unfrozen = (uint8_t)stable_unfrozen;
         o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0) |
@@ -562,61 +657,38 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         o.solver_kflops = (int32_t)fmin(2e9, (sh_flops[0] + sh_flops[1]) * 1e-3);
         o.n_blocks = n;
         o.n_interfaces = nitf;
-        o.n_targets_reached = (uint8_t)tk.n_reached;
+        o.n_targets_reached = (uint8_t)n_reached;
         o.error = overflow ? 2 : 0;
-        const bool all_reached = tk.n_remaining == 0;
-        o.terminated = (uint8_t)(!stable_frozen || all_reached);
+        const bool all_reached = sh_task.n_remaining == 0;
+        o.collision_block = (uint8_t)sh_coll[0];
+        o.collision_obstacle = (uint8_t)sh_coll[1];
+        o.collision_floor = (uint8_t)sh_coll[2];
+        o.collision_boundary = (uint8_t)sh_coll[3];
+        o.collision = (uint8_t)(sh_coll[0] | sh_coll[1] | sh_coll[2] | sh_coll[3]);
+        o.terminated = (uint8_t)(!stable_frozen || o.collision || all_reached);     // gym_env.py:141-144
         o.truncated = (uint8_t)(P.max_steps > 0 && n >= P.max_steps);
-        if (!stable_frozen) o.reward = -1.0f;
-        else if (!all_reached) o.reward = (float)(-1 + tk.n_reached);
-        else o.reward = (float)tk.n_reached;
-        out[e] = o;   // lin_reward is patched below
-        if (placed) P.done[e] = (uint8_t)(o.terminated | o.truncated);
-    }
-
-    BW_STAMP(5);
-    // ---------------- phase 5: raster update of the new block (one thread per image row), lin_reward,
-    // and the fused observation write: f32 [1,64,64] image + 6 binary features
-    __shared__ uint64_t sh_bits[IMG];
-    {
-        const int row = tid;
-        uint64_t cur = P.block_bits[(size_t)e * IMG + row];
-        double lin = 0.0;
-        if (placed) {
-            const uint64_t bits = raster_row(P, P.shapes[s_shape[n - 1]], s_pose[n - 1], row);
-            if (bits) {
-                cur |= bits;
-                P.block_bits[(size_t)e * IMG + row] = cur;
-                const float *rw = P.reward_img + (size_t)e * IMG * IMG + row * IMG;
-                uint64_t bb = bits;
-                while (bb) {
-                    const int j = __ffsll((long long)bb) - 1;
-                    bb &= bb - 1;
-                    lin += (double)rw[j];
-                }
-            }
-        }
-        sh_bits[row] = cur;
-        lin = warp_sum(lin);
-        if (lane == 0) sh_lin[warp] = lin;
-    }
-    __syncthreads();
-    if (tid == 0) {
+        if (!stable_frozen || o.collision) o.reward = -1.0f;                        // gym_env.py:11-22
+        else if (!all_reached) o.reward = (float)(-1 + n_reached);
+        else o.reward = (float)n_reached;
         if (placed) {
             // successor_dqn.py:397-401
-            const float s = (float)(sh_lin[0] + sh_lin[1]);
+            const float sum = (float)(sh_lin[0] + sh_lin[1]);
             float lr = 0.0f;
-            if (stable_frozen) lr = s / 100.0f;
-            if (stable_unfrozen) lr = s;
-            out[e].lin_reward = lr;
+            if (stable_frozen) lr = sum / 100.0f;
+            if (stable_unfrozen) lr = sum;
+            o.lin_reward = lr;
+            P.done[e] = (uint8_t)(o.terminated | o.truncated);
         }
-        P.last_out[e] = out[e];
+        out[e] = o;
+        P.last_out[e] = o;
         P.su_valid[e] = 1;
         if (binary != nullptr) {
             float *bf = binary + (size_t)e * 6;   // get_state_features, successor_dqn.py:53-60
-            bf[0] = (float)stable_frozen; bf[1] = 0.0f; bf[2] = 0.0f; bf[3] = 0.0f; bf[4] = 0.0f; bf[5] = 0.0f;
+            bf[0] = (float)stable_frozen; bf[1] = (float)o.collision; bf[2] = (float)o.collision_block;
+            bf[3] = (float)o.collision_obstacle; bf[4] = (float)o.collision_floor; bf[5] = (float)o.collision_boundary;
         }
     }
+    // ---------------- phase 5: the fused observation write: f32 [1,64,64] / u8 [64,64] image of all blocks
 #ifdef BW_PROFILE
     __syncthreads();
     if (tid == 0) {   // cycle counts smuggled out through fields the profile run does not need
@@ -632,7 +704,7 @@ step_kernel(Params P, const bw_action *__restrict__ actions, const uint8_t *__re
         if (block_img != nullptr) {
             float *dbg = block_img + (size_t)e * IMG * IMG;
             for (int q = 0; q < 6; q++) dbg[q] = (float)sh_prof_sub[1][q];
-            for (int q = 0; q < 3; q++) dbg[8 + q] = (float)sh_prof_book[q];
+            for (int q = 0; q < 3; q++) dbg[8 + q] = 0.0f;
         }
     }
 #endif

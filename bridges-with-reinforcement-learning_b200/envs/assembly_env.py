@@ -139,8 +139,12 @@ class AssemblyEnv:
 
     def __init__(self, render=False, bounds=None, stability="rbe", mu=0.8, density=1.0, cra_env=True,
                  pybullet_env=False, device=0):
-        if pybullet_env or stability == "pybullet":
-            raise NotImplementedError("the PyBullet back-end is not part of bridges_b200 (SURVEY.md section 8f)")
+        if stability == "pybullet":
+            raise NotImplementedError("the PyBullet settling check is not part of bridges_b200 (SURVEY.md section 8f)")
+        # pybullet_env=True switches the collision flags of `_check_collision` (assembly_env.py:346-391) on;
+        # they come from the CUDA step (exact polygon penetration depths, tol 0.005), not from Bullet
+        self.collision = bool(pybullet_env)
+        self.collision_tol = 0.005
         if stability not in ("rbe", None):
             raise NotImplementedError("stability must be 'rbe' (default) or None")
         if bounds is None:

@@ -45,7 +45,11 @@ def gaussian_kernel1d(kernel_size=101, sigma=16):
 
 class BatchedAssemblyGym:
     def __init__(self, num_envs, shapes, max_steps=None, device=0, mu=0.8, density=1.0, xlim=(-3.0, 7.0),
-                 ylim=(0.0, 10.0), bounds=None, tmax=1e-6, amin=1e-3, stable_tol=1e-6, stream=None):
+                 ylim=(0.0, 10.0), bounds=None, tmax=1e-6, amin=1e-3, stable_tol=1e-6, stream=None,
+                 collision=False, collision_tol=0.005):
+        """collision=True: the flags of `AssemblyEnv._check_collision` (assembly_env.py:346-391, what the
+        reference produces with pybullet_env=True) from exact polygon penetration depths; False: constant
+        False flags (the reference without a physics client, assembly_env.py:310-312)."""
         if not torch.cuda.is_available():
             raise L.BridgesError("bridges_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -67,6 +71,10 @@ class BatchedAssemblyGym:
         cfg.floor_halfwidth = 0.5 * float(self.bounds[1][0] - self.bounds[0][0])
         cfg.floor_depth = float(self.bounds[1][1] - self.bounds[0][1])
         cfg.mu, cfg.density, cfg.tmax, cfg.amin, cfg.stable_tol = mu, density, tmax, amin, stable_tol
+        cfg.collision_mode = 1 if collision else 0
+        cfg.collision_tol = float(collision_tol)
+        for k in range(3):
+            cfg.bounds_lo[k], cfg.bounds_hi[k] = float(self.bounds[0][k]), float(self.bounds[1][k])
         # enqueue on torch's current stream unless told otherwise, so that tensor fills / copies
         # issued through torch and the library's kernels are ordered without extra syncs
         with torch.cuda.device(self.device):

@@ -127,7 +127,8 @@ class AssemblyGym:
                 self._core.close()
             ae = self.assembly_env
             self._core = BatchedAssemblyGym(1, self.shapes, max_steps=self.max_steps, device=ae.device, mu=ae.mu,
-                                            density=ae.density, bounds=ae.bounds)
+                                            density=ae.density, bounds=ae.bounds, collision=ae.collision,
+                                            collision_tol=ae.collision_tol)
             self._core_shapes = key
         return self._core
 
@@ -153,7 +154,10 @@ class AssemblyGym:
         ae._state_info = {
             "last_block": ae.blocks[-1] if ae.blocks else None,
             "collision": bool(out["collision"]),
-            "collision_info": {"obstacles": [], "blocks": [], "floor": False, "bounding_box": False},
+            # the step reports flags, not object ids: a non-empty list stands for "at least one"
+            "collision_info": {"obstacles": [True] if out["collision_obstacle"] else [],
+                               "blocks": [True] if out["collision_block"] else [],
+                               "floor": bool(out["collision_floor"]), "bounding_box": bool(out["collision_boundary"])},
             "frozen_block": ae.frozen_block_index,
             "stable": stable if ae.stability else None,
             "stability_info": None if not (out["solver_status"] & 1) else dict(error="not converged"),

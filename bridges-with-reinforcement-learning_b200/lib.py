@@ -14,7 +14,7 @@ BW_MAX_OBSTACLES = 8
 BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
-BW_ABI_VERSION = 1
+BW_ABI_VERSION = 2
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")
@@ -25,7 +25,9 @@ class bw_config(C.Structure):
                 ("xlim", C.c_double * 2), ("ylim", C.c_double * 2),
                 ("floor_halfwidth", C.c_double), ("floor_depth", C.c_double),
                 ("mu", C.c_double), ("density", C.c_double), ("tmax", C.c_double), ("amin", C.c_double),
-                ("stable_tol", C.c_double), ("stream", C.c_void_p)]
+                ("stable_tol", C.c_double), ("stream", C.c_void_p),
+                ("collision_mode", C.c_int32), ("reserved0", C.c_int32), ("collision_tol", C.c_double),
+                ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3)]
 
 
 class bw_shape_desc(C.Structure):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 1
+#define BW_ABI_VERSION 2
 
 /* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
 #define BW_MAX_BLOCKS 16
@@ -70,6 +70,16 @@ typedef struct {
     double amin;             /* minimum interface area, 0.001 (assembly_env.py:304) */
     double stable_tol;       /* verdict threshold on the relative equilibrium residual, default 1e-6 */
     void *stream;            /* cudaStream_t to enqueue on when use_caller_stream = 1 */
+    /* AssemblyEnv(pybullet_env=...): 0 = no physics client, every collision flag is constant False
+     * (assembly_env.py:310-312, the training default); 1 = the flags of _check_collision
+     * (assembly_env.py:346-391) for the last block: bounds test on the block position (:360) and
+     * penetration deeper than collision_tol against blocks / floor / obstacles, computed as exact
+     * convex-polygon penetration depths (separating-axis form) instead of Bullet contact points */
+    int32_t collision_mode;
+    int32_t reserved0;
+    double collision_tol;    /* tol of _check_collision, default 0.005 */
+    double bounds_lo[3];     /* AssemblyEnv.bounds[0], default (-3, -3, -1) (assembly_env.py:164-168) */
+    double bounds_hi[3];     /* AssemblyEnv.bounds[1], default (7, 7, 9) */
 } bw_config;
 
 /* One entry of the block library: what Shape.from_urdf (assembly_env.py:54-68) extracts,
@@ -131,7 +141,7 @@ typedef struct {
     int32_t solver_kflops;        /* work estimate of both solves, in 1e3 flops */
     uint8_t stable;               /* obs['stable']: verdict with only the new block frozen */
     uint8_t stable_unfrozen;      /* stabilities_freezing()[1]: last block released */
-    uint8_t collision;            /* constant 0 without PyBullet (assembly_env.py:310-312) */
+    uint8_t collision;            /* constant 0 with collision_mode = 0 (assembly_env.py:310-312) */
     uint8_t collision_block, collision_obstacle, collision_floor, collision_boundary;
     uint8_t terminated;           /* gym_env.py:141-144 */
     uint8_t truncated;            /* max_steps reached */

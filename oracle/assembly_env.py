@@ -220,14 +220,30 @@ class Block(Shape):
         return f"Block ({self.object_id})"
 
 
+def polygon_separation(a, b):
+    """Signed separation of two posed convex polygons (negative = penetration depth): the largest,
+    over the faces of both, of the smallest half-plane value of the other polygon's vertices."""
+    sep = -math.inf
+    for p, q in ((a, b), (b, a)):
+        for (cx, cz), (nx, nz) in zip(p.face_centers_2d, p.face_normals_2d):
+            s = min((vx - cx) * nx + (vz - cz) * nz for vx, vz in q.polygon_2d)
+            if s > sep:
+                sep = s
+    return sep
+
+
 class AssemblyEnv:
     """assembly_env.py:159-438, default back-ends (CRA model, no PyBullet)."""
 
     def __init__(self, render=False, bounds=None, stability="rbe", mu=0.8, density=1.0, cra_env=True,
-                 pybullet_env=False, tmax=1e-6, amin=1e-3):
+                 pybullet_env=False, tmax=1e-6, amin=1e-3, collision_tol=0.005):
         from . import stability as st
-        if pybullet_env:
-            raise NotImplementedError("PyBullet back-end is out of scope (SURVEY.md section 8f row 4)")
+        # pybullet_env=True: the collision flags of `_check_collision` (assembly_env.py:346-391) are
+        # produced -- by exact convex-polygon penetration depths instead of Bullet's contact points
+        # (PARITY UNPINNED against Bullet: pybullet==3.2.6 is not in /root/reference nor installed).
+        # The PyBullet settling check `is_stable_pybullet` stays out of scope.
+        self.collision_enabled = bool(pybullet_env)
+        self.collision_tol = collision_tol
         if bounds is None:
             bounds = [[-3.0, -3.0, -1.0], [7.0, 7.0, 9.0]]
         self.bounds = bounds
@@ -269,9 +285,37 @@ class AssemblyEnv:
         self.cra_assembly = st.CRAAssembly(self.bounds, self.blocks, tmax=self.tmax, amin=self.amin)
         self.num_interface_extractions += 1
 
+    def _check_collision(self):
+        """assembly_env.py:346-391 for the last block: bounds test on the block POSITION (:360),
+        then penetration deeper than `tol` against every other block, the floor and the obstacles.
+        Bullet's `contact distance < -tol` is restated as the exact penetration depth of two convex
+        polygons (separating-axis form): sep = max over the faces of both polygons of
+        min over the other polygon's vertices of (v - c).n, collision iff sep < -tol; the floor is
+        the half-plane z <= 0.  Canonical arithmetic: (vx-cx)*nx + (vz-cz)*nz, separately rounded."""
+        info = {"obstacles": [], "blocks": [], "floor": False, "bounding_box": False}
+        if len(self.blocks) == 0:
+            return False, info
+        block = self.blocks[-1]
+        tol = self.collision_tol
+        lo, hi = self.bounds
+        if any(block.position[k] < lo[k] for k in range(3)) or any(block.position[k] > hi[k] for k in range(3)):
+            info["bounding_box"] = True
+        for i, b in enumerate(self.blocks[:-1]):
+            if polygon_separation(b, block) < -tol:
+                info["blocks"].append(i)
+        if min(v[1] for v in block.polygon_2d) < -tol:
+            info["floor"] = True
+        for i, obs in enumerate(self.obstacles):
+            if polygon_separation(obs, block) < -tol:
+                info["obstacles"].append(i)
+        return any(bool(v) for v in info.values()), info
+
     def _update_state_info(self):
-        collision = False
-        collision_info = {"obstacles": [], "blocks": [], "floor": False, "bounding_box": False}
+        if self.collision_enabled:
+            collision, collision_info = self._check_collision()
+        else:                                   # assembly_env.py:310-312
+            collision = False
+            collision_info = {"obstacles": [], "blocks": [], "floor": False, "bounding_box": False}
         self._state_info = {
             "last_block": self.blocks[-1] if self.blocks else None,
             "collision": collision,

@@ -1,7 +1,7 @@
 """Attribute ncu warp-stall samples (SASS page csv) to CUDA source lines using nvdisasm -g output.
 usage: ncu_lines.py <src_page.csv> <nvdisasm -g -c listing> [kernel substring]"""
 import csv, re, sys, collections
-src_csv, sass, kern = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "step_kernel")
+src_csv, sass, kern = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "step_kernelILb0")
 # line table: ordered list of (line) per instruction of the kernel
 lines, cur, inside = [], None, False
 for ln in open(sass):

@@ -2,7 +2,7 @@
 usage: ncu_regions.py <src_page.csv> <nvdisasm -g -c listing>"""
 import csv, re, sys, collections
 src_csv, sass = sys.argv[1], sys.argv[2]
-kern = "step_kernel"
+kern = sys.argv[3] if len(sys.argv) > 3 else "step_kernelILb0"
 lines, cur, inside = [], None, False
 for ln in open(sass):
     if ln.startswith(".text.") or ".section" in ln and ".text." in ln:
