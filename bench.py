@@ -241,6 +241,46 @@ def run_sweep(args, rank, local_rank, world, dev):
             "rank0_stats": stats}
 
 
+def run_batch_scan(args, local_rank, sizes):
+    """The same step at larger lock-step batches (device-timed, L2 flushed between steps): at 1024
+    envs a launch is a partial wave whose length is the slowest environment's solve; with more
+    environments per GPU the SMs fill up and the per-step cost approaches the mean solve."""
+    import numpy as np
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    dev = torch.device("cuda", local_rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    rows = []
+    for E in sizes:
+        env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=args.max_steps, device=local_rank)
+        env.reset(task_def(args.tower_height))
+        img = torch.empty((E, 1, 64, 64), dtype=torch.float32, device=dev)
+        binary = torch.empty((E, 6), dtype=torch.float32, device=dev)
+        K = 60
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        n_pre = []
+        for i in range(20 + K):
+            env.enumerate_actions(X_GROUND, (0.0,), amax=128, with_bits=False)
+            acts = env.select_random(seed=args.seed * 1000003 + i * 7919 + 17)[0]
+            if i >= 20:
+                flush.fill_(i & 0xff)
+                ev[i - 20][0].record()
+            env.step(acts, block_img=img, binary=binary)
+            if i >= 20:
+                ev[i - 20][1].record()
+                if i % 20 == 0:
+                    n_pre.append(np.maximum(env.read_out()["n_blocks"].astype(np.float64) - 1, 0).mean())
+            env.reset_done()
+        torch.cuda.synchronize()
+        t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+        bytes_per_launch = E * (16528 + 16 * args.tower_height + 32 * float(np.mean(n_pre)))
+        rows.append({"envs": E, "env_steps_per_s": E * K / t, "ms_per_step": 1e3 * t / K,
+                     "achieved_GBps": bytes_per_launch * K / t / 1e9})
+        env.close()
+        del env, img, binary
+    return rows
+
+
 def run_gpu(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -417,6 +457,13 @@ def run_gpu(args, rank, local_rank, world):
     }
     if sweep is not None:
         line["sweep"] = sweep
+    if args.batch_scan:
+        scan = run_batch_scan(args, local_rank, [4096, 16384, 65536])
+        peak_hbm = peak
+        for r in scan:
+            r["hbm_frac"] = r["achieved_GBps"] / peak_hbm
+        line["batch_scan"] = {"note": "same step kernel and workload at larger lock-step batches per GPU (rank 0)",
+                              "rows": scan}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
@@ -440,6 +487,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0, help="CPU-arm worker processes (0 = all host cores)")
     ap.add_argument("--no-flush", action="store_true", help="profiling only: skip the L2 flush between steps")
     ap.add_argument("--sweep", action="store_true", help="also run the 65,536-assembly stability sweep (configs[3])")
+    ap.add_argument("--batch-scan", action="store_true", help="also time the step at 4096 / 16384 / 65536 envs per GPU")
     ap.add_argument("--sweep-assemblies", type=int, default=65536)
     ap.add_argument("--sweep-steps", type=int, default=10)
     args = ap.parse_args()
