@@ -409,13 +409,18 @@ def run_gpu(args, rank, local_rank, world):
 
     t_e2e = e2e_loop(L.bw_obs_out(None, h_u8.data_ptr(), h_bin.data_ptr()), W + K)
     t_e2e_f32 = e2e_loop(L.bw_obs_out(h_img.data_ptr(), None, h_bin.data_ptr()), W + K + Ke)
+    # the same call with the zero-copy path switched off: H2D memcpy, kernel, D2H memcpys, in sequence
+    lib.bw_set_host_transfer(h, 1)
+    t_e2e_staged = e2e_loop(L.bw_obs_out(None, h_u8.data_ptr(), h_bin.data_ptr()), W + K + 2 * Ke)
+    lib.bw_set_host_transfer(h, 0)
     h2d = E * dt["action"].itemsize
     d2h = E * (dt["step_out"].itemsize + 64 * 64 + 6 * 4)
     d2h_f32 = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
 
     # ---- max over ranks
     sweep = run_sweep(args, rank, local_rank, world, dev) if args.sweep else None
-    t_dev, t_e2e, t_e2e_f32, wall, t_cand = max_over_ranks([t_dev, t_e2e, t_e2e_f32, wall, t_cand], device=dev)
+    t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged = max_over_ranks(
+        [t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -432,7 +437,10 @@ def run_gpu(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": world * E * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "bw_step_host: pinned host actions in; step records + u8 raster [E,64,64] "
-                                    "(render_blocks_2d's bool image) + binary features out",
+                                    "(render_blocks_2d's bool image) + binary features out; pinned buffers are "
+                                    "read / written by the kernel over PCIe as each environment finishes",
+                "staged_copies": {"value": world * E * Ke / t_e2e_staged, "unit": UNIT,
+                                  "note": "same call, bw_set_host_transfer(h, 1): cudaMemcpyAsync before and after the kernel"},
                 "with_f32_images": {"value": world * E * Ke / t_e2e_f32, "unit": UNIT, "d2h_bytes_per_step": d2h_f32}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

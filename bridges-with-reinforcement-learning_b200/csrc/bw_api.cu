@@ -19,6 +19,7 @@ struct bw_handle {
     bool own_stream = false;
     bool shapes_loaded = false;
     bool timing = false;
+    bool force_staged = false;   // bw_set_host_transfer(h, 1): *_host calls always stage through device buffers
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int smem_step = 0;
     int64_t launches = 0;
@@ -450,11 +451,46 @@ static int ensure_img(bw_handle *h, int which) {
     return BW_OK;
 }
 
+// Device-visible alias of a pinned (page-locked, mapped) host buffer, or nullptr for pageable memory.
+// With unified addressing every cudaHostAlloc / cudaHostRegister'ed range has one (torch's
+// pin_memory() included).
+static void *mapped_alias(const void *host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+    return attr.devicePointer;
+}
+
 int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
                  const bw_obs_out *obs) {
     if (!h || !h_actions || !h_out) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
     const size_t E = (size_t)h->P.E;
+    // Zero-copy path: when every host buffer of this call is pinned, the step kernel reads the
+    // actions from and writes its records / images straight to host memory over PCIe, each
+    // environment as soon as it is finished -- the transfers overlap the solves of the slower
+    // environments instead of following the kernel.  Pageable buffers take the staged path below.
+    {
+        void *m_act = mapped_alias(h_actions), *m_out = mapped_alias(h_out);
+        void *m_mask = h_mask ? mapped_alias(h_mask) : nullptr;
+        void *m_f32 = (obs && obs->block_img_f32) ? mapped_alias(obs->block_img_f32) : nullptr;
+        void *m_u8 = (obs && obs->block_img_u8) ? mapped_alias(obs->block_img_u8) : nullptr;
+        void *m_bin = (obs && obs->binary) ? mapped_alias(obs->binary) : nullptr;
+        const bool all_mapped = m_act && m_out && (!h_mask || m_mask) && (!(obs && obs->block_img_f32) || m_f32) &&
+                                (!(obs && obs->block_img_u8) || m_u8) && (!(obs && obs->binary) || m_bin);
+        if (all_mapped && !h->force_staged) {
+            bw_obs_out dev = {static_cast<float *>(m_f32), static_cast<uint8_t *>(m_u8), static_cast<float *>(m_bin)};
+            int rc = bw_step(h, static_cast<const bw_action *>(m_act), static_cast<const uint8_t *>(m_mask),
+                             static_cast<bw_step_out *>(m_out), &dev);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(h->stream));
+            return BW_OK;
+        }
+    }
     CU(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
     if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
     bw_obs_out dev = {nullptr, nullptr, nullptr};
@@ -481,6 +517,12 @@ int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask
     if (dev.binary)
         CU(cudaMemcpyAsync(obs->binary, dev.binary, sizeof(float) * E * 6, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_set_host_transfer(bw_handle *h, int32_t mode) {
+    if (!h || mode < 0 || mode > 1) return BW_ERR_INVALID;
+    h->force_staged = (mode == 1);
     return BW_OK;
 }
 

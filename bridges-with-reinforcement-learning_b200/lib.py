@@ -127,6 +127,7 @@ SIGNATURES = {
     "bw_reset_done": (C.c_int, [_H]),
     "bw_step": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
     "bw_step_host": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
+    "bw_set_host_transfer": (C.c_int, [_H, C.c_int32]),
     "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_observe_host": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_enumerate_actions": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),

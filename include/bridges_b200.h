@@ -209,6 +209,12 @@ int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_
             const bw_obs_out *obs);
 int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
                  const bw_obs_out *obs);
+/* How bw_step_host moves its buffers.  0 (default): automatic -- when every host buffer of the call
+ * is pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()) the step kernel reads the
+ * actions from and writes records / images to host memory directly over PCIe, every environment
+ * as soon as it is done, so the transfers overlap the solves; pageable buffers are staged through
+ * device buffers with cudaMemcpyAsync.  1: always stage. */
+int bw_set_host_transfer(bw_handle *h, int32_t mode);
 
 /* ---- observations: _get_obs + get_state_features / get_task_features ----------------
  * any pointer may be NULL.  Images are [E,1,64,64] f32, row 0 = top (rendering.py:105-113). */

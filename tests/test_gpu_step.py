@@ -221,6 +221,49 @@ def test_host_entry_point_and_observation_formats():
         assert np.array_equal(h_bin[:, 0], ref["stable"].astype(np.float32)) and not h_bin[:, 1:].any()
 
 
+def test_host_entry_point_pinned_buffers_zero_copy():
+    """Pinned host buffers: bw_step_host lets the kernel read the actions from / write its outputs to
+    host memory directly; results equal the staged path (bw_set_host_transfer(h, 1)) bit for bit."""
+    import ctypes as C
+    import torch
+    from bridges_b200 import lib as L
+    E = 96
+    task = dict(obstacles=[(0.6, 0, 0.3)], targets=[(0.6, 0, 0.9)])
+    a = _gpu_env(E, [H.URDF["trapezoid"]], max_steps=10)
+    b = _gpu_env(E, [H.URDF["trapezoid"]], max_steps=10)
+    a.reset(task)
+    b.reset(task)
+    b.lib.bw_set_host_transfer(b.handle, 1)
+    dt = a.dt
+    bufs = []
+    for env in (a, b):
+        bufs.append(dict(act=torch.zeros(E * dt["action"].itemsize, dtype=torch.uint8).pin_memory(),
+                         out=torch.zeros(E * dt["step_out"].itemsize, dtype=torch.uint8).pin_memory(),
+                         u8=torch.zeros((E, 64, 64), dtype=torch.uint8).pin_memory(),
+                         f32=torch.zeros((E, 1, 64, 64), dtype=torch.float32).pin_memory(),
+                         bin=torch.zeros((E, 6), dtype=torch.float32).pin_memory()))
+    x_ground = [-2.0 + 2.0 * i / 9 for i in range(10)]
+    for k in range(6):
+        a.enumerate_actions(x_ground, (0.0,), amax=128, with_bits=False)
+        acts, _ = a.select_random(seed=77 + k)
+        host_acts = acts.cpu()
+        for env, bf in zip((a, b), bufs):
+            bf["act"].copy_(host_acts)
+            obs = L.bw_obs_out(bf["f32"].data_ptr(), bf["u8"].data_ptr(), bf["bin"].data_ptr())
+            L.check(env.lib, env.handle, env.lib.bw_step_host(env.handle, bf["act"].data_ptr(), None,
+                                                              bf["out"].data_ptr(), C.byref(obs)))
+        oa = bufs[0]["out"].numpy().view(dt["step_out"])
+        ob = bufs[1]["out"].numpy().view(dt["step_out"])
+        for name in ("stable", "stable_unfrozen", "reward", "lin_reward", "terminated", "truncated", "n_blocks",
+                     "n_interfaces", "distance_to_targets", "error"):
+            assert np.array_equal(oa[name], ob[name]), (k, name)
+        assert torch.equal(bufs[0]["u8"], bufs[1]["u8"]) and torch.equal(bufs[0]["f32"], bufs[1]["f32"])
+        assert torch.equal(bufs[0]["bin"], bufs[1]["bin"])
+        assert bufs[0]["u8"].any() and (oa["n_blocks"] == k + 1).any()
+        bits, _ = a.raster_bits()
+        assert np.array_equal(bufs[0]["u8"].numpy().astype(bool), a.bits_to_bool(bits))
+
+
 def test_masks_empty_scene_and_capacity():
     env = _gpu_env(4, [H.URDF["cube"]])
     env.reset(dict())
