@@ -20,11 +20,25 @@ constexpr int ENUM_CHUNK = 64;        // candidates posed per pass (shared-memor
 // not be replicated over the lanes of a warp.  B: one thread per (candidate, image row inside its
 // window) evaluates the row's bit mask and the overlap with the block / obstacle rasters.
 __global__ void __launch_bounds__(ENUM_THREADS, 8)
-enumerate_kernel(Params P, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
+enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                  int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
                  int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits) {
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
+    // block library and pixel nodes in shared memory; the helpers of bw_common.cuh read them through P
+    __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
+    __shared__ double s_grid[2 * IMG];
+    Params P = PG;
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(s_lib);
+        const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
+        for (int q = tid; q < words; q += ENUM_THREADS) dst[q] = src[q];
+        if (tid < IMG) { s_grid[tid] = PG.xs[tid]; s_grid[IMG + tid] = PG.ys[tid]; }
+        P.shapes = reinterpret_cast<const ShapeDev *>(s_lib);
+        P.xs = s_grid;
+        P.ys = s_grid + IMG;
+    }
     __shared__ Pose s_pose[NB];
     __shared__ uint8_t s_shape[NB];
     __shared__ uint64_t s_block[IMG], s_obst[IMG];

@@ -39,6 +39,8 @@ struct bw_handle {
     bw_interface *d_itf = nullptr;
     int32_t *d_nitf = nullptr;
     double *d_ground = nullptr, *d_offsets = nullptr;
+    double ground_cached[256], offsets_cached[256];   // host copies of what d_ground / d_offsets hold
+    int n_ground_cached = -1, n_offsets_cached = -1;
     bw_block *d_qblocks = nullptr, *d_rblocks = nullptr;
     uint8_t *d_qflags = nullptr;
     ShapeDev *d_rshapes = nullptr;
@@ -564,10 +566,19 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
         return fail(h, BW_ERR_CAPACITY, "at most 256 ground offsets / block offsets");
     if ((n_ground > 0 && !h_x_discr_ground) || (n_offsets > 0 && !h_offset_values)) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
-    if (n_ground > 0)
-        CU(cudaMemcpyAsync(h->d_ground, h_x_discr_ground, sizeof(double) * n_ground, cudaMemcpyHostToDevice, h->stream));
-    if (n_offsets > 0)
-        CU(cudaMemcpyAsync(h->d_offsets, h_offset_values, sizeof(double) * n_offsets, cudaMemcpyHostToDevice, h->stream));
+    // the offset tables rarely change between calls: upload only when they do
+    if (n_ground > 0 && (h->n_ground_cached != n_ground ||
+                         memcmp(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground) != 0)) {
+        memcpy(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground);
+        h->n_ground_cached = n_ground;
+        CU(cudaMemcpyAsync(h->d_ground, h->ground_cached, sizeof(double) * n_ground, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (n_offsets > 0 && (h->n_offsets_cached != n_offsets ||
+                          memcmp(h->offsets_cached, h_offset_values, sizeof(double) * n_offsets) != 0)) {
+        memcpy(h->offsets_cached, h_offset_values, sizeof(double) * n_offsets);
+        h->n_offsets_cached = n_offsets;
+        CU(cudaMemcpyAsync(h->d_offsets, h->offsets_cached, sizeof(double) * n_offsets, cudaMemcpyHostToDevice, h->stream));
+    }
     launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
                      d_action_bits, h->stream);
     h->launches++;
