@@ -131,8 +131,9 @@ struct Solver {
         }
     }
 
-    // f = P_K(g), typ
-    __device__ __forceinline__ void project_all() {
+    // f = P_K(g), typ; returns whether any contact point changed its cone face since the last call
+    __device__ __forceinline__ bool project_all() {
+        bool changed = false;
 #pragma unroll 1
         for (int c = lane; c < nc; c += 32) {
             double fn, ft;
@@ -140,8 +141,10 @@ struct Solver {
             project_cone(g[2 * c], g[2 * c + 1], mu, inv_den, fn, ft, t);
             f[2 * c] = fn;
             f[2 * c + 1] = ft;
+            changed |= (t != (int)typ[c]);
             typ[c] = (uint8_t)t;
         }
+        return __any_sync(FULL, changed);
     }
 
     // (A f)_i
@@ -383,6 +386,8 @@ struct Solver {
         for (int i = lane; i < m; i += 32) y[i] = 0.0;
 #pragma unroll 1
         for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
+#pragma unroll 1
+        for (int c = lane; c < nc; c += 32) typ[c] = 255;
         __syncwarp();
         flops = 0.0;
 #ifdef BW_PROFILE
@@ -398,11 +403,12 @@ struct Solver {
             for (int i = lane; i < m; i += 32) yk[i] = y[i];
             __syncwarp();
             bool have_r = false;
+            bool full_step = false;            // the previous Newton step of this stage was taken with t = 1
 #pragma unroll 1
             for (int it = 0; it < MAX_NEWTON; it++) {
                 if (implied_by >= 0 && *sibling == implied_by) { status = 3; break; }
                 BW_T0(t_a);
-                project_all();
+                const bool changed = project_all();
                 __syncwarp();
                 // gradient of the proximal sub-problem and, for free, the equilibrium residual b - A f
                 double gn2 = 0.0, rr2 = 0.0;
@@ -417,8 +423,15 @@ struct Solver {
                 }
                 warp_sum2(gn2, rr2);
                 BW_ACC(0, t_a);
-                // f is in K, so ||b - A f|| bounds r* from above at every iterate
-                if (gn2 <= 1e-20 || (exit_anytime && rr2 <= r_exit * r_exit)) { r = sqrt(rr2); have_r = true; break; }
+                // f is in K, so ||b - A f|| bounds r* from above at every iterate.  A full Newton step that
+                // leaves every contact on its cone face has solved the (then quadratic) sub-problem exactly:
+                // what is left of the gradient is rounding noise (it grows with |y| and can stay above the
+                // absolute threshold for ever on systems without equilibrium)
+                if (gn2 <= 1e-20 || (full_step && !changed) || (exit_anytime && rr2 <= r_exit * r_exit)) {
+                    r = sqrt(rr2);
+                    have_r = true;
+                    break;
+                }
                 BW_T0(t_b);
                 assemble_H(inv_rho);               // zero-fills rows 0..m-1, leaves row m alone
 #pragma unroll 1
@@ -483,6 +496,7 @@ struct Solver {
                 __syncwarp();
                 BW_ACC(4, t_e);
                 iters++;
+                full_step = (t == 1.0);
                 flops += (double)m * m * m / 3.0 + 2.0 * m * m + 156.0 * nc + 12.0 * m;
                 // no representable progress any more (|t d| below the rounding of y)
                 const double ymax = warp_max(yy);
