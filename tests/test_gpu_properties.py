@@ -1,0 +1,119 @@
+"""Size-independent properties at BASELINE.json's full sweep size (configs[3]: 65,536 random assemblies of
+1..15 blocks, shapes trapezoid / hexagon / cube1, mu cycled over 0.3 / 0.8 / 2.0), where the CPU oracle
+is too slow to be the checker:
+
+  * released-block equilibrium implies frozen-block equilibrium (the frozen block only adds supports);
+  * a larger friction coefficient never turns a stable assembly unstable (the cones grow);
+  * the edge-less rule of stability.py:53-56;
+  * results do not depend on how the assemblies are partitioned into batches (what sharding over GPUs
+    relies on) nor on the evaluation being repeated;
+  * the f32 observation, the u8 observation and the bit raster describe the same image, and the raster
+    of an assembly is the union of the rasters of its blocks rendered one by one.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOTAL = 65536
+SHAPES = ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"]
+MUS = np.array([0.3, 0.8, 2.0])
+
+
+def _build(lo, hi):
+    """assemblies [lo, hi) of the sweep: block counts and placements depend on the global index only"""
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    n = hi - lo
+    env = BatchedAssemblyGym(n, SHAPES, max_steps=None)
+    ids = np.arange(lo, hi)
+    env.set_mu(MUS[ids % 3])
+    env.reset(dict())
+    target = np.random.default_rng(0).integers(1, 16, size=TOTAL)[lo:hi]
+    for k in range(15):
+        c = env.enumerate_actions(np.linspace(-2.0, 4.0, 13), (0.0, 0.25, -0.25), amax=512, with_bits=False)
+        # a per-assembly pseudo-random valid candidate that does not depend on the batch layout
+        valid = c["valid"].bool()
+        nvalid = valid.sum(dim=1)
+        gid = torch.from_numpy(ids).to(valid.device)
+        pick = ((gid * 2654435761 + k * 40503 + 12345) % 1000003) % nvalid.clamp(min=1)
+        order = torch.cumsum(valid.int(), dim=1) - 1
+        idx = ((order == pick[:, None]) & valid).int().argmax(dim=1)
+        cand = c["cand"].view(n, 512, -1)
+        acts = cand[torch.arange(n, device=valid.device), idx].contiguous().view(-1)
+        mask = ((target > k) & (nvalid.cpu().numpy() > 0)).astype(np.uint8)
+        env.step(acts, mask=mask)
+    env.evaluate()
+    return env
+
+
+def _fields(out):
+    return {k: out[k].copy() for k in ("stable", "stable_unfrozen", "n_blocks", "n_interfaces", "solver_status", "error")}
+
+
+def test_full_sweep_properties():
+    import torch
+    env = _build(0, TOTAL)
+    out0 = env.read_out()
+    a = _fields(out0)
+    assert not a["error"].any()
+    # "not converged" (stable = None in the reference's terms) only for residuals inside the stated band
+    nc0, nc1 = (a["solver_status"] & 1) != 0, (a["solver_status"] & 2) != 0
+    assert nc0.sum() + nc1.sum() <= 8
+    assert ((out0["residual"][nc0] > 1e-9) & (out0["residual"][nc0] < 1e-4)).all()
+    assert ((out0["residual_unfrozen"][nc1] > 1e-9) & (out0["residual_unfrozen"][nc1] < 1e-4)).all()
+    band = nc0 | nc1
+    assert 7.0 < a["n_blocks"].mean() < 9.0 and 0.1 < a["stable"].mean() < 0.6
+    # released equilibrium => frozen equilibrium
+    assert not (a["stable_unfrozen"] & ~a["stable"] & 1).any()
+    # edge-less rule: without interfaces only the empty assembly (or a lone frozen block) is stable
+    no_itf = a["n_interfaces"] == 0
+    assert (a["stable_unfrozen"][no_itf] == (a["n_blocks"][no_itf] == 0)).all()
+    assert (a["stable"][no_itf] == (a["n_blocks"][no_itf] <= 1)).all()
+    # repeated evaluation: identical verdicts
+    env.evaluate()
+    b = _fields(env.read_out())
+    for k in a:
+        if k != "solver_status":                   # which sibling finishes first is not deterministic
+            assert np.array_equal(a[k], b[k]), k
+    # observation formats agree with the bit raster
+    bits, _ = env.raster_bits()
+    img = torch.empty((TOTAL, 1, 64, 64), dtype=torch.float32, device="cuda")
+    u8 = torch.empty((TOTAL, 64, 64), dtype=torch.uint8, device="cuda")
+    env.step([None] * 0 or env.actions_array([None] * TOTAL), block_img=img, block_u8=u8)
+    env.sync()
+    want = torch.from_numpy(env.bits_to_bool(bits[:4096]))
+    assert torch.equal(u8[:4096].cpu().bool(), want) and torch.equal(img[:4096, 0].cpu() == 1.0, want)
+    assert torch.equal(img[:, 0].to(torch.uint8), u8)
+    popcount = np.array([bin(int(w)).count("1") for w in bits[:4096].reshape(-1)]).reshape(4096, 64).sum(axis=1)
+    assert np.array_equal(popcount, u8[:4096].sum(dim=(1, 2)).cpu().numpy())
+    # the raster of an assembly = union of its blocks rendered one by one (bw_render_blocks_host)
+    from bridges_b200.envs.batched import shape_desc
+    from bridges_b200 import lib as L
+    blocks, nb = env.get_state()
+    descs = (L.bw_shape_desc * len(SHAPES))(*[shape_desc(t) for t in env.shape_tables])
+    for e in (0, 1, 2, 777, 4095, 40000, 65535):
+        union = np.zeros(64, dtype=np.uint64)
+        for i in range(nb[e]):
+            one = np.zeros(64, dtype=np.uint64)
+            blk = np.ascontiguousarray(blocks[e][i:i + 1])
+            env._check(env.lib.bw_render_blocks_host(env.handle, descs, len(SHAPES), blk.ctypes.data, 1, None, None,
+                                                     one.ctypes.data))
+            union |= one
+        assert np.array_equal(union, bits[e]), e
+    # more friction never destabilises
+    env.set_mu(np.full(TOTAL, 2.0))
+    env.evaluate()
+    c = _fields(env.read_out())
+    ok = ~band & ((c["solver_status"] & 3) == 0)
+    assert not (a["stable"] & ~c["stable"] & 1)[ok].any() and not (a["stable_unfrozen"] & ~c["stable_unfrozen"] & 1)[ok].any()
+    assert c["stable"].sum() > a["stable"].sum()
+    env.close()
+    # the same assemblies evaluated in four separate batches (the per-GPU shards of a 4-GPU run)
+    for r in range(4):
+        lo, hi = r * TOTAL // 4, (r + 1) * TOTAL // 4
+        part = _build(lo, hi)
+        p = _fields(part.read_out())
+        for k in ("stable", "stable_unfrozen", "n_blocks", "n_interfaces"):
+            assert np.array_equal(p[k], a[k][lo:hi]), (r, k)
+        part.close()
