@@ -84,6 +84,56 @@ def random_policy(seed=0):
     return policy
 
 
+def q_network_policy(policy_net, reward_features, obstacle_features, epsilon=0.0, seed=0, chunk_rows=8192):
+    """Greedy / epsilon-greedy policy over the valid candidates of EVERY environment with one batched
+    pass through an existing Q-network -- the lock-step form of the inference in `rollout_episode`
+    (robotoddler/training/successor_dqn.py:383-390).  `policy_net` keeps the reference's signature
+        policy_net(block_features, binary_features, action_features, reward_features, obstacle_features)
+            -> (q_values [R], ...)
+    (models/cv.py:76-105 SuccessorMLP, :41-65 ConvNet, ...) and sees R = sum of valid candidates rows:
+    row r pairs the state of its environment with one candidate raster.  reward_features /
+    obstacle_features: [E,1,64,64] task features (`env.observe(reward=True, obstacle=True)`).
+    Exploration picks a uniformly random valid candidate with probability epsilon per environment."""
+    gen = {"g": None}
+
+    def policy(env, cand):
+        E, dev, amax = env.num_envs, env.device, cand["amax"]
+        if gen["g"] is None:
+            gen["g"] = torch.Generator(device=dev)
+            gen["g"].manual_seed(seed)
+        valid = cand["valid"].bool()
+        slots = torch.arange(amax, device=dev)[None, :] < cand["n"][:, None]
+        valid = valid & slots
+        e_idx, a_idx = valid.nonzero(as_tuple=True)
+        state = env.observe(block=True, binary=True)
+        q_full = torch.full((E, amax), float("-inf"), device=dev)
+        was_training = getattr(policy_net, "training", False)
+        if hasattr(policy_net, "eval"):
+            policy_net.eval()
+        with torch.no_grad():
+            for lo in range(0, e_idx.numel(), chunk_rows):
+                er, ar = e_idx[lo:lo + chunk_rows], a_idx[lo:lo + chunk_rows]
+                action_f = env.expand_bits(cand["bits"][er, ar].contiguous())
+                q = policy_net(state["block"][er], state["binary"][er], action_f, reward_features[er],
+                               obstacle_features[er])
+                q = q[0] if isinstance(q, (tuple, list)) else q
+                q_full[er, ar] = q.reshape(-1).float()
+        if was_training:
+            policy_net.train()
+        index = q_full.argmax(dim=1)
+        if epsilon > 0.0:
+            noise = torch.rand((E, amax), device=dev, generator=gen["g"]).masked_fill(~valid, -1.0)
+            explore = torch.rand(E, device=dev, generator=gen["g"]) < epsilon
+            index = torch.where(explore, noise.argmax(dim=1), index)
+        has = valid.any(dim=1)
+        item = env.dt["action"].itemsize
+        chosen = cand["cand"].view(E, amax, item)[torch.arange(E, device=dev), index]
+        noop = torch.from_numpy(env.actions_array([None])[:1].view("uint8").copy()).to(dev)
+        actions = torch.where(has[:, None], chosen, noop[None, :].expand(E, item)).contiguous().view(-1)
+        return actions, torch.where(has, index, torch.full_like(index, -1)).to(torch.int32)
+    return policy
+
+
 def rollout_lockstep(env, policy, n_steps, x_discr_ground, offset_values=(0.0,), amax=128, replay=None,
                      gather=True):
     """Advance every environment `n_steps` times.

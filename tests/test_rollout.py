@@ -80,3 +80,63 @@ def test_lockstep_rollout_transitions_are_consistent():
     assert 0.05 < data["done"].mean() < 0.6
     # lin_reward is zero for unstable successors (successor_dqn.py:397-401)
     assert (data["lin_reward"][unstable] == 0).all()
+
+
+@pytest.mark.gpu
+def test_q_network_policy_batched_inference():
+    """One batched pass of a Q-network with the reference's 5-argument signature over the valid candidates
+    of all environments (successor_dqn.py:383-390 in lock-step form): the greedy choice equals a per-env
+    argmax computed on the host, envs without candidates get a no-op, and a rollout driven by an
+    nn.Module runs end to end."""
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    from bridges_b200.rollout import DeviceReplayBuffer, q_network_policy, rollout_lockstep
+    E = 48
+    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=10)
+    env.reset(dict(obstacles=[(0.6, 0, 0.3)], targets=[(0.6, 0, 0.9)]))
+    feats = env.observe(block=False, binary=False, obstacle=True, reward=True)
+    xg = np.linspace(-2, 0, 10)
+    seen = []
+
+    def lin_q(block, binary, action, reward, obstacle):          # q = lin_reward of the candidate
+        assert block.shape == action.shape == reward.shape == obstacle.shape and binary.shape == (block.shape[0], 6)
+        seen.append(block.shape[0])
+        return (action * reward).sum(dim=(1, 2, 3)), None, None
+
+    # bring the envs to different states first
+    rollout_lockstep(env, q_network_policy(lin_q, feats["reward"], feats["obstacle"], epsilon=1.0, seed=3), 2, xg,
+                     gather=False)
+    cand = env.enumerate_actions(xg, (0.0,), amax=128, with_bits=True)
+    actions, index = q_network_policy(lin_q, feats["reward"], feats["obstacle"])(env, cand)
+    env.sync()
+    valid = cand["valid"].cpu().numpy().astype(bool)
+    valid &= np.arange(128)[None, :] < cand["n"].cpu().numpy()[:, None]      # slots past n_cand are stale
+    bits = cand["bits"].cpu().numpy().view(np.uint64)
+    reward = feats["reward"].cpu().numpy()[:, 0]
+    acts = actions.cpu().numpy().view(env.dt["action"])
+    cands = cand["cand"].cpu().numpy().view(env.dt["action"]).reshape(E, 128)
+    assert seen[-1] == int(valid.sum())                          # one row per valid candidate, nothing else
+    for e in range(E):
+        img = BatchedAssemblyGym.bits_to_bool(bits[e])           # [128, 64, 64]
+        q = (img * reward[e][None]).sum(axis=(1, 2))
+        q[~valid[e]] = -np.inf
+        best = int(index[e].item())
+        assert valid[e, best] and q[best] >= q.max() - 1e-5 * max(1.0, abs(q.max()))
+        assert acts[e] == cands[e, best]
+
+    class TinyNet(torch.nn.Module):                              # same interface as models/cv.py:76-105
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4 * 16 + 6, 1)
+
+        def forward(self, block, binary, action, reward, obstacle):
+            x = torch.cat([torch.nn.functional.adaptive_avg_pool2d(t, 4).flatten(1) for t in (block, action, reward, obstacle)], 1)
+            return self.lin(torch.cat([x, binary], 1)).squeeze(1), None, None
+
+    net = TinyNet().to(env.device)
+    replay = DeviceReplayBuffer(2048, env.device)
+    rollout_lockstep(env, q_network_policy(net, feats["reward"], feats["obstacle"], epsilon=0.2, seed=1), 6, xg,
+                     replay=replay, gather=False)
+    assert len(replay) == 6 * E
+    data = {k: v[:len(replay)].cpu().numpy() for k, v in replay.data.items()}
+    assert np.array_equal(data["next_block_bits"], data["block_bits"] | data["action_bits"])
+    assert not (data["block_bits"] & data["action_bits"]).any()
