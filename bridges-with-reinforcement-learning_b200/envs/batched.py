@@ -159,7 +159,17 @@ class BatchedAssemblyGym:
         return arr
 
     def reset(self, tasks=None, mask=None):
+        """mask: host array or a uint8 CUDA tensor [E] (then, without tasks, nothing synchronises)."""
         d_tasks = self._to_device_bytes(self.make_tasks(tasks)) if tasks is not None else None
+        if isinstance(mask, torch.Tensor) and mask.is_cuda:
+            d_mask = mask.to(torch.uint8).contiguous()
+            self._check(self.lib.bw_reset(self.handle, d_tasks.data_ptr() if d_tasks is not None else None,
+                                          d_mask.data_ptr()))
+            if d_tasks is not None:
+                self.sync()
+            else:
+                self._keep = d_mask                 # stays alive until the next call; same stream as torch
+            return
         d_mask = self._to_device_bytes(np.asarray(mask, dtype=np.uint8)) if mask is not None else None
         self._check(self.lib.bw_reset(self.handle, d_tasks.data_ptr() if d_tasks is not None else None,
                                       d_mask.data_ptr() if d_mask is not None else None))
@@ -208,6 +218,21 @@ class BatchedAssemblyGym:
         self.sync()
         out = self._out if out is None else out
         return out.cpu().numpy().view(self.dt["step_out"])
+
+    def out_fields(self, out=None, names=("reward", "lin_reward", "terminated", "truncated", "stable",
+                                          "stable_unfrozen", "n_blocks")):
+        """Fields of the bw_step_out records as CUDA tensors [E] (no host synchronisation)."""
+        out = self._out if out is None else out
+        rec = out.view(self.num_envs, self.dt["step_out"].itemsize)
+        tmap = {"<f4": torch.float32, "<f8": torch.float64, "<i4": torch.int32, "|u1": torch.uint8}
+        res = {}
+        for name in names:
+            fdt, off = self.dt["step_out"].fields[name][:2]
+            if fdt.shape:
+                raise L.BridgesError("array fields are not exposed as tensors")
+            col = rec[:, off:off + fdt.itemsize].contiguous()
+            res[name] = col.view(tmap[fdt.str]).reshape(self.num_envs)
+        return res
 
     def evaluate(self):
         """Verdicts of the current assemblies without placing a block (Action.shape = -1)."""

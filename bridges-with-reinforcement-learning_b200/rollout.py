@@ -29,12 +29,25 @@ def gather_transitions(batch, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return batch
     world = dist.get_world_size(group)
-    out = {}
+    # one collective: every row is packed into a byte record, the records are gathered, then unpacked
+    n = next(iter(batch.values())).shape[0]
+    cols, layout = [], []
     for name, t in batch.items():
-        src = t.to(torch.uint8) if t.dtype == torch.bool else t
-        dst = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-        dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
-        out[name] = dst.to(torch.bool) if t.dtype == torch.bool else dst
+        src = (t.to(torch.uint8) if t.dtype == torch.bool else t).contiguous().reshape(n, -1)
+        raw = src.view(torch.uint8)
+        cols.append(raw)
+        layout.append((name, t.dtype, tuple(t.shape[1:]), raw.shape[1]))
+    packed = torch.cat(cols, dim=1).contiguous()
+    dst = torch.empty((world * n, packed.shape[1]), dtype=torch.uint8, device=packed.device)
+    dist.all_gather_into_tensor(dst, packed, group=group)
+    out, off = {}, 0
+    for name, dtype, shape, width in layout:
+        raw = dst[:, off:off + width].contiguous()
+        off += width
+        if dtype == torch.bool:
+            out[name] = raw.reshape((world * n,) + shape).to(torch.bool)
+        else:
+            out[name] = raw.view(dtype).reshape((world * n,) + shape)
     return out
 
 
@@ -159,11 +172,11 @@ def rollout_lockstep(env, policy, n_steps, x_discr_ground, offset_values=(0.0,),
         next_binary = torch.empty_like(binary)
         out_dev = env.step(actions, binary=next_binary)
         after = env.raster_bits_device()
-        out = env.read_out(out_dev)
-        done = torch.from_numpy((out["terminated"] | out["truncated"]).astype(bool)).to(dev) | ~has_action
+        out = env.out_fields(out_dev, ("reward", "lin_reward", "terminated", "truncated"))   # device views, no sync
+        done = ((out["terminated"] | out["truncated"]) != 0) | ~has_action
         batch = dict(block_bits=before, action_bits=sel, next_block_bits=after, binary=binary.clone(),
-                     next_binary=next_binary, reward=torch.from_numpy(out["reward"].copy()).to(dev),
-                     lin_reward=torch.from_numpy(out["lin_reward"].copy()).to(dev), done=done, env=env_ids)
+                     next_binary=next_binary, reward=out["reward"].clone(), lin_reward=out["lin_reward"].clone(),
+                     done=done, env=env_ids)
         keep = has_action                                   # envs without a valid candidate yield no transition
         if gather:
             full = gather_transitions(dict(batch, keep=keep))
@@ -174,7 +187,6 @@ def rollout_lockstep(env, policy, n_steps, x_discr_ground, offset_values=(0.0,),
         last = (batch, keep)
         env.reset_done()
         # environments that could not move end their episode too (rollout_episode, successor_dqn.py:409-411)
-        if bool((~has_action).any()):
-            env.reset(None, mask=(~has_action).to(torch.uint8).cpu().numpy())
+        env.reset(None, mask=(~has_action).to(torch.uint8))
         binary = torch.where(done[:, None], fresh, next_binary)
     return last
