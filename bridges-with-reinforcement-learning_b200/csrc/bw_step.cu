@@ -340,48 +340,70 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 
     BW_STAMP(1);
     // ---------------- phase 2: interfaces (one candidate per body pair, lexicographic order)
+    // Thread per pair for the bounding-box reject; the surviving pairs of a warp are then examined one
+    // after the other by the whole warp, lane = (face of a, face of b), so that the first interface in
+    // (face a, face b) order is found with one test per lane instead of up to 36 tests in one thread.
     unsigned hitmask = 0;  // bit r = pair (r*64 + tid) has an interface
     for (int r = 0; r < 3; r++) {
         const int p = r * 64 + tid;
-        bool hit = false;
+        bool near = false;
         if (p < NPAIR) {
             const int A = c_pair_a[p], B = c_pair_b[p];
             if (B < nbody) {
                 const double *BA = s_body + A * BODY_DOUBLES, *BB = s_body + B * BODY_DOUBLES;
                 const double slack = P.tmax + 1e-9;
-                if (BA[4] <= BB[5] + slack && BB[4] <= BA[5] + slack && BA[6] <= BB[7] + slack && BB[6] <= BA[7] + slack) {
-                    const int nfa = (A == 0) ? 1 : P.shapes[s_shape[A - 1]].n_faces;
-                    const int nfb = P.shapes[s_shape[B - 1]].n_faces;
-                    const double dmin = fmin(BA[3], BB[3]);
-                    for (int fa = 0; fa < nfa && !hit; fa++) {
-                        const double *FA = s_face + (A * NF + fa) * FACE_DOUBLES;
-                        const double nx = FA[0], nz = FA[1], cx = FA[2], cz = FA[3];
-                        const double tx = nz, tz = -nx;
-                        const double sa0 = dadd(dmul(dsub(FA[4], cx), tx), dmul(dsub(FA[5], cz), tz));
-                        const double sa1 = dadd(dmul(dsub(FA[6], cx), tx), dmul(dsub(FA[7], cz), tz));
-                        const double alo = fmin(sa0, sa1), ahi = fmax(sa0, sa1);
-                        for (int fb = 0; fb < nfb; fb++) {
-                            const double *FB = s_face + (B * NF + fb) * FACE_DOUBLES;
-                            if (dadd(dmul(nx, FB[0]), dmul(nz, FB[1])) >= 0.0) continue;
-                            const double d0 = dadd(dmul(dsub(FB[4], cx), nx), dmul(dsub(FB[5], cz), nz));
-                            const double d1 = dadd(dmul(dsub(FB[6], cx), nx), dmul(dsub(FB[7], cz), nz));
-                            if (fabs(d0) > P.tmax || fabs(d1) > P.tmax) continue;
+                near = BA[4] <= BB[5] + slack && BB[4] <= BA[5] + slack && BA[6] <= BB[7] + slack && BB[6] <= BA[7] + slack;
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, near);
+        unsigned found = 0;
+#pragma unroll 1
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int pp = r * 64 + warp * 32 + src;                  // uniform in the warp
+            const int A = c_pair_a[pp], B = c_pair_b[pp];
+            const int nfa = (A == 0) ? 1 : P.shapes[s_shape[A - 1]].n_faces;
+            const int nfb = P.shapes[s_shape[B - 1]].n_faces;
+            const double dmin = fmin(s_body[A * BODY_DOUBLES + 3], s_body[B * BODY_DOUBLES + 3]);
+#pragma unroll 1
+            for (int fa0 = 0; fa0 < nfa; fa0 += 4) {                  // faces 0-3 of a, then 4-5
+                const int fa = fa0 + (lane >> 3), fb = lane & 7;
+                bool ok = false;
+                double lo = 0.0, hi = 0.0;
+                if (fa < nfa && fb < nfb) {
+                    const double *FA = s_face + (A * NF + fa) * FACE_DOUBLES;
+                    const double *FB = s_face + (B * NF + fb) * FACE_DOUBLES;
+                    const double nx = FA[0], nz = FA[1], cx = FA[2], cz = FA[3];
+                    if (dadd(dmul(nx, FB[0]), dmul(nz, FB[1])) < 0.0) {
+                        const double d0 = dadd(dmul(dsub(FB[4], cx), nx), dmul(dsub(FB[5], cz), nz));
+                        const double d1 = dadd(dmul(dsub(FB[6], cx), nx), dmul(dsub(FB[7], cz), nz));
+                        if (!(fabs(d0) > P.tmax || fabs(d1) > P.tmax)) {
+                            const double tx = nz, tz = -nx;
+                            const double sa0 = dadd(dmul(dsub(FA[4], cx), tx), dmul(dsub(FA[5], cz), tz));
+                            const double sa1 = dadd(dmul(dsub(FA[6], cx), tx), dmul(dsub(FA[7], cz), tz));
                             const double sb0 = dadd(dmul(dsub(FB[4], cx), tx), dmul(dsub(FB[5], cz), tz));
                             const double sb1 = dadd(dmul(dsub(FB[6], cx), tx), dmul(dsub(FB[7], cz), tz));
-                            const double lo = fmax(alo, fmin(sb0, sb1));
-                            const double hi = fmin(ahi, fmax(sb0, sb1));
-                            const double size = dmul(dsub(hi, lo), dmin);
-                            if (!(size >= P.amin)) continue;
-                            s_pair_lohi[2 * p] = lo;
-                            s_pair_lohi[2 * p + 1] = hi;
-                            s_pair_faces[p] = (uint16_t)(fa * 8 + fb);
-                            hit = true;
-                            break;
+                            lo = fmax(fmin(sa0, sa1), fmin(sb0, sb1));
+                            hi = fmin(fmax(sa0, sa1), fmax(sb0, sb1));
+                            ok = dmul(dsub(hi, lo), dmin) >= P.amin;
                         }
                     }
                 }
+                const unsigned okmask = __ballot_sync(FULL, ok);
+                if (okmask) {
+                    if (lane == __ffs(okmask) - 1) {
+                        s_pair_lohi[2 * pp] = lo;
+                        s_pair_lohi[2 * pp + 1] = hi;
+                        s_pair_faces[pp] = (uint16_t)(fa * 8 + fb);
+                    }
+                    found |= 1u << src;
+                    break;
+                }
             }
         }
+        __syncwarp();
+        const bool hit = (found >> lane) & 1u;
         const unsigned bal = __ballot_sync(FULL, hit);
         if (lane == 0) sh_cnt[r][warp] = __popc(bal);
         if (hit) hitmask |= (1u << r) | ((unsigned)__popc(bal & ((1u << lane) - 1)) << (8 + 8 * r));
@@ -453,22 +475,58 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     if (save_nitf != nullptr && tid == 0) save_nitf[e] = nitf;
     __syncthreads();
 
-    // adjacency lists body -> contacts (deterministic order)
-    if (tid == 0) {
-        int acc = 0;
-        // counts first
-        uint8_t cnt[NBODY];
-        for (int b = 0; b < NBODY; b++) cnt[b] = 0;
-        for (int c = 0; c < nc; c++) { cnt[s_ca[c]]++; cnt[s_cb[c]]++; }
-        for (int b = 0; b < NBODY; b++) { s_adj_ptr[b] = (uint8_t)acc; acc += cnt[b]; }
-        s_adj_ptr[NBODY] = (uint8_t)acc;
-    }
-    __syncthreads();
-    if (tid < nbody) {
-        int w = s_adj_ptr[tid];
-        for (int c = 0; c < nc; c++) {
-            if (s_ca[c] == tid) s_adj[w++] = (uint8_t)c;
-            else if (s_cb[c] == tid) s_adj[w++] = (uint8_t)(c | 0x80);
+    // adjacency lists body -> contacts, ascending contact index (deterministic summation order).
+    // Thread = contact point (two rounds above 64 points); per body one ballot per warp gives the
+    // counts and the rank of every contact inside its 32-point segment.
+    __shared__ uint8_t sh_seg_cnt[NBODY][4];          // [body][segment], segment = round * 2 + warp
+    {
+        int my_a[2], my_b[2], rank_a[2] = {0, 0}, rank_b[2] = {0, 0};
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int c = q * 64 + tid;
+            my_a[q] = (c < nc) ? s_ca[c] : -1;
+            my_b[q] = (c < nc) ? s_cb[c] : -1;
+        }
+        const int nq = (nc + 63) >> 6;
+        const unsigned lt = (1u << lane) - 1;
+#pragma unroll 1
+        for (int X = 0; X < nbody; X++) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (q < nq) {
+                    const bool fa = my_a[q] == X, fb = my_b[q] == X;
+                    const unsigned bal = __ballot_sync(FULL, fa || fb);
+                    if (lane == 0) sh_seg_cnt[X][q * 2 + warp] = (uint8_t)__popc(bal);
+                    if (fa) rank_a[q] = __popc(bal & lt);
+                    if (fb) rank_b[q] = __popc(bal & lt);
+                } else if (lane == 0) {
+                    sh_seg_cnt[X][q * 2 + warp] = 0;
+                }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {                               // exclusive scan of the per-body totals
+            int tot = 0;
+            if (lane < nbody) tot = sh_seg_cnt[lane][0] + sh_seg_cnt[lane][1] + sh_seg_cnt[lane][2] + sh_seg_cnt[lane][3];
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane <= NBODY) s_adj_ptr[lane] = (uint8_t)(inc - tot);    // bodies >= nbody: empty lists at the end
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int c = q * 64 + tid;
+            if (c < nc) {
+                const int seg = q * 2 + warp;
+                int pa = s_adj_ptr[my_a[q]] + rank_a[q], pb = s_adj_ptr[my_b[q]] + rank_b[q];
+                for (int sg = 0; sg < seg; sg++) { pa += sh_seg_cnt[my_a[q]][sg]; pb += sh_seg_cnt[my_b[q]][sg]; }
+                s_adj[pa] = (uint8_t)c;
+                s_adj[pb] = (uint8_t)(c | 0x80);
+            }
         }
     }
     __syncthreads();
