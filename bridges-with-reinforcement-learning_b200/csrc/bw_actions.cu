@@ -230,8 +230,30 @@ __global__ void select_random_kernel(Params P, const bw_action *__restrict__ can
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P.E) return;
     const int cnt = n_cand[e];
+    const uint8_t *row = valid + (size_t)e * amax;
+    // valid flags are 0/1 bytes: count / search them 16 at a time when the row is 16-byte aligned
+    const bool wide = (amax & 15) == 0 && (reinterpret_cast<uintptr_t>(valid) & 15) == 0;
     int nvalid = 0;
-    for (int a = 0; a < cnt; a++) nvalid += valid[(size_t)e * amax + a];
+    if (wide) {
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+        for (int q = 0; q * 16 < cnt; q++) {
+            uint4 v = row4[q];
+            const int left = cnt - q * 16;               // flags past n_cand are stale: mask them off
+            if (left < 16) {
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                for (int k = 0; k < 4; k++) {
+                    const int keep = left - 4 * k;
+                    if (keep <= 0) w[k] = 0;
+                    else if (keep < 4) w[k] &= (1u << (8 * keep)) - 1;
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            nvalid += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+                      __popc(v.w & 0x01010101u);
+        }
+    } else {
+        for (int a = 0; a < cnt; a++) nvalid += row[a];
+    }
     bw_action act;
     act.target_block = -1; act.target_face = 0; act.shape = -1; act.face = 0;
     act.offset_x = 0.0; act.offset_y = 0.0; act.frozen = 0; act.reserved0 = 0;
@@ -239,8 +261,19 @@ __global__ void select_random_kernel(Params P, const bw_action *__restrict__ can
     if (nvalid > 0) {
         const uint64_t r = mix64(seed ^ mix64((uint64_t)e * 0x632BE59BD9B4E019ull + (uint64_t)P.n_blocks[e]));
         int k = (int)(r % (uint64_t)nvalid);
-        for (int a = 0; a < cnt; a++) {
-            if (valid[(size_t)e * amax + a]) {
+        int a = 0;
+        if (wide) {                                       // skip whole 16-flag groups first
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+            for (;; a += 16) {
+                const uint4 v = row4[a >> 4];
+                const int c16 = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+                                __popc(v.w & 0x01010101u);
+                if (k < c16 || a + 16 >= cnt) break;
+                k -= c16;
+            }
+        }
+        for (; a < cnt; a++) {
+            if (row[a]) {
                 if (k == 0) { chosen = a; break; }
                 k--;
             }
