@@ -234,6 +234,7 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     P.marker = h->d_shapes + BW_MAX_SHAPES;
     if (cfg->collision_mode != 0 && cfg->collision_mode != 1) return fail(h, BW_ERR_INVALID, "collision_mode must be 0 or 1");
     P.collision_mode = cfg->collision_mode;
+    P.screen = getenv("BW_NO_SCREEN") ? 0 : 1;     // tuning hook (tools/ only): solver without the mechanism screen
     P.collision_tol = cfg->collision_tol;
     for (int k = 0; k < 3; k++) { P.bounds_lo[k] = cfg->bounds_lo[k]; P.bounds_hi[k] = cfg->bounds_hi[k]; }
 

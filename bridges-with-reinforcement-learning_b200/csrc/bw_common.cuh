@@ -71,6 +71,7 @@ struct Params {
     const ShapeDev *shapes;    // [n_shapes]
     const ShapeDev *marker;    // the 0.6 cube of obstacles / target markers (cube06.urdf)
     int32_t collision_mode;    // 0: flags constant False; 1: polygon penetration (assembly_env.py:346-391)
+    int32_t screen;            // 1: rigid-mechanism certificates before the equilibrium solve (bw_solver.cuh)
     double collision_tol;
     double bounds_lo[3], bounds_hi[3];
     // state

@@ -5,7 +5,7 @@
 //     find f in K = prod {(fn, ft): |ft| <= mu fn}  with  A f = b,
 // three rows per free block.  Computed quantity: r = min_{f in K} ||A f - b|| (b normalised) and,
 // when r = 0, the minimum-norm f.  Method: proximal-point iteration on the
-// dual  d(y) = b.y - 1/2 ||P_K(A^T y)||^2  with rho = 1e2, 1e4, ...; every proximal sub-problem by
+// dual  d(y) = b.y - 1/2 ||P_K(A^T y)||^2  with rho = 1e4, 1e8, 1e8, ...; every proximal sub-problem by
 // a semismooth Newton method:
 //     gradient   b - A P_K(A^T y) - (y - y_k)/rho
 //     Hessian    A J A^T + I/rho      (J = generalised Jacobian of the cone projection)
@@ -21,7 +21,7 @@ namespace bw {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NSCHED = 6;
-__constant__ double c_rho[NSCHED] = {1e2, 1e4, 1e6, 1e8, 1e8, 1e8};
+__constant__ double c_rho[NSCHED] = {1e4, 1e8, 1e8, 1e8, 1e8, 1e8};
 constexpr int MAX_NEWTON = 60;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -102,6 +102,7 @@ struct Solver {
     double flops;            // work estimate, see DESIGN.md section 6
 #ifdef BW_PROFILE
     long long acc_t[6];      // grad, assemble, factor+solve, A^T d + dots, line search + update, residual
+    long long t_screen;      // mechanism screen
 #define BW_T0(name) const long long name = clock64()
 #define BW_ACC(i, t0) acc_t[i] += clock64() - (t0)
 #else
@@ -379,6 +380,140 @@ struct Solver {
         return warp_sum(fh);
     }
 
+    // Mechanism screen: a Farkas certificate of "no equilibrium" whose dual vector is one rigid virtual
+    // motion of a sub-assembly S of the free blocks.  Inside S the relative motion at every contact is
+    // zero, so only the contacts between S and the rest matter: with the wrenches (Fx, Fz, torque/L0 about
+    // the origin) of the two friction-cone edge rays of every such contact point, sigma_k r_k (sigma = +1
+    // when S holds body b of the contact, -1 when it holds body a), and the weight wrench b_S of S,
+    //     n . (sigma_k r_k) >= 0 for all boundary rays  and  n . b_S < 0
+    // proves that no non-negative combination of the rays balances b_S, i.e. A f = b has no solution in K.
+    // Candidate sets: for every free block i the blocks resting on it, S_i = {i} + every later free block
+    // in contact with a member (for a single tower: the top of the structure from i upwards), from the
+    // last block down.  Candidate motions n per boundary contact point: the rotation about that point
+    // (r+ x r-) and the translations perpendicular to its two edge rays, both signs.  Checked with margins
+    // (EPS on the rays, DELTA on the weight) so that only clear certificates count; everything else goes
+    // to solve().  On the bench rollouts this decides 96 % of the systems without equilibrium
+    // (tools/solver_lab.py: an LP on the aggregated 3-row systems catches the same cases).
+    // Scratch: g, h, f (rays), invd (bodies of a contact), L (contact adjacency masks of the bodies).
+    __device__ bool screen(const double *body, double invL0) {
+        constexpr double EPS = 1e-10, DELTA = 1e-5;
+        if (nc > 64) return false;
+        uint8_t *cba = reinterpret_cast<uint8_t *>(invd), *cbb = cba + nc;
+        unsigned *adjm = reinterpret_cast<unsigned *>(L);               // [NBODY] free-free contact adjacency (68 B <= the 80 B of a 1-block L)
+        if (lane < NBODY) adjm[lane] = 0u;
+        __syncwarp();
+#pragma unroll 1
+        for (int c = lane; c < nc; c += 32) {
+            const double *Gb = G + c * 12 + 6;                  // wrench on body b about its centroid
+            const int A = c_a[c], B = c_b[c];
+            const double cx = body[B * 8], cz = body[B * 8 + 1];
+            const double nx = Gb[0], nz = Gb[1], nt = Gb[2] + (cx * Gb[1] - cz * Gb[0]) * invL0;
+            const double tx = Gb[3], tz = Gb[4], tt = Gb[5] + (cx * Gb[4] - cz * Gb[3]) * invL0;
+            const double px = nx + mu * tx, pz = nz + mu * tz, pt = nt + mu * tt;
+            const double qx = nx - mu * tx, qz = nz - mu * tz, qt = nt - mu * tt;
+            const double ip = fast_rsqrt(px * px + pz * pz + pt * pt), iq = fast_rsqrt(qx * qx + qz * qz + qt * qt);
+            g[2 * c] = px * ip; g[2 * c + 1] = pz * ip; f[2 * c] = pt * ip;
+            h[2 * c] = qx * iq; h[2 * c + 1] = qz * iq; f[2 * c + 1] = qt * iq;
+            cba[c] = (uint8_t)A;
+            cbb[c] = (uint8_t)B;
+            if (rowbase[A] >= 0 && rowbase[B] >= 0) {
+                atomicOr(&adjm[A], 1u << B);
+                atomicOr(&adjm[B], 1u << A);
+            }
+        }
+        __syncwarp();
+        // lane = free block i: S_i as a mask over bodies and its weight wrench (0, ws, ts)
+        int mybody = 0;
+        unsigned myadj = 0, S = 0;
+        double w1 = 0.0, t1 = 0.0;
+        if (lane < nfree) {
+            mybody = freebody[lane];
+            myadj = adjm[mybody];
+            S = 1u << mybody;
+            w1 = b[3 * lane + 1];
+            t1 = body[mybody * 8] * w1 * invL0;
+        }
+        double ws = w1, ts = t1;
+#pragma unroll 1
+        for (int j = 1; j < nfree; j++) {
+            const int bj = __shfl_sync(FULL, mybody, j);
+            const unsigned aj = __shfl_sync(FULL, myadj, j);
+            const double wj = __shfl_sync(FULL, w1, j), tj = __shfl_sync(FULL, t1, j);
+            if (j > lane && (aj & S)) { S |= 1u << bj; ws += wj; ts += tj; }
+        }
+#pragma unroll 1
+        for (int i = nfree - 1; i >= 0; i--) {
+            const unsigned Si = __shfl_sync(FULL, S, i);
+            const double bw = __shfl_sync(FULL, ws, i), bt = __shfl_sync(FULL, ts, i);
+            // boundary contacts of S_i: sigma = +1 (bit in mp) when S holds body b, -1 (mm) for body a
+            unsigned mp0 = 0, mm0 = 0, mp1 = 0, mm1 = 0;
+            {
+                int c = lane;
+                bool ina = (c < nc) && ((Si >> cba[c]) & 1u), inb = (c < nc) && ((Si >> cbb[c]) & 1u);
+                mp0 = __ballot_sync(FULL, inb && !ina);
+                mm0 = __ballot_sync(FULL, ina && !inb);
+                if (nc > 32) {
+                    c = lane + 32;
+                    ina = (c < nc) && ((Si >> cba[c]) & 1u); inb = (c < nc) && ((Si >> cbb[c]) & 1u);
+                    mp1 = __ballot_sync(FULL, inb && !ina);
+                    mm1 = __ballot_sync(FULL, ina && !inb);
+                }
+            }
+            if ((mp0 | mm0 | mp1 | mm1) == 0) {
+                if (bw > 0.0) return true;        // nothing holds S
+                continue;
+            }
+            const double bn2 = bw * bw + bt * bt;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const unsigned mine = half ? (mp1 | mm1) : (mp0 | mm0);
+                if (mine == 0) continue;
+                bool found = false;
+                if ((mine >> lane) & 1u) {
+                    const int q = half * 32 + lane;
+                    const double ax = g[2 * q], az = g[2 * q + 1], at = f[2 * q];
+                    const double ex = h[2 * q], ez = h[2 * q + 1], et = f[2 * q + 1];
+                    // rotation about the contact point; translations perpendicular to the two edge rays
+                    const double n0x = az * et - at * ez, n0z = at * ex - ax * et, n0t = ax * ez - az * ex;
+                    const double n1x = az, n1z = -ax, n2x = ez, n2z = -ex;
+                    double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300, mn2 = 1e300, mx2 = -1e300;
+#pragma unroll 1
+                    for (int hk = 0; hk < 2; hk++) {
+                        const unsigned plus = hk ? mp1 : mp0;
+                        unsigned todo = plus | (hk ? mm1 : mm0);
+#pragma unroll 1
+                        while (todo) {
+                            const int kb = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int k = hk * 32 + kb;
+                            const double sg = ((plus >> kb) & 1u) ? 1.0 : -1.0;
+                            const double rx = g[2 * k] * sg, rz = g[2 * k + 1] * sg, rt = f[2 * k] * sg;
+                            const double sx = h[2 * k] * sg, sz = h[2 * k + 1] * sg, st = f[2 * k + 1] * sg;
+                            const double d0 = n0x * rx + n0z * rz + n0t * rt, e0 = n0x * sx + n0z * sz + n0t * st;
+                            const double d1 = n1x * rx + n1z * rz, e1 = n1x * sx + n1z * sz;
+                            const double d2 = n2x * rx + n2z * rz, e2 = n2x * sx + n2z * sz;
+                            mn0 = fmin(mn0, fmin(d0, e0)); mx0 = fmax(mx0, fmax(d0, e0));
+                            mn1 = fmin(mn1, fmin(d1, e1)); mx1 = fmax(mx1, fmax(d1, e1));
+                            mn2 = fmin(mn2, fmin(d2, e2)); mx2 = fmax(mx2, fmax(d2, e2));
+                        }
+                    }
+                    // with l = |n|:  all sigma r . n >= -EPS l  and  n . b_S <= -DELTA l |b_S|   (or the mirror image)
+                    const double l0 = n0x * n0x + n0z * n0z + n0t * n0t, l1 = n1x * n1x + n1z * n1z, l2 = n2x * n2x + n2z * n2z;
+                    const double w0 = n0z * bw + n0t * bt, w1n = n1z * bw, w2n = n2z * bw;   // n . b_S, b_S = (0, bw, bt)
+                    const double E2 = EPS * EPS, D2 = DELTA * DELTA * bn2;
+                    if (l0 > 1e-18) found |= ((mn0 >= 0.0 || mn0 * mn0 <= E2 * l0) && w0 < 0.0 && w0 * w0 >= D2 * l0) ||
+                                             ((mx0 <= 0.0 || mx0 * mx0 <= E2 * l0) && w0 > 0.0 && w0 * w0 >= D2 * l0);
+                    if (l1 > 1e-18) found |= ((mn1 >= 0.0 || mn1 * mn1 <= E2 * l1) && w1n < 0.0 && w1n * w1n >= D2 * l1) ||
+                                             ((mx1 <= 0.0 || mx1 * mx1 <= E2 * l1) && w1n > 0.0 && w1n * w1n >= D2 * l1);
+                    if (l2 > 1e-18) found |= ((mn2 >= 0.0 || mn2 * mn2 <= E2 * l2) && w2n < 0.0 && w2n * w2n >= D2 * l2) ||
+                                             ((mx2 <= 0.0 || mx2 * mx2 <= E2 * l2) && w2n > 0.0 && w2n * w2n >= D2 * l2);
+                }
+                if (__any_sync(FULL, found)) return true;
+            }
+        }
+        return false;
+    }
+
     // returns status: 0 feasible (r <= r_exit), 1 stalled at r* > 0, 2 not converged,
     // 3 verdict implied by the sibling solve (released-block equilibrium => frozen-block equilibrium)
     __device__ int solve(double &r_out, int &iters_out) {
@@ -470,7 +605,11 @@ struct Solver {
                 const double base = phi0 + fh0;
                 double t = 1.0;
                 double p = base - fdoth(1.0) - dd * inv_rho;
-                if (p < -1e-12 * phi0) {
+                // the full step is kept whenever it satisfies the search's own acceptance test
+                // |phi'(1)| <= 0.1 phi'(0): on a piece without a change of cone face phi'(1) is rounding noise
+                // of either sign (it grows with |y|), and a search started by that noise ends at t = 0.9 --
+                // the gradient then shrinks by only 10x per Newton step instead of vanishing
+                if (p < -0.1 * phi0) {
                     // bracket the root with a safeguarded regula falsi until |phi'| <= 0.1 phi'(0)
                     double lo = 0.0, plo = phi0, hi = 1.0, phi = p;
 #pragma unroll 1

@@ -599,17 +599,35 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         } else if (warp == 0 && placed && prev_released_ok && !want_forces) {
             stable = 1; status = 4; res = prev_released_res;
         } else {
-            status = S.solve(res, iters);
-            // out of stages with a residual already under the verdict threshold: converged within the margin
-            if (status == 2 && res <= P.stable_tol) status = 0;
-            if (status == 3) { stable = S.implied_by; res = nan(""); }
-            else stable = (status != 2) && (res <= P.stable_tol);
+            bool certified = false;
+#ifdef BW_PROFILE
+            for (int q = 0; q < 6; q++) S.acc_t[q] = 0;
+            S.t_screen = 0;
+#endif
+            if (!want_forces && P.screen != 0) {
+                BW_T0(t_s);
+                certified = S.screen(s_body, invL0);
+#ifdef BW_PROFILE
+                S.t_screen = clock64() - t_s;
+#endif
+            }
+            if (certified) {
+                stable = 0; status = 5; res = nan("");   // rigid-mechanism certificate: no equilibrium, no solve
+            } else {
+                status = S.solve(res, iters);
+                // out of stages with a residual already under the verdict threshold: converged within the margin
+                if (status == 2 && res <= P.stable_tol) status = 0;
+                if (status == 3) { stable = S.implied_by; res = nan(""); }
+                else stable = (status != 2) && (res <= P.stable_tol);
+            }
         }
         if (lane == 0) { sh_verdict[warp] = stable; __threadfence_block(); }
 #ifdef BW_PROFILE
         if (lane == 0) {
             sh_prof_solve[warp] = clock64() - prof_t[2];
-            for (int q = 0; q < 6; q++) sh_prof_sub[warp][q] = (nitf > 0 && nfree > 0 && !overflow) ? S.acc_t[q] : 0;
+            const bool ran = (nitf > 0 && nfree > 0 && !overflow) && !(warp == 0 && status == 4);
+            for (int q = 0; q < 5; q++) sh_prof_sub[warp][q] = ran ? S.acc_t[q] : 0;
+            sh_prof_sub[warp][5] = ran ? S.t_screen : 0;
         }
 #endif
         if (lane == 0) {

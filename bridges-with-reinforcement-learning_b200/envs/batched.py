@@ -236,7 +236,12 @@ class BatchedAssemblyGym:
 
     def evaluate(self):
         """Verdicts of the current assemblies without placing a block (Action.shape = -1)."""
-        return self.step([None] * self.num_envs)
+        if getattr(self, "_noop_actions", None) is None:
+            arr = np.zeros(self.num_envs, dtype=self.dt["action"])
+            arr["target_block"] = -1
+            arr["shape"] = -1
+            self._noop_actions = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(self.device)
+        return self.step(self._noop_actions)
 
     # ------------------------------------------------------------------ observations
     def observe(self, block=True, binary=True, obstacle=False, reward=False):

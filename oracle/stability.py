@@ -243,7 +243,7 @@ def equilibrium_residual(A, b, mu):
     return float(np.linalg.norm(resid)) / nb
 
 
-RHO_SCHEDULE = (1e2, 1e4, 1e6, 1e8, 1e8, 1e8)
+RHO_SCHEDULE = (1e4, 1e8, 1e8, 1e8, 1e8, 1e8)
 
 
 def min_norm_forces(A, b, mu, schedule=RHO_SCHEDULE, max_newton=60):
@@ -296,7 +296,7 @@ def min_norm_forces(A, b, mu, schedule=RHO_SCHEDULE, max_newton=60):
 
             t = 1.0
             p = dphi(t)
-            if p < -1e-12 * phi0:
+            if p < -0.1 * phi0:          # full step kept when it passes the search's own acceptance test
                 # bracket the root of the piecewise-linear derivative (safeguarded regula falsi)
                 lo, plo, hi, phi = 0.0, phi0, 1.0, p
                 for _ls in range(20):

@@ -36,13 +36,13 @@ for nb in range(1, 11):
         print(f"n_blocks={nb:2d} n={sel.sum():5d} total mean {cols[6][sel].mean():9.0f} max {cols[6][sel].max():9.0f}  iters mean {it[sel].mean():5.1f}")
 
 sb = np.concatenate(subs)
-for k, n in enumerate(["grad(A^T y, proj, A f)", "assemble H", "cholesky+solves", "A^T d + dots", "line search + update", "residual()"]):
+for k, n in enumerate(["grad(A^T y, proj, A f)", "assemble H", "cholesky+solves", "A^T d + dots", "line search + update", "mechanism screen"]):
     print(f"warp1 solve / {n:24s} mean {sb[:, k].mean():9.0f}  share {sb[:, k].sum() / sb[:, :6].sum():6.1%}")
 for k, n in enumerate(["memset+task load", "targets+state write", "distances"]):
     print(f"bookkeeping cumulative / {n:22s} mean {sb[:, 8 + k].mean():9.0f}")
 big = o["n_blocks"] >= 8
 if big.sum():
     print(f"--- envs with >= 8 blocks (n={int(big.sum())}): warp1 solve cycles by sub-phase, mean per env")
-    for k, n in enumerate(["grad", "assemble H", "cholesky+solves", "A^T d + dots", "line search + update", "residual()"]):
+    for k, n in enumerate(["grad", "assemble H", "cholesky+solves", "A^T d + dots", "line search + update", "mechanism screen"]):
         print(f"   {n:24s} {sb[big, k].mean():9.0f}  share {sb[big, k].sum() / sb[big, :6].sum():6.1%}")
     print("   total per env mean %.0f max %.0f; newton iters (both warps) mean %.1f" % (cols[6][big].mean(), cols[6][big].max(), it[big].mean()))
