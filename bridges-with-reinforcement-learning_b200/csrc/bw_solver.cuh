@@ -92,6 +92,7 @@ struct Solver {
     uint8_t *typ;
     int8_t *rowbase;         // body -> first row or -1 (support)
     uint8_t *freebody;       // free block index -> body
+    uint8_t *firstcol;       // free block index -> first column of its rows' envelope (set by solve())
     int m, nfree, nc, nitf, lane;
     double mu, inv_den;
     double r_exit;           // a residual <= r_exit ends the solve as feasible (1e-9 when the forces are
@@ -257,8 +258,9 @@ struct Solver {
             const double *rA = L + tri(c0), *rB = L + tri(c0 + 1), *rC = L + tri(c0 + 2);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
             // c0 is a multiple of 3: three columns per trip, all twelve loads issued before the FMAs
+            // (columns left of the envelope of the pivot rows hold exact zeros: skipped)
 #pragma unroll 2
-            for (int p = 0; p < c0; p += 3) {
+            for (int p = firstcol[c0 / 3]; p < c0; p += 3) {
                 const double la0 = rA[p], lb0 = rB[p], lc0 = rC[p];
                 const double la1 = rA[p + 1], lb1 = rB[p + 1], lc1 = rC[p + 1];
                 const double la2 = rA[p + 2], lb2 = rB[p + 2], lc2 = rC[p + 2];
@@ -394,7 +396,8 @@ struct Solver {
     // (EPS on the rays, DELTA on the weight) so that only clear certificates count; everything else goes
     // to solve().  On the bench rollouts this decides 96 % of the systems without equilibrium
     // (tools/solver_lab.py: an LP on the aggregated 3-row systems catches the same cases).
-    // Scratch: g, h, f (rays), invd (bodies of a contact), L (contact adjacency masks of the bodies).
+    // Scratch: g, h, f (rays), invd (bodies of a contact), L (contact adjacency masks of the bodies),
+    // typ (boundary contact list of the current set).
     __device__ bool screen(const double *body, double invL0) {
         constexpr double EPS = 1e-10, DELTA = 1e-5;
         if (nc > 64) return false;
@@ -463,53 +466,53 @@ struct Solver {
                 if (bw > 0.0) return true;        // nothing holds S
                 continue;
             }
-            const double bn2 = bw * bw + bt * bt;
-#pragma unroll 1
-            for (int half = 0; half < 2; half++) {
-                const unsigned mine = half ? (mp1 | mm1) : (mp0 | mm0);
-                if (mine == 0) continue;
-                bool found = false;
-                if ((mine >> lane) & 1u) {
-                    const int q = half * 32 + lane;
-                    const double ax = g[2 * q], az = g[2 * q + 1], at = f[2 * q];
-                    const double ex = h[2 * q], ez = h[2 * q + 1], et = f[2 * q + 1];
-                    // rotation about the contact point; translations perpendicular to the two edge rays
-                    const double n0x = az * et - at * ez, n0z = at * ex - ax * et, n0t = ax * ez - az * ex;
-                    const double n1x = az, n1z = -ax, n2x = ez, n2z = -ex;
-                    double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300, mn2 = 1e300, mx2 = -1e300;
-#pragma unroll 1
-                    for (int hk = 0; hk < 2; hk++) {
-                        const unsigned plus = hk ? mp1 : mp0;
-                        unsigned todo = plus | (hk ? mm1 : mm0);
-#pragma unroll 1
-                        while (todo) {
-                            const int kb = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const int k = hk * 32 + kb;
-                            const double sg = ((plus >> kb) & 1u) ? 1.0 : -1.0;
-                            const double rx = g[2 * k] * sg, rz = g[2 * k + 1] * sg, rt = f[2 * k] * sg;
-                            const double sx = h[2 * k] * sg, sz = h[2 * k + 1] * sg, st = f[2 * k + 1] * sg;
-                            const double d0 = n0x * rx + n0z * rz + n0t * rt, e0 = n0x * sx + n0z * sz + n0t * st;
-                            const double d1 = n1x * rx + n1z * rz, e1 = n1x * sx + n1z * sz;
-                            const double d2 = n2x * rx + n2z * rz, e2 = n2x * sx + n2z * sz;
-                            mn0 = fmin(mn0, fmin(d0, e0)); mx0 = fmax(mx0, fmax(d0, e0));
-                            mn1 = fmin(mn1, fmin(d1, e1)); mx1 = fmax(mx1, fmax(d1, e1));
-                            mn2 = fmin(mn2, fmin(d2, e2)); mx2 = fmax(mx2, fmax(d2, e2));
-                        }
-                    }
-                    // with l = |n|:  all sigma r . n >= -EPS l  and  n . b_S <= -DELTA l |b_S|   (or the mirror image)
-                    const double l0 = n0x * n0x + n0z * n0z + n0t * n0t, l1 = n1x * n1x + n1z * n1z, l2 = n2x * n2x + n2z * n2z;
-                    const double w0 = n0z * bw + n0t * bt, w1n = n1z * bw, w2n = n2z * bw;   // n . b_S, b_S = (0, bw, bt)
-                    const double E2 = EPS * EPS, D2 = DELTA * DELTA * bn2;
-                    if (l0 > 1e-18) found |= ((mn0 >= 0.0 || mn0 * mn0 <= E2 * l0) && w0 < 0.0 && w0 * w0 >= D2 * l0) ||
-                                             ((mx0 <= 0.0 || mx0 * mx0 <= E2 * l0) && w0 > 0.0 && w0 * w0 >= D2 * l0);
-                    if (l1 > 1e-18) found |= ((mn1 >= 0.0 || mn1 * mn1 <= E2 * l1) && w1n < 0.0 && w1n * w1n >= D2 * l1) ||
-                                             ((mx1 <= 0.0 || mx1 * mx1 <= E2 * l1) && w1n > 0.0 && w1n * w1n >= D2 * l1);
-                    if (l2 > 1e-18) found |= ((mn2 >= 0.0 || mn2 * mn2 <= E2 * l2) && w2n < 0.0 && w2n * w2n >= D2 * l2) ||
-                                             ((mx2 <= 0.0 || mx2 * mx2 <= E2 * l2) && w2n > 0.0 && w2n * w2n >= D2 * l2);
-                }
-                if (__any_sync(FULL, found)) return true;
+            // compact list of the boundary contacts (index | 0x80 when sigma = -1), at most 32 per set
+            const int nb0 = __popc(mp0 | mm0), nbd = nb0 + __popc(mp1 | mm1);
+            if (nbd > 32) continue;
+            {
+                const unsigned lt = (1u << lane) - 1;
+                if (((mp0 | mm0) >> lane) & 1u)
+                    typ[__popc((mp0 | mm0) & lt)] = (uint8_t)(lane | (((mm0 >> lane) & 1u) << 7));
+                if (((mp1 | mm1) >> lane) & 1u)
+                    typ[nb0 + __popc((mp1 | mm1) & lt)] = (uint8_t)((lane + 32) | (((mm1 >> lane) & 1u) << 7));
             }
+            __syncwarp();
+            const double bn2 = bw * bw + bt * bt;
+            bool found = false;
+            if (lane < nbd) {
+                const int q = typ[lane] & 0x7f;
+                const double ax = g[2 * q], az = g[2 * q + 1], at = f[2 * q];
+                const double ex = h[2 * q], ez = h[2 * q + 1], et = f[2 * q + 1];
+                // rotation about the contact point; translations perpendicular to the two edge rays
+                const double n0x = az * et - at * ez, n0z = at * ex - ax * et, n0t = ax * ez - az * ex;
+                const double n1x = az, n1z = -ax, n2x = ez, n2z = -ex;
+                double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300, mn2 = 1e300, mx2 = -1e300;
+#pragma unroll 1
+                for (int j = 0; j < nbd; j++) {
+                    const int e = typ[j];
+                    const int k = e & 0x7f;
+                    const double sg = (e & 0x80) ? -1.0 : 1.0;
+                    const double rx = g[2 * k] * sg, rz = g[2 * k + 1] * sg, rt = f[2 * k] * sg;
+                    const double sx = h[2 * k] * sg, sz = h[2 * k + 1] * sg, st = f[2 * k + 1] * sg;
+                    const double d0 = n0x * rx + n0z * rz + n0t * rt, e0 = n0x * sx + n0z * sz + n0t * st;
+                    const double d1 = n1x * rx + n1z * rz, e1 = n1x * sx + n1z * sz;
+                    const double d2 = n2x * rx + n2z * rz, e2 = n2x * sx + n2z * sz;
+                    mn0 = fmin(mn0, fmin(d0, e0)); mx0 = fmax(mx0, fmax(d0, e0));
+                    mn1 = fmin(mn1, fmin(d1, e1)); mx1 = fmax(mx1, fmax(d1, e1));
+                    mn2 = fmin(mn2, fmin(d2, e2)); mx2 = fmax(mx2, fmax(d2, e2));
+                }
+                // with l = |n|:  all sigma r . n >= -EPS l  and  n . b_S <= -DELTA l |b_S|   (or the mirror image)
+                const double l0 = n0x * n0x + n0z * n0z + n0t * n0t, l1 = n1x * n1x + n1z * n1z, l2 = n2x * n2x + n2z * n2z;
+                const double w0 = n0z * bw + n0t * bt, w1n = n1z * bw, w2n = n2z * bw;   // n . b_S, b_S = (0, bw, bt)
+                const double E2 = EPS * EPS, D2 = DELTA * DELTA * bn2;
+                if (l0 > 1e-18) found |= ((mn0 >= 0.0 || mn0 * mn0 <= E2 * l0) && w0 < 0.0 && w0 * w0 >= D2 * l0) ||
+                                         ((mx0 <= 0.0 || mx0 * mx0 <= E2 * l0) && w0 > 0.0 && w0 * w0 >= D2 * l0);
+                if (l1 > 1e-18) found |= ((mn1 >= 0.0 || mn1 * mn1 <= E2 * l1) && w1n < 0.0 && w1n * w1n >= D2 * l1) ||
+                                         ((mx1 <= 0.0 || mx1 * mx1 <= E2 * l1) && w1n > 0.0 && w1n * w1n >= D2 * l1);
+                if (l2 > 1e-18) found |= ((mn2 >= 0.0 || mn2 * mn2 <= E2 * l2) && w2n < 0.0 && w2n * w2n >= D2 * l2) ||
+                                         ((mx2 <= 0.0 || mx2 * mx2 <= E2 * l2) && w2n > 0.0 && w2n * w2n >= D2 * l2);
+            }
+            if (__any_sync(FULL, found)) return true;
         }
         return false;
     }
@@ -523,11 +526,22 @@ struct Solver {
         for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
 #pragma unroll 1
         for (int c = lane; c < nc; c += 32) typ[c] = 255;
+        // row envelope of H = A J A^T (and of its Cholesky factor, which only fills inside it): the rows of
+        // free block I start at the rows of the earliest free block it touches
+        if (lane < nfree) {
+            const int body = freebody[lane];
+            int first = 3 * lane;
+#pragma unroll 1
+            for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
+                const int e = adj[q];
+                const int other = (e >> 7) ? c_a[e & 0x7f] : c_b[e & 0x7f];
+                const int ro = rowbase[other];
+                if (ro >= 0 && ro < first) first = ro;
+            }
+            firstcol[lane] = (uint8_t)first;
+        }
         __syncwarp();
         flops = 0.0;
-#ifdef BW_PROFILE
-        for (int q = 0; q < 6; q++) acc_t[q] = 0;
-#endif
         double *rhs = L + tri(m);
         double rprev = -1.0, r = 1.0;
         int status = 2, iters = 0;

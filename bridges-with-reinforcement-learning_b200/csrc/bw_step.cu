@@ -66,7 +66,7 @@ struct Layout {
 };
 
 struct ProbOff {  // offsets inside one problem block
-    int y, yk, d, b, g, h, f, invd, H, typ, rowbase, freebody, size;
+    int y, yk, d, b, g, h, f, invd, H, typ, rowbase, freebody, firstcol, size;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -86,6 +86,7 @@ __host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
     o.typ = p; p += align16(MC);
     o.rowbase = p; p += align16(NBODY);
     o.freebody = p; p += align16(NB);
+    o.firstcol = p; p += align16(NB);
     o.size = align16(p);
     return o;
 }
@@ -188,6 +189,15 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #else
 #define BW_STAMP(i)
 #endif
+    __shared__ TaskDev sh_task;            // loaded here, long before the bookkeeping needs it
+    __shared__ uint8_t sh_occ[NB];
+    {
+        static_assert(sizeof(TaskDev) % 8 == 0 && NB % 4 == 0, "word-wise copies");
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(P.task + e);
+        if (tid < (int)(sizeof(TaskDev) / 8)) reinterpret_cast<uint64_t *>(&sh_task)[tid] = src[tid];
+        if (tid >= 32 && tid < 32 + NB / 4)
+            reinterpret_cast<uint32_t *>(sh_occ)[tid - 32] = reinterpret_cast<const uint32_t *>(P.face_occ + (size_t)e * NB)[tid - 32];
+    }
     const bw_action act = actions[e];
     const int n_old = P.n_blocks[e];
     const uint64_t old_bits = P.block_bits[(size_t)e * IMG + tid];   // image row tid, used after the placement
@@ -556,6 +566,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         S.typ = pb + po.typ;
         S.rowbase = reinterpret_cast<int8_t *>(pb + po.rowbase);
         S.freebody = pb + po.freebody;
+        S.firstcol = pb + po.firstcol;
         S.lane = lane;
         S.nc = nc;
         S.nitf = overflow ? 0 : nitf;
@@ -650,16 +661,9 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     // targets, block graph, state write; then thread 0 composes the step record.
     TaskDev *task = P.task + e;
     const int stable_frozen = sh_stable[0], stable_unfrozen = sh_stable[1];
-    __shared__ TaskDev sh_task;
-    if (tid == 0) sh_task = *task;
-    if (warp == 1) {
-        lin = warp_sum(lin);
-        if (lane == 0) sh_lin[1] = lin;
-    } else {
-        lin = warp_sum(lin);
-        if (lane == 0) sh_lin[0] = lin;
-    }
-    __syncthreads();
+    lin = warp_sum(lin);
+    if (lane == 0) sh_lin[warp] = lin;
+    // (thread 0 below only touches the remaining / reached lists of sh_task, warp 1 only reads the targets)
     if (warp == 1) {
         // distance_to_targets (gym_env.py:154-160, geometry.py:89-105): min over blocks of the
         // point-to-bounding-box distance
@@ -683,7 +687,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             if (lane == 0) sh_dist[t] = dist;
         }
     } else if (tid == 0 && placed) {
-        TaskDev tk = sh_task;
+        TaskDev &tk = sh_task;
         // _update_targets (gym_env.py:162-168): AABB test, removal while iterating
         const double *B = s_body + n * BODY_DOUBLES;
         const double tol = 1e-6;
@@ -707,10 +711,16 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         }
         // block_graph occupancy (gym_env.py:224-232)
         uint8_t *occ = P.face_occ + (size_t)e * NB;
-        if (act.target_block >= 0) occ[act.target_block] |= (uint8_t)(1u << act.target_face);
+        if (act.target_block >= 0) occ[act.target_block] = sh_occ[act.target_block] | (uint8_t)(1u << act.target_face);
         occ[n - 1] = (uint8_t)(1u << act.face);
-        *task = tk;
-        sh_task = tk;
+        // the mutable tail of the task record: remaining[], reached[], n_remaining, n_reached (+ padding)
+        static_assert(offsetof(TaskDev, remaining) % 8 == 0 && sizeof(TaskDev) - offsetof(TaskDev, remaining) == 16, "task tail");
+        {
+            const uint64_t *tail = reinterpret_cast<const uint64_t *>(&tk.remaining[0]);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(&task->remaining[0]);
+            dst[0] = tail[0];
+            dst[1] = tail[1];
+        }
         P.n_blocks[e] = n;
         P.pose[(size_t)e * NB + (n - 1)] = s_pose[n - 1];
         P.shape_of[(size_t)e * NB + (n - 1)] = s_shape[n - 1];
@@ -781,6 +791,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             float *dbg = block_img + (size_t)e * IMG * IMG;
             for (int q = 0; q < 6; q++) dbg[q] = (float)sh_prof_sub[1][q];
             for (int q = 0; q < 3; q++) dbg[8 + q] = 0.0f;
+            for (int q = 0; q < 6; q++) dbg[16 + q] = (float)sh_prof_sub[0][q];
+            dbg[22] = (float)sh_iters[0]; dbg[23] = (float)sh_iters[1];
         }
     }
 #endif

@@ -9,6 +9,7 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=10)
 env.reset(task_def(2))
 rows = []
+subs = []
 img = torch.zeros((E, 1, 64, 64), dtype=torch.float32, device='cuda')
 for i in range(60):
     env.enumerate_actions(X_GROUND, (0.0,), amax=128, with_bits=False)
@@ -17,6 +18,7 @@ for i in range(60):
     out = env.read_out()
     if i >= 15:
         rows.append(out.copy())
+        subs.append(img[:, 0, 0, :32].cpu().numpy().copy())
     env.reset_done()
 per_launch_max = [r["reward"].astype(np.float64).max() for r in rows]
 per_launch_mean = [r["reward"].astype(np.float64).mean() for r in rows]
@@ -40,3 +42,10 @@ for name, sel in (("stable&stable_u", (o["stable"] == 1) & (o["stable_unfrozen"]
     if sel.sum():
         print("%-18s n=%6d  w0 mean %8.0f p99 %8.0f | w1 mean %8.0f p99 %8.0f | iters mean %.1f" % (name, sel.sum(), w0[sel].mean(), np.percentile(w0[sel], 99),
               w1[sel].mean(), np.percentile(w1[sel], 99), o["newton_iters"][sel].mean()))
+
+sb = np.concatenate(subs)
+print("warp 0 sub-phases of the 12 slowest env-steps, cycles per Newton step (grad, assemble, factor+solve, A^T d + dots, line search, | screen total):")
+for k in order[:12]:
+    it0 = max(sb[k, 22], 1.0)
+    print("  nb %2d itf %2d it0 %3d it1 %3d | %s | screen %7.0f" % (o["n_blocks"][k], o["n_interfaces"][k], sb[k, 22], sb[k, 23],
+          " ".join("%7.0f" % (sb[k, 16 + q] / it0) for q in range(5)), sb[k, 21]))
