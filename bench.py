@@ -54,7 +54,8 @@ def _cpu_worker(job):
     env.step (placement, 2 interface rebuilds, 2 RBE solves) + stabilities_freezing (1 rebuild,
     3 solves) + get_state_features (1 raster).  Candidate generation for the random policy runs
     outside the timed sections."""
-    seed, budget_s, tower_height, max_steps, max_env_steps = job
+    seed, budget_s, tower_height, max_steps, max_env_steps = job[:5]
+    warm_env_steps, min_s = (job[5], job[6]) if len(job) > 5 else (0, 0.0)
     import numpy as np
     from oracle import actions as oact
     from oracle import features as ofeat
@@ -67,13 +68,18 @@ def _cpu_worker(job):
     env = AssemblyGym(shapes=[Shape(urdf_file="shapes/trapezoid.urdf", name="trapezoid")], obstacles=t["obstacles"],
                       targets=t["targets"], reward_fct=sparse_reward, restrict_2d=True, max_steps=max_steps,
                       assembly_env=AssemblyEnv())
-    steps, timed = 0, 0.0
-    t_end = time.perf_counter() + budget_s
-    while time.perf_counter() < t_end and steps < max_env_steps:
+    steps, timed, warm = 0, 0.0, 0
+    t_begin = time.perf_counter()
+    t_end = t_begin + budget_s
+
+    def more():
+        now = time.perf_counter()
+        return now < t_end and (steps < max_env_steps or now - t_begin < min_s)
+    while more():
         obs, _ = env.reset()
         obstacle_f = render_blocks_2d(obs['obstacle_blocks'], xlim, ylim, img).astype(np.float32)[None]
         done = False
-        while not done and time.perf_counter() < t_end and steps < max_env_steps:
+        while not done and more():
             block_f, _ = ofeat.get_state_features(obs, xlim, ylim, img)
             cands = [*oact.generate_actions(env, X_GROUND, [0.0])]
             cand_f = ofeat.get_action_features(env, cands, xlim, ylim, img)
@@ -85,15 +91,20 @@ def _cpu_worker(job):
             obs, reward, terminated, truncated, _ = env.step(action)
             env.stabilities_freezing()
             ofeat.get_state_features(obs, xlim, ylim, img)
-            timed += time.perf_counter() - t0
-            steps += 1
+            if warm < warm_env_steps:          # untimed warm-up (first HiGHS / numpy calls of the process)
+                warm += 1
+            else:
+                timed += time.perf_counter() - t0
+                steps += 1
             done = bool(terminated or truncated)
     return steps, timed
 
 
-def cpu_env_rate(cores, budget_s, tower_height, max_steps, max_env_steps=10 ** 9):
-    """Aggregate env steps/s of `cores` independent oracle envs."""
-    jobs = [(1000 + i, budget_s, tower_height, max_steps, max_env_steps) for i in range(cores)]
+def cpu_env_rate(cores, budget_s, tower_height, max_steps, max_env_steps=10 ** 9, warm_env_steps=4, min_s=0.0):
+    """Aggregate env steps/s of `cores` independent oracle envs (the first `warm_env_steps` env steps of every
+    worker are neither counted nor timed; a worker runs until it has done `max_env_steps` AND `min_s` seconds,
+    at most `budget_s`)."""
+    jobs = [(1000 + i, budget_s, tower_height, max_steps, max_env_steps, warm_env_steps, min_s) for i in range(cores)]
     if cores == 1:
         results = [_cpu_worker(jobs[0])]
     else:
@@ -108,13 +119,14 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = args.cpu_cores or os.cpu_count() or 1
-    # one "step" of this arm = a bounded sample: every worker advances ~4 env steps
+    # one "step" of this arm = a bounded sample: every worker advances 4 env steps; W warm-up steps per worker
+    # are untimed, and the timed sample lasts at least 8 s (a shorter one measures process start-up, not the env)
     per_step = 4 * cores
-    total_env_steps = per_step * (args.steps + args.warmup)
-    budget = min(150.0, max(10.0, 0.05 * total_env_steps))
+    total_env_steps = per_step * args.steps
     t0 = time.perf_counter()
-    rate, steps = cpu_env_rate(cores, budget, args.tower_height, args.max_steps,
-                               max_env_steps=max(8, total_env_steps // cores))
+    rate, steps = cpu_env_rate(cores, 150.0, args.tower_height, args.max_steps,
+                               max_env_steps=max(8, total_env_steps // cores),
+                               warm_env_steps=min(64, 4 * max(1, args.warmup)), min_s=8.0)
     wall = time.perf_counter() - t0
     k_done = max(1, min(args.steps, steps // per_step))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": k_done,
