@@ -164,40 +164,49 @@ struct Solver {
         return acc;
     }
 
+    // generalised Jacobian of the cone projection of a contact point from its face type, without branches:
+    // J = alpha I + beta (1, s)(1, s)^T  with alpha = 1 in the interior, beta = 1/(1+mu^2), s = +-mu on the
+    // two rays, J = 0 in the polar cone.  (jnn, jnt, jtt) = (J00, J01, J11).
+    __device__ __forceinline__ void jac(int tp, double mu2, double &jnn, double &jnt, double &jtt) const {
+        const double alpha = (tp == 1) ? 1.0 : 0.0;
+        const double beta = (tp >= 2) ? inv_den : 0.0;
+        const double sb = (tp == 3) ? -beta : beta;
+        jnn = alpha + beta;
+        jnt = mu * sb;
+        jtt = fma(mu2, beta, alpha);
+    }
+
     // H = A J A^T + I/rho into rows 0..m-1 of L.  Diagonal 3x3 tiles gather over the contacts of
     // their block (lanes over free blocks); an off-diagonal tile belongs to exactly one interface
     // (two contact points), so lanes over interfaces write it without accumulation conflicts.
+    // Every contact point runs the same instruction sequence whatever its cone face (the three faces of
+    // a warp's contact points used to serialise three code paths).
     __device__ void assemble_H(double inv_rho) {
         const int nz = tri(m);
 #pragma unroll 1
         for (int q = lane; q < nz; q += 32) L[q] = 0.0;
         __syncwarp();
-        const double isd = sqrt(inv_den);
+        const double mu2 = mu * mu;
         // diagonal tiles: three lanes per free block, lane (I, r) accumulates row r of the lower tile
 #pragma unroll 1
         for (int q = lane; q < m; q += 32) {
             const int I = q / 3, r = q - 3 * I;
             const int body = freebody[I];
             double e0 = 0.0, e1 = 0.0, e2 = 0.0;         // entries (r, 0..r)
+            const int a1 = adj_ptr[body + 1];
 #pragma unroll 2
-            for (int a = adj_ptr[body]; a < adj_ptr[body + 1]; a++) {
+            for (int a = adj_ptr[body]; a < a1; a++) {
                 const int e = adj[a];
                 const int c = e & 0x7f;
-                const int tp = typ[c];
-                if (tp == 0) continue;
                 const double *Gi = G + c * 12 + (e >> 7) * 6;
-                if (tp == 1) {
-                    const double ur = Gi[r], vr = Gi[3 + r];
-                    e0 += ur * Gi[0] + vr * Gi[3];
-                    e1 += ur * Gi[1] + vr * Gi[4];
-                    e2 += ur * Gi[2] + vr * Gi[5];
-                } else {
-                    const double sm = (tp == 2 ? mu : -mu);
-                    const double ur = (Gi[r] + sm * Gi[3 + r]) * inv_den;     // isd^2 = 1/(1+mu^2)
-                    e0 += ur * (Gi[0] + sm * Gi[3]);
-                    e1 += ur * (Gi[1] + sm * Gi[4]);
-                    e2 += ur * (Gi[2] + sm * Gi[5]);
-                }
+                const double n0 = Gi[0], n1 = Gi[1], n2 = Gi[2], t0 = Gi[3], t1 = Gi[4], t2 = Gi[5];
+                const double nr = Gi[r], tr = Gi[3 + r];
+                double jnn, jnt, jtt;
+                jac(typ[c], mu2, jnn, jnt, jtt);
+                const double ur = fma(nr, jnn, tr * jnt), vr = fma(nr, jnt, tr * jtt);   // row r of G_i^T J
+                e0 = fma(ur, n0, fma(vr, t0, e0));
+                e1 = fma(ur, n1, fma(vr, t1, e1));
+                e2 = fma(ur, n2, fma(vr, t2, e2));
             }
             double *p = L + tri(q) + 3 * I;
             p[0] = e0 + (r == 0 ? inv_rho : 0.0);
@@ -213,24 +222,18 @@ struct Solver {
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int c = c0 + q;
-                const int tp = typ[c];
-                if (tp == 0) continue;
                 const double *Ga = G + c * 12, *Gb = Ga + 6;
-                double u0, u1, u2, w0, w1, w2;
-                if (tp == 1) {
-                    u0 = Gb[3]; u1 = Gb[4]; u2 = Gb[5]; w0 = Ga[3]; w1 = Ga[4]; w2 = Ga[5];
-                    t00 += u0 * w0; t01 += u0 * w1; t02 += u0 * w2;
-                    t10 += u1 * w0; t11 += u1 * w1; t12 += u1 * w2;
-                    t20 += u2 * w0; t21 += u2 * w1; t22 += u2 * w2;
-                    u0 = Gb[0]; u1 = Gb[1]; u2 = Gb[2]; w0 = Ga[0]; w1 = Ga[1]; w2 = Ga[2];
-                } else {
-                    const double sm = (tp == 2 ? mu : -mu);
-                    u0 = (Gb[0] + sm * Gb[3]) * isd; u1 = (Gb[1] + sm * Gb[4]) * isd; u2 = (Gb[2] + sm * Gb[5]) * isd;
-                    w0 = (Ga[0] + sm * Ga[3]) * isd; w1 = (Ga[1] + sm * Ga[4]) * isd; w2 = (Ga[2] + sm * Ga[5]) * isd;
-                }
-                t00 += u0 * w0; t01 += u0 * w1; t02 += u0 * w2;
-                t10 += u1 * w0; t11 += u1 * w1; t12 += u1 * w2;
-                t20 += u2 * w0; t21 += u2 * w1; t22 += u2 * w2;
+                double jnn, jnt, jtt;
+                jac(typ[c], mu2, jnn, jnt, jtt);
+                // W = J [Ga_n; Ga_t]  (2 x 3), tile += Gb_n^T W_n + Gb_t^T W_t
+                const double wn0 = fma(jnn, Ga[0], jnt * Ga[3]), wn1 = fma(jnn, Ga[1], jnt * Ga[4]),
+                             wn2 = fma(jnn, Ga[2], jnt * Ga[5]);
+                const double wt0 = fma(jnt, Ga[0], jtt * Ga[3]), wt1 = fma(jnt, Ga[1], jtt * Ga[4]),
+                             wt2 = fma(jnt, Ga[2], jtt * Ga[5]);
+                const double u0 = Gb[0], u1 = Gb[1], u2 = Gb[2], v0 = Gb[3], v1 = Gb[4], v2 = Gb[5];
+                t00 = fma(u0, wn0, fma(v0, wt0, t00)); t01 = fma(u0, wn1, fma(v0, wt1, t01)); t02 = fma(u0, wn2, fma(v0, wt2, t02));
+                t10 = fma(u1, wn0, fma(v1, wt0, t10)); t11 = fma(u1, wn1, fma(v1, wt1, t11)); t12 = fma(u1, wn2, fma(v1, wt2, t12));
+                t20 = fma(u2, wn0, fma(v2, wt0, t20)); t21 = fma(u2, wn1, fma(v2, wt1, t21)); t22 = fma(u2, wn2, fma(v2, wt2, t22));
             }
             double *p = L + tri(rb) + ra;          // rb > ra: rows of the later block
             p[0] = t00; p[1] = t01; p[2] = t02;
