@@ -64,16 +64,16 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
 // typ: 0 = polar cone (f = 0), 1 = interior, 2 = ray ft = +mu fn, 3 = ray ft = -mu fn
 __device__ __forceinline__ void project_cone(double gn, double gt, double mu, double inv_den, double &fn, double &ft,
                                              int &typ) {
+    // written with selects: the contact points of a warp sit on different faces, and three serialised
+    // code paths cost more than the few redundant operations
     const double agt = fabs(gt);
-    if (agt <= mu * gn) {
-        fn = gn; ft = gt; typ = 1;
-    } else if (mu * agt <= -gn) {
-        fn = 0.0; ft = 0.0; typ = 0;
-    } else {
-        const double k = (gn + mu * agt) * inv_den;
-        fn = k;
-        if (gt > 0) { ft = mu * k; typ = 2; } else { ft = -mu * k; typ = 3; }
-    }
+    const bool inter = agt <= mu * gn;
+    const bool polar = mu * agt <= -gn;
+    const double k = (gn + mu * agt) * inv_den;
+    const double kt = (gt > 0) ? mu * k : -(mu * k);
+    fn = inter ? gn : (polar ? 0.0 : k);
+    ft = inter ? gt : (polar ? 0.0 : kt);
+    typ = inter ? 1 : (polar ? 0 : (gt > 0 ? 2 : 3));
 }
 
 // TWO = false: at most 31 rows (10 free blocks + the right-hand side), one row per lane;
@@ -290,17 +290,24 @@ struct Solver {
             const double d20 = __shfl_sync(FULL, (!TWO || rc < 32) ? t0 : u0, rc & 31);
             const double d21 = __shfl_sync(FULL, (!TWO || rc < 32) ? t1 : u1, rc & 31);
             const double d22 = __shfl_sync(FULL, (!TWO || rc < 32) ? t2 : u2, rc & 31);
-            double piv = d00;
-            if (!(piv > 1e-300)) piv = inv_rho;
-            const double i00 = fast_rsqrt(piv);
+            // 3x3 Cholesky of the diagonal block through its leading minors: with s11, s22 the Schur
+            // complements, M2 = d00 s11 and T = d00 M2 s22 need no earlier square root, so the three
+            // rsqrt chains run side by side instead of one after the other
+            //   1/sqrt(s11) = rsqrt(M2) sqrt(d00),   1/sqrt(s22) = rsqrt(T) sqrt(d00) sqrt(M2)
+            double p0 = d00;
+            if (!(p0 > 1e-300)) p0 = inv_rho;
+            const double i00 = fast_rsqrt(p0);
+            double M2 = fma(d11, p0, -(d10 * d10));
+            if (!(M2 > 1e-300 * p0)) M2 = inv_rho * p0;
+            const double c21 = fma(d21, p0, -(d20 * d10));            // d00 (d21 - l20 l10)
+            double T = fma(fma(p0, d22, -(d20 * d20)), M2, -(c21 * c21));   // d00 M2 s22
+            if (!(T > 1e-300 * (p0 * M2))) T = inv_rho * (p0 * M2);
+            const double rM2 = fast_rsqrt(M2), rT = fast_rsqrt(T);
+            const double sp0 = p0 * i00, sM2 = M2 * rM2;               // sqrt(d00), sqrt(M2)
+            const double i11 = rM2 * sp0;
+            const double i22 = rT * (sp0 * sM2);
             const double l10 = d10 * i00, l20 = d20 * i00;
-            piv = d11 - l10 * l10;
-            if (!(piv > 1e-300)) piv = inv_rho;
-            const double i11 = fast_rsqrt(piv);
             const double l21 = (d21 - l20 * l10) * i11;
-            piv = d22 - l20 * l20 - l21 * l21;
-            if (!(piv > 1e-300)) piv = inv_rho;
-            const double i22 = fast_rsqrt(piv);
             // x L_d^T = t for this lane's row(s)
             {
                 const double x0 = t0 * i00;
