@@ -104,6 +104,7 @@ struct Solver {
 #ifdef BW_PROFILE
     long long acc_t[6];      // grad, assemble, factor+solve, A^T d + dots, line search + update, residual
     long long t_screen;      // mechanism screen
+    long long acc_f[3];      // factor_and_solve: dot loops, pivot blocks + stores, back substitution
 #define BW_T0(name) const long long name = clock64()
 #define BW_ACC(i, t0) acc_t[i] += clock64() - (t0)
 #else
@@ -260,6 +261,7 @@ struct Solver {
         for (int c0 = 0; c0 < m; c0 += 3) {
             const double *rA = L + tri(c0), *rB = L + tri(c0 + 1), *rC = L + tri(c0 + 2);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+            BW_T0(t_f0);
             // c0 is a multiple of 3: three columns per trip, all twelve loads issued before the FMAs
             // (columns left of the envelope of the pivot rows hold exact zeros: skipped)
 #pragma unroll 2
@@ -280,6 +282,10 @@ struct Solver {
             }
             // t = H[i][c0..c0+2] - partial dots (entries right of the diagonal are never used)
             const double t0 = row0[c0] - a0, t1 = row0[c0 + 1] - a1, t2 = row0[c0 + 2] - a2;
+#ifdef BW_PROFILE
+            acc_f[0] += clock64() - t_f0;
+            const long long t_f1 = clock64();
+#endif
             double u0 = 0.0, u1 = 0.0, u2 = 0.0;
             if (TWO) { u0 = row1[c0] - b0; u1 = row1[c0 + 1] - b1; u2 = row1[c0 + 2] - b2; }
             // the diagonal block: rows c0, c0+1, c0+2
@@ -308,14 +314,19 @@ struct Solver {
             const double i22 = rT * (sp0 * sM2);
             const double l10 = d10 * i00, l20 = d20 * i00;
             const double l21 = (d21 - l20 * l10) * i11;
+            // the strictly lower entries of the INVERSE of the diagonal block take the place of l10, l20, l21
+            // (nothing reads those again but the back substitution, which then needs no triangular solve)
+            const double m10 = -(l10 * i00) * i11;
+            const double m21 = -(l21 * i11) * i22;
+            const double m20 = -fma(l21, m10, l20 * i00) * i22;
             // x L_d^T = t for this lane's row(s)
             {
                 const double x0 = t0 * i00;
                 const double x1 = (t1 - x0 * l10) * i11;
                 const double x2 = (t2 - x0 * l20 - x1 * l21) * i22;
                 if (i0 < nrows) {
-                    if (i0 > ra) row0[ra] = x0;
-                    if (i0 > rb) row0[rb] = x1;
+                    if (i0 > ra) row0[ra] = (i0 == rb) ? m10 : (i0 == rc ? m20 : x0);
+                    if (i0 > rb) row0[rb] = (i0 == rc) ? m21 : x1;
                     if (i0 > rc) row0[rc] = x2;
                 }
             }
@@ -323,14 +334,20 @@ struct Solver {
                 const double x0 = u0 * i00;
                 const double x1 = (u1 - x0 * l10) * i11;
                 const double x2 = (u2 - x0 * l20 - x1 * l21) * i22;
-                if (i1 > ra) row1[ra] = x0;
-                if (i1 > rb) row1[rb] = x1;
+                if (i1 > ra) row1[ra] = (i1 == rb) ? m10 : (i1 == rc ? m20 : x0);
+                if (i1 > rb) row1[rb] = (i1 == rc) ? m21 : x1;
                 if (i1 > rc) row1[rc] = x2;
             }
             if (lane == 0) { invd[ra] = i00; invd[rb] = i11; invd[rc] = i22; }
             __syncwarp();
+#ifdef BW_PROFILE
+            acc_f[1] += clock64() - t_f1;
+#endif
         }
-        // row m now holds z = L^-1 grad; back substitution L^T d = z, one 3x3 block per trip
+        BW_T0(t_f2);
+        // row m now holds z = L^-1 grad; back substitution L^T d = z, one 3x3 block per trip: the block's
+        // three unknowns are three short dot products with the stored inverse of the diagonal block, every
+        // lane runs the same instructions (results picked by selects) and its loads do not wait for the chain
         const double *rowm = L + tri(m);
         double z0 = (i0 < m) ? rowm[i0] : 0.0;
         double z1 = (TWO && i1 < m) ? rowm[i1] : 0.0;
@@ -338,28 +355,33 @@ struct Solver {
         for (int c0 = m - 3; c0 >= 0; c0 -= 3) {
             const int ra = c0, rb = c0 + 1, rc = c0 + 2;
             const double *rA = L + tri(ra), *rB = L + tri(rb), *rC = L + tri(rc);
+            const int k0 = (i0 < ra) ? i0 : 0;
+            const double la = rA[k0], lb = rB[k0], lc = rC[k0];
+            const double m10 = rB[ra], m20 = rC[ra], m21 = rC[rb];
+            const double i00 = invd[ra], i11 = invd[rb], i22 = invd[rc];
             const double za = __shfl_sync(FULL, (!TWO || ra < 32) ? z0 : z1, ra & 31);
             const double zb = __shfl_sync(FULL, (!TWO || rb < 32) ? z0 : z1, rb & 31);
             const double zc = __shfl_sync(FULL, (!TWO || rc < 32) ? z0 : z1, rc & 31);
-            const double l10 = rB[ra], l20 = rC[ra], l21 = rC[rb];
-            // L_d^T (da, db, dc) = (za, zb, zc)
-            const double dc = zc * invd[rc];
-            const double db = (zb - l21 * dc) * invd[rb];
-            const double da = (za - l10 * db - l20 * dc) * invd[ra];
-            if (i0 == ra) z0 = da;
-            else if (i0 == rb) z0 = db;
-            else if (i0 == rc) z0 = dc;
-            else if (i0 < ra) z0 -= rA[i0] * da + rB[i0] * db + rC[i0] * dc;
+            // (da, db, dc) = L_d^-T (za, zb, zc)
+            const double dc = i22 * zc;
+            const double db = fma(m21, zc, i11 * zb);
+            const double da = fma(m20, zc, fma(m10, zb, i00 * za));
+            {
+                const double upd = fma(-la, da, fma(-lb, db, fma(-lc, dc, z0)));
+                z0 = (i0 < ra) ? upd : (i0 == ra ? da : (i0 == rb ? db : (i0 == rc ? dc : z0)));
+            }
             if (TWO) {
-                if (i1 == ra) z1 = da;
-                else if (i1 == rb) z1 = db;
-                else if (i1 == rc) z1 = dc;
-                else if (i1 < ra) z1 -= rA[i1] * da + rB[i1] * db + rC[i1] * dc;
+                const int k1 = (i1 < ra) ? i1 : 0;
+                const double upd = fma(-rA[k1], da, fma(-rB[k1], db, fma(-rC[k1], dc, z1)));
+                z1 = (i1 < ra) ? upd : (i1 == ra ? da : (i1 == rb ? db : (i1 == rc ? dc : z1)));
             }
         }
         if (i0 < m) d[i0] = z0;
         if (TWO && i1 < m) d[i1] = z1;
         __syncwarp();
+#ifdef BW_PROFILE
+        acc_f[2] += clock64() - t_f2;
+#endif
     }
 
     // ||b - A P_K(A^T y)|| (b is normalised); leaves g = A^T y, f = P_K(g)

@@ -174,6 +174,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #ifdef BW_PROFILE
     __shared__ long long sh_prof_solve[2];
     __shared__ long long sh_prof_sub[2][6];
+    __shared__ long long sh_prof_f[3];
 #endif
     __shared__ double sh_lin[2];
     __shared__ uint64_t sh_bits[IMG];      // raster of all blocks after this step
@@ -613,6 +614,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             bool certified = false;
 #ifdef BW_PROFILE
             for (int q = 0; q < 6; q++) S.acc_t[q] = 0;
+            for (int q = 0; q < 3; q++) S.acc_f[q] = 0;
             S.t_screen = 0;
 #endif
             if (!want_forces && P.screen != 0) {
@@ -639,6 +641,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             const bool ran = (nitf > 0 && nfree > 0 && !overflow) && !(warp == 0 && status == 4);
             for (int q = 0; q < 5; q++) sh_prof_sub[warp][q] = ran ? S.acc_t[q] : 0;
             sh_prof_sub[warp][5] = ran ? S.t_screen : 0;
+            if (warp == 0) for (int q = 0; q < 3; q++) sh_prof_f[q] = ran ? S.acc_f[q] : 0;
         }
 #endif
         if (lane == 0) {
@@ -793,6 +796,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             for (int q = 0; q < 3; q++) dbg[8 + q] = 0.0f;
             for (int q = 0; q < 6; q++) dbg[16 + q] = (float)sh_prof_sub[0][q];
             dbg[22] = (float)sh_iters[0]; dbg[23] = (float)sh_iters[1];
+            for (int q = 0; q < 3; q++) dbg[24 + q] = (float)sh_prof_f[q];
         }
     }
 #endif

@@ -48,4 +48,5 @@ print("warp 0 sub-phases of the 12 slowest env-steps, cycles per Newton step (gr
 for k in order[:12]:
     it0 = max(sb[k, 22], 1.0)
     print("  nb %2d itf %2d it0 %3d it1 %3d | %s | screen %7.0f" % (o["n_blocks"][k], o["n_interfaces"][k], sb[k, 22], sb[k, 23],
-          " ".join("%7.0f" % (sb[k, 16 + q] / it0) for q in range(5)), sb[k, 21]))
+          " ".join("%7.0f" % (sb[k, 16 + q] / it0) for q in range(5)), sb[k, 21]) +
+          " | factor: dots %6.0f pivots %6.0f backsub %6.0f" % tuple(sb[k, 24 + q] / it0 for q in range(3)))
