@@ -44,6 +44,15 @@ __device__ __forceinline__ void warp_sum3(double &a, double &b, double &c) {
         c += __shfl_xor_sync(FULL, c, o);
     }
 }
+__device__ __forceinline__ void warp_sum4(double &a, double &b, double &c, double &d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+        c += __shfl_xor_sync(FULL, c, o);
+        d += __shfl_xor_sync(FULL, d, o);
+    }
+}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
@@ -177,23 +186,25 @@ struct Solver {
         jtt = fma(mu2, beta, alpha);
     }
 
-    // H = A J A^T + I/rho into rows 0..m-1 of L.  Diagonal 3x3 tiles gather over the contacts of
-    // their block (lanes over free blocks); an off-diagonal tile belongs to exactly one interface
-    // (two contact points), so lanes over interfaces write it without accumulation conflicts.
-    // Every contact point runs the same instruction sequence whatever its cone face (the three faces of
-    // a warp's contact points used to serialise three code paths).
-    __device__ void assemble_H(double inv_rho) {
+    // One pass over the rows (lane = row, three lanes per free block) walks the contact list of the row's
+    // block once for two results: the gradient of the proximal sub-problem  b - A f - (y - y_k)/rho  with the
+    // equilibrium residual b - A f, and row r of the block's diagonal 3x3 tile of H = A J A^T + I/rho.
+    // Every contact point runs the same instruction sequence whatever its cone face (the three faces of a
+    // warp's contact points used to serialise three code paths).  Writes d = rhs row = gradient, zero-fills
+    // rows 0..m-1 of L first; returns the partial sums of |grad|^2 and |b - A f|^2.
+    __device__ __forceinline__ void rows_pass(double inv_rho, double *rhs, double &gn2, double &rr2) {
         const int nz = tri(m);
 #pragma unroll 1
         for (int q = lane; q < nz; q += 32) L[q] = 0.0;
         __syncwarp();
         const double mu2 = mu * mu;
-        // diagonal tiles: three lanes per free block, lane (I, r) accumulates row r of the lower tile
+        gn2 = 0.0; rr2 = 0.0;
 #pragma unroll 1
         for (int q = lane; q < m; q += 32) {
             const int I = q / 3, r = q - 3 * I;
             const int body = freebody[I];
-            double e0 = 0.0, e1 = 0.0, e2 = 0.0;         // entries (r, 0..r)
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0;         // entries (r, 0..r) of the tile
+            double acc = 0.0;                            // (A f)_q
             const int a1 = adj_ptr[body + 1];
 #pragma unroll 2
             for (int a = adj_ptr[body]; a < a1; a++) {
@@ -202,6 +213,7 @@ struct Solver {
                 const double *Gi = G + c * 12 + (e >> 7) * 6;
                 const double n0 = Gi[0], n1 = Gi[1], n2 = Gi[2], t0 = Gi[3], t1 = Gi[4], t2 = Gi[5];
                 const double nr = Gi[r], tr = Gi[3 + r];
+                acc += nr * f[2 * c] + tr * f[2 * c + 1];
                 double jnn, jnt, jtt;
                 jac(typ[c], mu2, jnn, jnt, jtt);
                 const double ur = fma(nr, jnn, tr * jnt), vr = fma(nr, jnt, tr * jtt);   // row r of G_i^T J
@@ -209,11 +221,25 @@ struct Solver {
                 e1 = fma(ur, n1, fma(vr, t1, e1));
                 e2 = fma(ur, n2, fma(vr, t2, e2));
             }
+            const double px = (y[q] - yk[q]) * inv_rho;
+            const double rs = b[q] - acc;
+            const double gr = rs - px;
+            d[q] = gr;                                   // kept for the dot products after the solve
+            rhs[q] = gr;
+            gn2 += gr * gr;
+            rr2 += rs * rs;
             double *p = L + tri(q) + 3 * I;
             p[0] = e0 + (r == 0 ? inv_rho : 0.0);
             if (r >= 1) p[1] = e1 + (r == 1 ? inv_rho : 0.0);
             if (r == 2) p[2] = e2 + inv_rho;
         }
+        warp_sum2(gn2, rr2);
+    }
+
+    // Off-diagonal 3x3 tiles of H: a tile belongs to exactly one interface (two contact points), so lanes
+    // over interfaces write it without accumulation conflicts.
+    __device__ __forceinline__ void offdiag_tiles() {
+        const double mu2 = mu * mu;
 #pragma unroll 1
         for (int k = lane; k < nitf; k += 32) {
             const int c0 = 2 * k;
@@ -573,6 +599,8 @@ struct Solver {
             firstcol[lane] = (uint8_t)first;
         }
         __syncwarp();
+        project_all();                         // f, cone faces of g = 0; kept up to date by every step below
+        __syncwarp();
         flops = 0.0;
         double *rhs = L + tri(m);
         double rprev = -1.0, r = 1.0;
@@ -585,24 +613,13 @@ struct Solver {
             __syncwarp();
             bool have_r = false;
             bool full_step = false;            // the previous Newton step of this stage was taken with t = 1
+            bool changed = true;               // a contact changed its cone face in that step
 #pragma unroll 1
             for (int it = 0; it < MAX_NEWTON; it++) {
                 if (implied_by >= 0 && *sibling == implied_by) { status = 3; break; }
                 BW_T0(t_a);
-                const bool changed = project_all();
-                __syncwarp();
-                // gradient of the proximal sub-problem and, for free, the equilibrium residual b - A f
-                double gn2 = 0.0, rr2 = 0.0;
-#pragma unroll 1
-                for (int i = lane; i < m; i += 32) {
-                    const double px = (y[i] - yk[i]) * inv_rho;
-                    const double rs = b[i] - a_times_f_row(i);
-                    const double gr = rs - px;
-                    d[i] = gr;                     // kept for the dot products below
-                    gn2 += gr * gr;
-                    rr2 += rs * rs;
-                }
-                warp_sum2(gn2, rr2);
+                double gn2, rr2;
+                rows_pass(inv_rho, rhs, gn2, rr2);
                 BW_ACC(0, t_a);
                 // f is in K, so ||b - A f|| bounds r* from above at every iterate.  A full Newton step that
                 // leaves every contact on its cone face has solved the (then quadratic) sub-problem exactly:
@@ -614,9 +631,7 @@ struct Solver {
                     break;
                 }
                 BW_T0(t_b);
-                assemble_H(inv_rho);               // zero-fills rows 0..m-1, leaves row m alone
-#pragma unroll 1
-                for (int i = lane; i < m; i += 32) rhs[i] = d[i];
+                offdiag_tiles();
                 double gd = 0.0;
                 // keep the gradient in registers: d[] is overwritten by the solve
                 const double gr0 = (lane < m) ? d[lane] : 0.0;
@@ -627,10 +642,9 @@ struct Solver {
                 factor_and_solve(inv_rho);
                 BW_ACC(2, t_c);
                 BW_T0(t_d);
-                at_times(d, h);
-                __syncwarp();
-                // phi'(t) = grad.d + f.h - P_K(g + t h).h - t d.d / rho   (piecewise linear, decreasing)
-                double dd = 0.0, fh0 = 0.0;
+                // phi'(t) = grad.d + f.h - P_K(g + t h).h - t d.d / rho   (piecewise linear, decreasing).
+                // One pass over the contact points gives h = A^T d, f.h and the first evaluation P_K(g + h).h
+                double dd = 0.0, fh0 = 0.0, fh1 = 0.0;
                 {
                     const double d0 = (lane < m) ? d[lane] : 0.0;
                     gd = gr0 * d0;
@@ -641,16 +655,38 @@ struct Solver {
                         dd += d1 * d1;
                     }
 #pragma unroll 1
-                    for (int c = lane; c < 2 * nc; c += 32) fh0 += f[c] * h[c];
+                    for (int c = lane; c < nc; c += 32) {
+                        const double *Gc = G + c * 12;
+                        const int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
+                        double hn = 0.0, ht = 0.0;
+                        if (ra >= 0) {
+                            const double v0 = d[ra], v1 = d[ra + 1], v2 = d[ra + 2];
+                            hn = Gc[0] * v0 + Gc[1] * v1 + Gc[2] * v2;
+                            ht = Gc[3] * v0 + Gc[4] * v1 + Gc[5] * v2;
+                        }
+                        if (rb >= 0) {
+                            const double v0 = d[rb], v1 = d[rb + 1], v2 = d[rb + 2];
+                            hn += Gc[6] * v0 + Gc[7] * v1 + Gc[8] * v2;
+                            ht += Gc[9] * v0 + Gc[10] * v1 + Gc[11] * v2;
+                        }
+                        h[2 * c] = hn;
+                        h[2 * c + 1] = ht;
+                        fh0 += f[2 * c] * hn + f[2 * c + 1] * ht;
+                        double fn, ft;
+                        int tp;
+                        project_cone(g[2 * c] + hn, g[2 * c + 1] + ht, mu, inv_den, fn, ft, tp);
+                        fh1 += fn * hn + ft * ht;
+                    }
+                    flops += 20.0 * nc;
                 }
-                warp_sum3(gd, dd, fh0);
+                warp_sum4(gd, dd, fh0, fh1);
                 BW_ACC(3, t_d);
                 BW_T0(t_e);
                 const double phi0 = gd;
                 if (!(phi0 > 1e-30)) break;
                 const double base = phi0 + fh0;
                 double t = 1.0;
-                double p = base - fdoth(1.0) - dd * inv_rho;
+                double p = base - fh1 - dd * inv_rho;
                 // the full step is kept whenever it satisfies the search's own acceptance test
                 // |phi'(1)| <= 0.1 phi'(0): on a piece without a change of cone face phi'(1) is rounding noise
                 // of either sign (it grows with |y|), and a search started by that noise ends at t = 0.9 --
@@ -676,8 +712,24 @@ struct Solver {
                     y[i] = yn;
                     yy = fmax(yy, fabs(yn));
                 }
+                // g = A^T (y + t d) and its projection f, cone faces for the next gradient pass
+                {
+                    bool ch = false;
 #pragma unroll 1
-                for (int c = lane; c < 2 * nc; c += 32) g[c] += t * h[c];   // A^T (y + t d)
+                    for (int c = lane; c < nc; c += 32) {
+                        const double gn = g[2 * c] + t * h[2 * c], gt = g[2 * c + 1] + t * h[2 * c + 1];
+                        g[2 * c] = gn;
+                        g[2 * c + 1] = gt;
+                        double fn, ft;
+                        int tp;
+                        project_cone(gn, gt, mu, inv_den, fn, ft, tp);
+                        f[2 * c] = fn;
+                        f[2 * c + 1] = ft;
+                        ch |= (tp != (int)typ[c]);
+                        typ[c] = (uint8_t)tp;
+                    }
+                    changed = __any_sync(FULL, ch);
+                }
                 __syncwarp();
                 BW_ACC(4, t_e);
                 iters++;
