@@ -544,31 +544,31 @@ struct Solver {
                 // rotation about the contact point; translations perpendicular to the two edge rays
                 const double n0x = az * et - at * ez, n0z = at * ex - ax * et, n0t = ax * ez - az * ex;
                 const double n1x = az, n1z = -ax, n2x = ez, n2z = -ex;
-                double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300, mn2 = 1e300, mx2 = -1e300;
+                // with l = |n|:  all sigma r . n >= -EPS l  and  n . b_S <= -DELTA l |b_S|   (or the mirror image).
+                // Only the signs matter: per motion two flags "some ray below -EPS l" / "some ray above +EPS l"
+                const double l0 = n0x * n0x + n0z * n0z + n0t * n0t, l1 = n1x * n1x + n1z * n1z, l2 = n2x * n2x + n2z * n2z;
+                const double tol0 = EPS * (l0 * fast_rsqrt(fmax(l0, 1e-300))), tol1 = EPS * (l1 * fast_rsqrt(fmax(l1, 1e-300))),
+                             tol2 = EPS * (l2 * fast_rsqrt(fmax(l2, 1e-300)));
+                bool neg0 = false, pos0 = false, neg1 = false, pos1 = false, neg2 = false, pos2 = false;
 #pragma unroll 1
                 for (int j = 0; j < nbd; j++) {
                     const int e = typ[j];
                     const int k = e & 0x7f;
                     const double sg = (e & 0x80) ? -1.0 : 1.0;
-                    const double rx = g[2 * k] * sg, rz = g[2 * k + 1] * sg, rt = f[2 * k] * sg;
-                    const double sx = h[2 * k] * sg, sz = h[2 * k + 1] * sg, st = f[2 * k + 1] * sg;
-                    const double d0 = n0x * rx + n0z * rz + n0t * rt, e0 = n0x * sx + n0z * sz + n0t * st;
-                    const double d1 = n1x * rx + n1z * rz, e1 = n1x * sx + n1z * sz;
-                    const double d2 = n2x * rx + n2z * rz, e2 = n2x * sx + n2z * sz;
-                    mn0 = fmin(mn0, fmin(d0, e0)); mx0 = fmax(mx0, fmax(d0, e0));
-                    mn1 = fmin(mn1, fmin(d1, e1)); mx1 = fmax(mx1, fmax(d1, e1));
-                    mn2 = fmin(mn2, fmin(d2, e2)); mx2 = fmax(mx2, fmax(d2, e2));
+                    const double rx = g[2 * k], rz = g[2 * k + 1], rt = f[2 * k];
+                    const double sx = h[2 * k], sz = h[2 * k + 1], st = f[2 * k + 1];
+                    const double d0 = sg * (n0x * rx + n0z * rz + n0t * rt), e0 = sg * (n0x * sx + n0z * sz + n0t * st);
+                    const double d1 = sg * (n1x * rx + n1z * rz), e1 = sg * (n1x * sx + n1z * sz);
+                    const double d2 = sg * (n2x * rx + n2z * rz), e2 = sg * (n2x * sx + n2z * sz);
+                    neg0 |= (d0 < -tol0) | (e0 < -tol0); pos0 |= (d0 > tol0) | (e0 > tol0);
+                    neg1 |= (d1 < -tol1) | (e1 < -tol1); pos1 |= (d1 > tol1) | (e1 > tol1);
+                    neg2 |= (d2 < -tol2) | (e2 < -tol2); pos2 |= (d2 > tol2) | (e2 > tol2);
                 }
-                // with l = |n|:  all sigma r . n >= -EPS l  and  n . b_S <= -DELTA l |b_S|   (or the mirror image)
-                const double l0 = n0x * n0x + n0z * n0z + n0t * n0t, l1 = n1x * n1x + n1z * n1z, l2 = n2x * n2x + n2z * n2z;
                 const double w0 = n0z * bw + n0t * bt, w1n = n1z * bw, w2n = n2z * bw;   // n . b_S, b_S = (0, bw, bt)
-                const double E2 = EPS * EPS, D2 = DELTA * DELTA * bn2;
-                if (l0 > 1e-18) found |= ((mn0 >= 0.0 || mn0 * mn0 <= E2 * l0) && w0 < 0.0 && w0 * w0 >= D2 * l0) ||
-                                         ((mx0 <= 0.0 || mx0 * mx0 <= E2 * l0) && w0 > 0.0 && w0 * w0 >= D2 * l0);
-                if (l1 > 1e-18) found |= ((mn1 >= 0.0 || mn1 * mn1 <= E2 * l1) && w1n < 0.0 && w1n * w1n >= D2 * l1) ||
-                                         ((mx1 <= 0.0 || mx1 * mx1 <= E2 * l1) && w1n > 0.0 && w1n * w1n >= D2 * l1);
-                if (l2 > 1e-18) found |= ((mn2 >= 0.0 || mn2 * mn2 <= E2 * l2) && w2n < 0.0 && w2n * w2n >= D2 * l2) ||
-                                         ((mx2 <= 0.0 || mx2 * mx2 <= E2 * l2) && w2n > 0.0 && w2n * w2n >= D2 * l2);
+                const double D2 = DELTA * DELTA * bn2;
+                if (l0 > 1e-18) found |= (!neg0 && w0 < 0.0 && w0 * w0 >= D2 * l0) || (!pos0 && w0 > 0.0 && w0 * w0 >= D2 * l0);
+                if (l1 > 1e-18) found |= (!neg1 && w1n < 0.0 && w1n * w1n >= D2 * l1) || (!pos1 && w1n > 0.0 && w1n * w1n >= D2 * l1);
+                if (l2 > 1e-18) found |= (!neg2 && w2n < 0.0 && w2n * w2n >= D2 * l2) || (!pos2 && w2n > 0.0 && w2n * w2n >= D2 * l2);
             }
             if (__any_sync(FULL, found)) return true;
         }
