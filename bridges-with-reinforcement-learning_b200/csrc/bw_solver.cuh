@@ -454,8 +454,10 @@ struct Solver {
     // (EPS on the rays, DELTA on the weight) so that only clear certificates count; everything else goes
     // to solve().  On the bench rollouts this decides 96 % of the systems without equilibrium
     // (tools/solver_lab.py: an LP on the aggregated 3-row systems catches the same cases).
+    // All sets are examined in one pass: lane = (set, boundary contact point) work item, at most a few
+    // chunks of 32 items (a tower has two boundary contact points per set).
     // Scratch: g, h, f (rays), invd (bodies of a contact), L (contact adjacency masks of the bodies),
-    // typ (boundary contact list of the current set).
+    // y, yk, d (work items).
     __device__ bool screen(const double *body, double invL0) {
         constexpr double EPS = 1e-10, DELTA = 1e-5;
         if (nc > 64) return false;
@@ -502,43 +504,61 @@ struct Solver {
             const double wj = __shfl_sync(FULL, w1, j), tj = __shfl_sync(FULL, t1, j);
             if (j > lane && (aj & S)) { S |= 1u << bj; ws += wj; ts += tj; }
         }
+        // boundary contacts of S_lane as bit masks over the contact points (bm) and, among them, those with S on
+        // the a side (am: sigma = -1); all sets at once, lane = set
+        unsigned bm0 = 0, bm1 = 0, am0 = 0, am1 = 0;
 #pragma unroll 1
-        for (int i = nfree - 1; i >= 0; i--) {
-            const unsigned Si = __shfl_sync(FULL, S, i);
-            const double bw = __shfl_sync(FULL, ws, i), bt = __shfl_sync(FULL, ts, i);
-            // boundary contacts of S_i: sigma = +1 (bit in mp) when S holds body b, -1 (mm) for body a
-            unsigned mp0 = 0, mm0 = 0, mp1 = 0, mm1 = 0;
-            {
-                int c = lane;
-                bool ina = (c < nc) && ((Si >> cba[c]) & 1u), inb = (c < nc) && ((Si >> cbb[c]) & 1u);
-                mp0 = __ballot_sync(FULL, inb && !ina);
-                mm0 = __ballot_sync(FULL, ina && !inb);
-                if (nc > 32) {
-                    c = lane + 32;
-                    ina = (c < nc) && ((Si >> cba[c]) & 1u); inb = (c < nc) && ((Si >> cbb[c]) & 1u);
-                    mp1 = __ballot_sync(FULL, inb && !ina);
-                    mm1 = __ballot_sync(FULL, ina && !inb);
-                }
+        for (int c = 0; c < nc; c++) {
+            const unsigned ina = (S >> cba[c]) & 1u, inb = (S >> cbb[c]) & 1u;
+            const unsigned bd = ina ^ inb, sa = ina & ~inb;
+            if (c < 32) { bm0 |= bd << c; am0 |= sa << c; }
+            else { bm1 |= bd << (c - 32); am1 |= sa << (c - 32); }
+        }
+        int nbd = __popc(bm0) + __popc(bm1);
+        // nothing holds S
+        if (__any_sync(FULL, lane < nfree && nbd == 0 && ws > 0.0)) return true;
+        if (lane >= nfree || nbd > 32) nbd = 0;          // sets with more than 32 boundary contacts are not examined
+        // one work item per (set, boundary contact point): the candidate motions of that contact point against
+        // all boundary rays of its set.  Items are listed set by set (exclusive scan of the counts) in the
+        // memory of y, yk, d, which solve() initialises later.
+        int inc = nbd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int total = __shfl_sync(FULL, inc, 31);
+        uint16_t *items = reinterpret_cast<uint16_t *>(y);
+        const int cap = 12 * (int)(yk - y);               // 3 arrays of (yk - y) doubles, four items per double
+        if (total == 0 || total > cap) return false;
+        {
+            int pos = inc - nbd;
+            unsigned w0 = nbd ? bm0 : 0u, w1m = nbd ? bm1 : 0u;
+#pragma unroll 1
+            while (w0) {
+                const int c = __ffs(w0) - 1;
+                w0 &= w0 - 1;
+                items[pos++] = (uint16_t)((lane << 8) | c);
             }
-            if ((mp0 | mm0 | mp1 | mm1) == 0) {
-                if (bw > 0.0) return true;        // nothing holds S
-                continue;
+#pragma unroll 1
+            while (w1m) {
+                const int c = __ffs(w1m) - 1;
+                w1m &= w1m - 1;
+                items[pos++] = (uint16_t)((lane << 8) | (c + 32));
             }
-            // compact list of the boundary contacts (index | 0x80 when sigma = -1), at most 32 per set
-            const int nb0 = __popc(mp0 | mm0), nbd = nb0 + __popc(mp1 | mm1);
-            if (nbd > 32) continue;
-            {
-                const unsigned lt = (1u << lane) - 1;
-                if (((mp0 | mm0) >> lane) & 1u)
-                    typ[__popc((mp0 | mm0) & lt)] = (uint8_t)(lane | (((mm0 >> lane) & 1u) << 7));
-                if (((mp1 | mm1) >> lane) & 1u)
-                    typ[nb0 + __popc((mp1 | mm1) & lt)] = (uint8_t)((lane + 32) | (((mm1 >> lane) & 1u) << 7));
-            }
-            __syncwarp();
-            const double bn2 = bw * bw + bt * bt;
-            bool found = false;
-            if (lane < nbd) {
-                const int q = typ[lane] & 0x7f;
+        }
+        __syncwarp();
+        bool found = false;
+#pragma unroll 1
+        for (int base = 0; base < total; base += 32) {
+            const int pidx = base + lane;
+            const bool act = pidx < total;
+            const int it = act ? items[pidx] : 0;
+            const int set = it >> 8, q = it & 0xff;
+            unsigned r0 = __shfl_sync(FULL, bm0, set), r1 = __shfl_sync(FULL, bm1, set);
+            const unsigned s0 = __shfl_sync(FULL, am0, set), s1 = __shfl_sync(FULL, am1, set);
+            const double bw = __shfl_sync(FULL, ws, set), bt = __shfl_sync(FULL, ts, set);
+            if (act) {
                 const double ax = g[2 * q], az = g[2 * q + 1], at = f[2 * q];
                 const double ex = h[2 * q], ez = h[2 * q + 1], et = f[2 * q + 1];
                 // rotation about the contact point; translations perpendicular to the two edge rays
@@ -551,19 +571,26 @@ struct Solver {
                              tol2 = EPS * (l2 * fast_rsqrt(fmax(l2, 1e-300)));
                 bool neg0 = false, pos0 = false, neg1 = false, pos1 = false, neg2 = false, pos2 = false;
 #pragma unroll 1
-                for (int j = 0; j < nbd; j++) {
-                    const int e = typ[j];
-                    const int k = e & 0x7f;
-                    const double sg = (e & 0x80) ? -1.0 : 1.0;
-                    const double rx = g[2 * k], rz = g[2 * k + 1], rt = f[2 * k];
-                    const double sx = h[2 * k], sz = h[2 * k + 1], st = f[2 * k + 1];
-                    const double d0 = sg * (n0x * rx + n0z * rz + n0t * rt), e0 = sg * (n0x * sx + n0z * sz + n0t * st);
-                    const double d1 = sg * (n1x * rx + n1z * rz), e1 = sg * (n1x * sx + n1z * sz);
-                    const double d2 = sg * (n2x * rx + n2z * rz), e2 = sg * (n2x * sx + n2z * sz);
-                    neg0 |= (d0 < -tol0) | (e0 < -tol0); pos0 |= (d0 > tol0) | (e0 > tol0);
-                    neg1 |= (d1 < -tol1) | (e1 < -tol1); pos1 |= (d1 > tol1) | (e1 > tol1);
-                    neg2 |= (d2 < -tol2) | (e2 < -tol2); pos2 |= (d2 > tol2) | (e2 > tol2);
+                for (int half = 0; half < 2; half++) {
+                    unsigned w = half ? r1 : r0;
+                    const unsigned sm = half ? s1 : s0;
+#pragma unroll 1
+                    while (w) {
+                        const int kb = __ffs(w) - 1;
+                        w &= w - 1;
+                        const int k = kb + 32 * half;
+                        const double sg = ((sm >> kb) & 1u) ? -1.0 : 1.0;
+                        const double rx = g[2 * k], rz = g[2 * k + 1], rt = f[2 * k];
+                        const double sx = h[2 * k], sz = h[2 * k + 1], st = f[2 * k + 1];
+                        const double d0 = sg * (n0x * rx + n0z * rz + n0t * rt), e0 = sg * (n0x * sx + n0z * sz + n0t * st);
+                        const double d1 = sg * (n1x * rx + n1z * rz), e1 = sg * (n1x * sx + n1z * sz);
+                        const double d2 = sg * (n2x * rx + n2z * rz), e2 = sg * (n2x * sx + n2z * sz);
+                        neg0 |= (d0 < -tol0) | (e0 < -tol0); pos0 |= (d0 > tol0) | (e0 > tol0);
+                        neg1 |= (d1 < -tol1) | (e1 < -tol1); pos1 |= (d1 > tol1) | (e1 > tol1);
+                        neg2 |= (d2 < -tol2) | (e2 < -tol2); pos2 |= (d2 > tol2) | (e2 > tol2);
+                    }
                 }
+                const double bn2 = bw * bw + bt * bt;
                 const double w0 = n0z * bw + n0t * bt, w1n = n1z * bw, w2n = n2z * bw;   // n . b_S, b_S = (0, bw, bt)
                 const double D2 = DELTA * DELTA * bn2;
                 if (l0 > 1e-18) found |= (!neg0 && w0 < 0.0 && w0 * w0 >= D2 * l0) || (!pos0 && w0 > 0.0 && w0 * w0 >= D2 * l0);
