@@ -69,6 +69,13 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     return fma(0.5 * x, e, x);
 }
 
+// 1/a for a normal a: hardware approximation + one Newton step (line-search abscissae only)
+__device__ __forceinline__ double fast_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    return fma(fma(-a, x, 1.0), x, x);
+}
+
 // projection of (gn, gt) onto the friction cone |ft| <= mu fn.
 // typ: 0 = polar cone (f = 0), 1 = interior, 2 = ray ft = +mu fn, 3 = ray ft = -mu fn
 __device__ __forceinline__ void project_cone(double gn, double gt, double mu, double inv_den, double &fn, double &ft,
@@ -724,7 +731,7 @@ struct Solver {
 #pragma unroll 1
                     for (int ls = 0; ls < 20; ls++) {
                         const double w = hi - lo;
-                        t = lo + w * plo / (plo - phi);
+                        t = lo + w * plo * fast_rcp(plo - phi);      // plo > 0 > phi; the safeguard below bounds t anyway
                         t = fmin(fmax(t, lo + 0.1 * w), hi - 0.1 * w);
                         p = base - fdoth(t) - t * dd * inv_rho;
                         if (fabs(p) <= 0.1 * phi0) break;
