@@ -305,6 +305,11 @@ def run_gpu(args, rank, local_rank, world):
         raise SystemExit("bench.py needs a CUDA device: bridges_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        # several ranks share the host: keep this rank (and the pinned buffers it allocates) on its GPU's NUMA node
+        from bridges_b200.sharding import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -475,6 +480,7 @@ def run_gpu(args, rank, local_rank, world):
                                          "mask, robotoddler/utils/actions.py:7-82) + random selection"},
         "wall_s_timed_region": wall,
     }
+    line["e2e"]["host_binding"] = (f"rank bound to the {len(numa_cpus)} CPUs next to its GPU" if numa_cpus else "none")
     if sweep is not None:
         line["sweep"] = sweep
     if args.batch_scan:
@@ -505,6 +511,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0, help="CPU-arm worker processes (0 = all host cores)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not bind the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-flush", action="store_true", help="profiling only: skip the L2 flush between steps")
     ap.add_argument("--sweep", action="store_true", help="also run the 65,536-assembly stability sweep (configs[3])")
     ap.add_argument("--batch-scan", action="store_true", help="also time the step at 4096 / 16384 / 65536 envs per GPU")

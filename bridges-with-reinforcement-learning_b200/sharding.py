@@ -1,8 +1,42 @@
 """Env-level data parallelism: independent assemblies are partitioned contiguously over the
 ranks (one process per GPU); there is no collective on the step path.  Collectives are used
 only to combine timings / verdict arrays after the fact."""
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index, sysfs="/sys/bus/pci/devices"):
+    """Best effort: restrict this process to the CPUs next to GPU `device_index` (its PCI device's
+    `local_cpulist`), so that the pinned host buffers of the zero-copy step path are allocated on, and
+    written through, the GPU's own NUMA node when several ranks share one host.  Returns the CPU set that
+    was applied, or None when nothing was changed (no sysfs entry, no CUDA, affinity not permitted)."""
+    try:
+        bus_id = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = os.path.join(sysfs, "%04x:%02x:%02x.0" % (dom, bus_id, dev), "local_cpulist")
+        with open(path) as fh:
+            local = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (AttributeError, OSError, ValueError, RuntimeError, AssertionError):
+        return None
 
 
 def shard_range(total, rank, world):

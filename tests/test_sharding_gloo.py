@@ -61,3 +61,16 @@ def test_reference_arm_prints_on_rank0_only():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["unit"] == "env_steps/s" and line["higher_is_better"] is True
+
+
+def test_numa_binding_helpers():
+    """`bind_to_gpu_numa_node` is best effort: a parsed cpulist, and no change without a CUDA device."""
+    import os
+    from bridges_b200.sharding import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_to_gpu_numa_node(0) is None
+        assert os.sched_getaffinity(0) == before
