@@ -287,6 +287,7 @@ struct Solver {
     // triangular solve.  m is a multiple of 3, so the right-hand-side row m lies below every block.
     __device__ void factor_and_solve(double inv_rho) {
         const int nrows = m + 1;
+        const double sqrt_rho = fast_rsqrt(inv_rho);
         const int i0 = lane, i1 = lane + 32;
         double *row0 = L + tri(i0 < nrows ? i0 : 0);       // idle lanes read row 0 (results unused)
         double *row1 = L + tri((TWO && i1 < nrows) ? i1 : 0);
@@ -333,18 +334,18 @@ struct Solver {
             // complements, M2 = d00 s11 and T = d00 M2 s22 need no earlier square root, so the three
             // rsqrt chains run side by side instead of one after the other
             //   1/sqrt(s11) = rsqrt(M2) sqrt(d00),   1/sqrt(s22) = rsqrt(T) sqrt(d00) sqrt(M2)
-            double p0 = d00;
-            if (!(p0 > 1e-300)) p0 = inv_rho;
-            const double i00 = fast_rsqrt(p0);
-            double M2 = fma(d11, p0, -(d10 * d10));
-            if (!(M2 > 1e-300 * p0)) M2 = inv_rho * p0;
-            const double c21 = fma(d21, p0, -(d20 * d10));            // d00 (d21 - l20 l10)
-            double T = fma(fma(p0, d22, -(d20 * d20)), M2, -(c21 * c21));   // d00 M2 s22
-            if (!(T > 1e-300 * (p0 * M2))) T = inv_rho * (p0 * M2);
+            // (H is positive definite; a pivot that rounding drives to <= 0 -- or NaN -- is replaced by 1/rho.
+            // The tests run beside the rsqrt chains and only select the results.)
+            const double i00r = fast_rsqrt(d00);
+            const double M2 = fma(d11, d00, -(d10 * d10));
+            const double c21 = fma(d21, d00, -(d20 * d10));            // d00 (d21 - l20 l10)
+            const double T = fma(fma(d00, d22, -(d20 * d20)), M2, -(c21 * c21));   // d00 M2 s22
             const double rM2 = fast_rsqrt(M2), rT = fast_rsqrt(T);
-            const double sp0 = p0 * i00, sM2 = M2 * rM2;               // sqrt(d00), sqrt(M2)
-            const double i11 = rM2 * sp0;
-            const double i22 = rT * (sp0 * sM2);
+            const bool ok0 = d00 > 1e-300, ok1 = ok0 && M2 > 1e-300 * d00, ok2 = ok1 && T > 1e-300 * (d00 * M2);
+            const double sp0 = d00 * i00r, sM2 = M2 * rM2;             // sqrt(d00), sqrt(M2)
+            const double i00 = ok0 ? i00r : sqrt_rho;
+            const double i11 = ok1 ? rM2 * sp0 : sqrt_rho;
+            const double i22 = ok2 ? rT * (sp0 * sM2) : sqrt_rho;
             const double l10 = d10 * i00, l20 = d20 * i00;
             const double l21 = (d21 - l20 * l10) * i11;
             // the strictly lower entries of the INVERSE of the diagonal block take the place of l10, l20, l21
