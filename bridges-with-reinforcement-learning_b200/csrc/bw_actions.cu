@@ -62,17 +62,33 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         s_obst[tid] = P.obst_bits[(size_t)e * IMG + tid];
     }
     __syncthreads();
-    if (tid == 0) {
-        // receiving faces of placed blocks: all faces (assembly_env.py:153), occupied ones
-        // skipped (max_blocks_per_face = 1, actions.py:42-44)
-        int k = 0;
-        for (int j = 0; j < n; j++) {
-            const int nf = P.shapes[s_shape[j]].n_faces;
-            const uint8_t occ = P.face_occ[(size_t)e * NB + j];
-            for (int f = 0; f < nf; f++)
-                if (!((occ >> f) & 1u)) { s_free_b[k] = (uint8_t)j; s_free_f[k] = (uint8_t)f; k++; }
+    if (tid < 32) {
+        // receiving faces of placed blocks: all faces (assembly_env.py:153), occupied ones skipped
+        // (max_blocks_per_face = 1, actions.py:42-44).  Lane = block: count, exclusive scan, then every lane
+        // lists the free faces of its block -- same (block, face) order as the reference's nested loops.
+        int nf = 0;
+        unsigned freem = 0;
+        if (tid < n) {
+            nf = P.shapes[s_shape[tid]].n_faces;
+            freem = ~(unsigned)P.face_occ[(size_t)e * NB + tid] & ((1u << nf) - 1u);
         }
-        s_nfree = k;
+        const int cnt = __popc(freem);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += v;
+        }
+        int k = inc - cnt;
+        while (freem) {
+            const int f = __ffs(freem) - 1;
+            freem &= freem - 1;
+            s_free_b[k] = (uint8_t)tid;
+            s_free_f[k] = (uint8_t)f;
+            k++;
+        }
+        if (tid == 31) s_nfree = inc;
+    } else if (tid == 32) {
         int g = 0;
         for (int s = 0; s < P.n_shapes; s++) {
             const ShapeDev &sh = P.shapes[s];
@@ -142,9 +158,19 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             for (int q = tid; q < nchunk * IMG; q += ENUM_THREADS) dst[q] = 0;
         }
         __syncthreads();
-        if (tid == 0) {
-            c_rowstart[0] = 0;
-            for (int t = 0; t < nchunk; t++) c_rowstart[t + 1] += c_rowstart[t];
+        if (tid < 32) {
+            // inclusive scan of the row counts (two candidates per lane), c_rowstart[t + 1] = rows of 0..t
+            const int a0 = (2 * tid < nchunk) ? c_rowstart[2 * tid + 1] : 0;
+            const int a1 = (2 * tid + 1 < nchunk) ? c_rowstart[2 * tid + 2] : 0;
+            int inc = a0 + a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += v;
+            }
+            if (2 * tid < nchunk) c_rowstart[2 * tid + 1] = inc - a1;
+            if (2 * tid + 1 < nchunk) c_rowstart[2 * tid + 2] = inc;
+            if (tid == 0) c_rowstart[0] = 0;
         }
         __syncthreads();
         // ---- phase B: thread per (candidate, row of its window)
