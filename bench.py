@@ -319,7 +319,9 @@ def run_gpu(args, rank, local_rank, world):
         cores = args.cpu_cores or os.cpu_count() or 1
         t0 = time.perf_counter()
         rate, steps = cpu_env_rate(cores, args.cpu_budget, args.tower_height, args.max_steps)
+        rate1, steps1 = cpu_env_rate(1, min(5.0, args.cpu_budget), args.tower_height, args.max_steps)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "one_core": {"value": rate1, "unit": UNIT, "sample": f"{steps1} env steps in one process"},
                     "sample": f"{steps} env steps of the restated reference CPU env (oracle/: numpy + HiGHS, "
                               f"reference call pattern 5 solves + 3 interface rebuilds + 1 raster per step) in "
                               f"{time.perf_counter() - t0:.1f} s wall on {cores} processes; same task and policy"}
