@@ -407,6 +407,7 @@ def run_gpu(args, rank, local_rank, world):
     h_u8 = torch.empty((E, 64, 64), dtype=torch.uint8).pin_memory()
     h_img = torch.empty((E, 1, 64, 64), dtype=torch.float32).pin_memory()
     h_bin = torch.empty((E, 6), dtype=torch.float32).pin_memory()
+    h_bits = torch.empty((E, 64), dtype=torch.int64).pin_memory()
     Ke = min(K, args.e2e_steps)
 
     def e2e_loop(obs, seed0):
@@ -432,14 +433,17 @@ def run_gpu(args, rank, local_rank, world):
     lib.bw_set_host_transfer(h, 1)
     t_e2e_staged = e2e_loop(L.bw_obs_out(None, h_u8.data_ptr(), h_bin.data_ptr()), W + K + 2 * Ke)
     lib.bw_set_host_transfer(h, 0)
+    # (c) the raster bit-packed (bw_obs_out.block_bits, 512 B per environment) for host consumers that unpack lazily
+    t_e2e_bits = e2e_loop(L.bw_obs_out(None, None, h_bin.data_ptr(), h_bits.data_ptr()), W + K + 3 * Ke)
+    d2h_bits = E * (dt["step_out"].itemsize + 64 * 8 + 6 * 4)
     h2d = E * dt["action"].itemsize
     d2h = E * (dt["step_out"].itemsize + 64 * 64 + 6 * 4)
     d2h_f32 = E * (dt["step_out"].itemsize + 64 * 64 * 4 + 6 * 4)
 
     # ---- max over ranks
     sweep = run_sweep(args, rank, local_rank, world, dev) if args.sweep else None
-    t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged = max_over_ranks(
-        [t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged], device=dev)
+    t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged, t_e2e_bits = max_over_ranks(
+        [t_dev, t_e2e, t_e2e_f32, wall, t_cand, t_e2e_staged, t_e2e_bits], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -460,7 +464,10 @@ def run_gpu(args, rank, local_rank, world):
                                     "read / written by the kernel over PCIe as each environment finishes",
                 "staged_copies": {"value": world * E * Ke / t_e2e_staged, "unit": UNIT,
                                   "note": "same call, bw_set_host_transfer(h, 1): cudaMemcpyAsync before and after the kernel"},
-                "with_f32_images": {"value": world * E * Ke / t_e2e_f32, "unit": UNIT, "d2h_bytes_per_step": d2h_f32}},
+                "with_f32_images": {"value": world * E * Ke / t_e2e_f32, "unit": UNIT, "d2h_bytes_per_step": d2h_f32},
+                "with_bit_rasters": {"value": world * E * Ke / t_e2e_bits, "unit": UNIT, "d2h_bytes_per_step": d2h_bits,
+                                     "note": "not the headline: the raster leaves the GPU bit-packed (64 x u64 per "
+                                             "environment), BatchedAssemblyGym.bits_to_bool unpacks it on demand"}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": peak_src,

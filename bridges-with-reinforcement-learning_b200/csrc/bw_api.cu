@@ -36,6 +36,7 @@ struct bw_handle {
     float *d_img[3] = {nullptr, nullptr, nullptr};
     float *d_binary = nullptr;
     uint8_t *d_img_u8 = nullptr;
+    uint64_t *d_bits_out = nullptr;      // staged copy of bw_obs_out.block_bits
     bw_interface *d_itf = nullptr;
     int32_t *d_nitf = nullptr;
     double *d_ground = nullptr, *d_offsets = nullptr;
@@ -391,7 +392,7 @@ int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
     h->launches++;
     if (d_tasks != nullptr) {
         // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
-        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr}, nullptr, nullptr,
+        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr,
                     0, h->smem_step, h->stream);
         h->launches++;
     }
@@ -432,7 +433,7 @@ int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_
     if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
     // one kernel: placement, interfaces, both solves, bookkeeping, raster update and the
     // observation write
-    launch_step(h->P, d_actions, d_mask, d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr}, nullptr, nullptr, 0,
+    launch_step(h->P, d_actions, d_mask, d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, 0,
                 h->smem_step, h->stream);
     h->launches++;
     if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
@@ -483,10 +484,13 @@ int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask
         void *m_f32 = (obs && obs->block_img_f32) ? mapped_alias(obs->block_img_f32) : nullptr;
         void *m_u8 = (obs && obs->block_img_u8) ? mapped_alias(obs->block_img_u8) : nullptr;
         void *m_bin = (obs && obs->binary) ? mapped_alias(obs->binary) : nullptr;
+        void *m_bits = (obs && obs->block_bits) ? mapped_alias(obs->block_bits) : nullptr;
         const bool all_mapped = m_act && m_out && (!h_mask || m_mask) && (!(obs && obs->block_img_f32) || m_f32) &&
-                                (!(obs && obs->block_img_u8) || m_u8) && (!(obs && obs->binary) || m_bin);
+                                (!(obs && obs->block_img_u8) || m_u8) && (!(obs && obs->binary) || m_bin) &&
+                                (!(obs && obs->block_bits) || m_bits);
         if (all_mapped && !h->force_staged) {
-            bw_obs_out dev = {static_cast<float *>(m_f32), static_cast<uint8_t *>(m_u8), static_cast<float *>(m_bin)};
+            bw_obs_out dev = {static_cast<float *>(m_f32), static_cast<uint8_t *>(m_u8), static_cast<float *>(m_bin),
+                              static_cast<uint64_t *>(m_bits)};
             int rc = bw_step(h, static_cast<const bw_action *>(m_act), static_cast<const uint8_t *>(m_mask),
                              static_cast<bw_step_out *>(m_out), &dev);
             if (rc) return rc;
@@ -496,7 +500,7 @@ int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask
     }
     CU(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(bw_action) * E, cudaMemcpyHostToDevice, h->stream));
     if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
-    bw_obs_out dev = {nullptr, nullptr, nullptr};
+    bw_obs_out dev = {nullptr, nullptr, nullptr, nullptr};
     if (obs && obs->block_img_f32) {
         if (int rc = ensure_img(h, 0)) return rc;
         dev.block_img_f32 = h->d_img[0];
@@ -509,6 +513,10 @@ int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask
         if (!h->d_binary) CU(dev_alloc(h, &h->d_binary, E * 6, false));
         dev.binary = h->d_binary;
     }
+    if (obs && obs->block_bits) {
+        if (!h->d_bits_out) CU(dev_alloc(h, &h->d_bits_out, E * IMG, false));
+        dev.block_bits = h->d_bits_out;
+    }
     int rc = bw_step(h, h->d_actions, h_mask ? h->d_mask : nullptr, h->d_out, &dev);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_out, h->d_out, sizeof(bw_step_out) * E, cudaMemcpyDeviceToHost, h->stream));
@@ -519,6 +527,8 @@ int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask
         CU(cudaMemcpyAsync(obs->block_img_u8, dev.block_img_u8, E * IMG * IMG, cudaMemcpyDeviceToHost, h->stream));
     if (dev.binary)
         CU(cudaMemcpyAsync(obs->binary, dev.binary, sizeof(float) * E * 6, cudaMemcpyDeviceToHost, h->stream));
+    if (dev.block_bits)
+        CU(cudaMemcpyAsync(obs->block_bits, dev.block_bits, sizeof(uint64_t) * E * IMG, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -750,7 +760,7 @@ int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h
     CU(cudaMemsetAsync(h->d_itf, 0, sizeof(bw_interface) * E * BW_MAX_INTERFACES, h->stream));
     // the state did not change since the last step: re-evaluating it reproduces the same
     // interfaces and dual iterates, this time with the read-back enabled
-    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr}, h->d_itf, h->d_nitf,
+    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, h->d_itf, h->d_nitf,
                 variant, h->smem_step, h->stream);
     h->launches++;
     CU(cudaGetLastError());

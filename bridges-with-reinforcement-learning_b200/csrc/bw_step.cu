@@ -815,6 +815,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                                         (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f));
         }
     }
+    if (obs.block_bits != nullptr) obs.block_bits[(size_t)e * IMG + tid] = sh_bits[tid];
     if (obs.block_img_u8 != nullptr) {
         uint4 *dst = reinterpret_cast<uint4 *>(obs.block_img_u8 + (size_t)e * IMG * IMG);
 #pragma unroll

@@ -192,8 +192,10 @@ class BatchedAssemblyGym:
                 arr[e] = (a.target_block, a.target_face, a.shape, a.face, a.offset_x, a.offset_y, int(a.frozen), 0)
         return arr
 
-    def step(self, actions, mask=None, block_img=None, binary=None, block_u8=None):
+    def step(self, actions, mask=None, block_img=None, binary=None, block_u8=None, block_bits=None):
         """actions: structured array / list (host) or a uint8 CUDA tensor holding bw_action[E].
+        Optional outputs (CUDA tensors): block_img f32 [E,1,64,64], block_u8 [E,64,64], binary f32 [E,6],
+        block_bits int64 [E,64] (bit-packed raster, see `bits_to_bool`).
         Returns the device uint8 tensor holding bw_step_out[E] (see `read_out`)."""
         if isinstance(actions, torch.Tensor):
             d_act = actions
@@ -204,10 +206,11 @@ class BatchedAssemblyGym:
             d_act = self._actions
         d_mask = self._to_device_bytes(np.asarray(mask, dtype=np.uint8)) if mask is not None else None
         obs = None
-        if block_img is not None or binary is not None or block_u8 is not None:
+        if block_img is not None or binary is not None or block_u8 is not None or block_bits is not None:
             obs = L.bw_obs_out(block_img.data_ptr() if block_img is not None else None,
                                block_u8.data_ptr() if block_u8 is not None else None,
-                               binary.data_ptr() if binary is not None else None)
+                               binary.data_ptr() if binary is not None else None,
+                               block_bits.data_ptr() if block_bits is not None else None)
         self._check(self.lib.bw_step(self.handle, d_act.data_ptr(), d_mask.data_ptr() if d_mask is not None else None,
                                      self._out.data_ptr(), C.byref(obs) if obs is not None else None))
         if d_mask is not None:

@@ -14,7 +14,7 @@ BW_MAX_OBSTACLES = 8
 BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
-BW_ABI_VERSION = 2
+BW_ABI_VERSION = 3
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")
@@ -72,7 +72,8 @@ class bw_step_out(C.Structure):
 
 
 class bw_obs_out(C.Structure):
-    _fields_ = [("block_img_f32", C.c_void_p), ("block_img_u8", C.c_void_p), ("binary", C.c_void_p)]
+    _fields_ = [("block_img_f32", C.c_void_p), ("block_img_u8", C.c_void_p), ("binary", C.c_void_p),
+                ("block_bits", C.c_void_p)]
 
 
 class bw_interface(C.Structure):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 2
+#define BW_ABI_VERSION 3
 
 /* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
 #define BW_MAX_BLOCKS 16
@@ -156,11 +156,13 @@ typedef struct {
 
 /* Optional observation outputs of a step; any pointer may be NULL.  The raster is
  * render_blocks_2d(obs['blocks']) (rendering.py:105-113, a bool image) either as the float32
- * tensor get_state_features makes of it (successor_dqn.py:63) or as one byte per pixel. */
+ * tensor get_state_features makes of it (successor_dqn.py:63), as one byte per pixel, or bit-packed. */
 typedef struct {
     float *block_img_f32;   /* [E,1,64,64] */
     uint8_t *block_img_u8;  /* [E,64,64], 0/1 */
     float *binary;          /* [E,6] = (stable, collision, collision_block, _obstacle, _floor, _boundary) */
+    uint64_t *block_bits;   /* [E,64] the same raster bit-packed: bit x of word r = pixel (row r, column x);
+                               512 B instead of 4 KB / 16 KB per environment for consumers that can take it */
 } bw_obs_out;
 
 /* One contact interface with its two contact points and their forces (bw_get_forces) */

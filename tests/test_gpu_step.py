@@ -205,7 +205,8 @@ def test_host_entry_point_and_observation_formats():
         h_u8 = np.zeros((E, 64, 64), dtype=np.uint8)
         h_f32 = np.zeros((E, 1, 64, 64), dtype=np.float32)
         h_bin = np.zeros((E, 6), dtype=np.float32)
-        obs = L.bw_obs_out(h_f32.ctypes.data, h_u8.ctypes.data, h_bin.ctypes.data)
+        h_bits = np.zeros((E, 64), dtype=np.uint64)
+        obs = L.bw_obs_out(h_f32.ctypes.data, h_u8.ctypes.data, h_bin.ctypes.data, h_bits.ctypes.data)
         L.check(a.lib, a.handle, a.lib.bw_step_host(a.handle, arr.ctypes.data, None, h_out.ctypes.data, C.byref(obs)))
         b.step([act] * E)
         ref = b.read_out()
@@ -218,6 +219,8 @@ def test_host_entry_point_and_observation_formats():
         want = b.bits_to_bool(bits)
         assert np.array_equal(h_u8.astype(bool), want) and set(np.unique(h_u8)) <= {0, 1}
         assert np.array_equal(h_f32[:, 0], want.astype(np.float32))
+        assert np.array_equal(h_bits, np.asarray(bits).astype(np.uint64).reshape(E, 64))      # bit-packed output
+        assert np.array_equal(b.bits_to_bool(h_bits), want)
         assert np.array_equal(h_bin[:, 0], ref["stable"].astype(np.float32)) and not h_bin[:, 1:].any()
 
 
@@ -241,7 +244,8 @@ def test_host_entry_point_pinned_buffers_zero_copy():
                          out=torch.zeros(E * dt["step_out"].itemsize, dtype=torch.uint8).pin_memory(),
                          u8=torch.zeros((E, 64, 64), dtype=torch.uint8).pin_memory(),
                          f32=torch.zeros((E, 1, 64, 64), dtype=torch.float32).pin_memory(),
-                         bin=torch.zeros((E, 6), dtype=torch.float32).pin_memory()))
+                         bin=torch.zeros((E, 6), dtype=torch.float32).pin_memory(),
+                         bits=torch.zeros((E, 64), dtype=torch.int64).pin_memory()))
     x_ground = [-2.0 + 2.0 * i / 9 for i in range(10)]
     for k in range(6):
         a.enumerate_actions(x_ground, (0.0,), amax=128, with_bits=False)
@@ -249,7 +253,7 @@ def test_host_entry_point_pinned_buffers_zero_copy():
         host_acts = acts.cpu()
         for env, bf in zip((a, b), bufs):
             bf["act"].copy_(host_acts)
-            obs = L.bw_obs_out(bf["f32"].data_ptr(), bf["u8"].data_ptr(), bf["bin"].data_ptr())
+            obs = L.bw_obs_out(bf["f32"].data_ptr(), bf["u8"].data_ptr(), bf["bin"].data_ptr(), bf["bits"].data_ptr())
             L.check(env.lib, env.handle, env.lib.bw_step_host(env.handle, bf["act"].data_ptr(), None,
                                                               bf["out"].data_ptr(), C.byref(obs)))
         oa = bufs[0]["out"].numpy().view(dt["step_out"])
@@ -258,7 +262,8 @@ def test_host_entry_point_pinned_buffers_zero_copy():
                      "n_interfaces", "distance_to_targets", "error"):
             assert np.array_equal(oa[name], ob[name]), (k, name)
         assert torch.equal(bufs[0]["u8"], bufs[1]["u8"]) and torch.equal(bufs[0]["f32"], bufs[1]["f32"])
-        assert torch.equal(bufs[0]["bin"], bufs[1]["bin"])
+        assert torch.equal(bufs[0]["bin"], bufs[1]["bin"]) and torch.equal(bufs[0]["bits"], bufs[1]["bits"])
+        assert np.array_equal(a.bits_to_bool(bufs[0]["bits"].numpy().view(np.uint64)), bufs[0]["u8"].numpy().astype(bool))
         assert bufs[0]["u8"].any() and (oa["n_blocks"] == k + 1).any()
         bits, _ = a.raster_bits()
         assert np.array_equal(bufs[0]["u8"].numpy().astype(bool), a.bits_to_bool(bits))
