@@ -40,7 +40,33 @@ def task_def(tower_height, square=0.6):
     return dict(obstacles=obstacles, targets=targets)
 
 
+def bridge_def(num_obstacles, square=0.6):
+    """horizontal_bridge_setup, gym_env.py:24-42: a row of obstacle cubes on the floor, the target beyond it"""
+    obstacles = [(i * square, 0, square / 2) for i in range(1, num_obstacles + 1)]
+    targets = [(num_obstacles * square + 2.5 * square, 0, square / 2)]
+    return dict(obstacles=obstacles, targets=targets)
+
+
+def task_spec(args):
+    """Picklable description of the benchmark task: obstacles, targets and the block library."""
+    if args.task == "bridge":
+        t = bridge_def(args.num_obstacles)
+        shapes = [x.strip() for x in args.shapes.split(",") if x.strip()]
+    else:
+        t = task_def(args.tower_height)
+        shapes = ["trapezoid"]
+    return dict(kind=args.task, shapes=shapes, obstacles=t["obstacles"], targets=t["targets"])
+
+
 def config_dict(args, n_gpus):
+    if args.task == "bridge":
+        return {"workload": f"horizontal_bridge_setup(num_obstacles={args.num_obstacles}) with shapes [{args.shapes}], "
+                            f"{args.envs} lock-step envs per GPU, max_steps={args.max_steps}, random valid actions, "
+                            f"auto-reset (BASELINE.json configs[4] shape)",
+                "envs_per_gpu": args.envs, "num_obstacles": args.num_obstacles, "shapes": args.shapes,
+                "max_steps": args.max_steps, "image": "64x64 f32", "mu": 0.8,
+                "parallelism": f"env-sharded x{n_gpus}, no collective on the step path",
+                "cache": "L2 flushed between timed steps (256 MiB write outside the event pairs)"}
     return {"workload": f"tower_height={args.tower_height} trapezoid task, {args.envs} lock-step envs per GPU, "
                         f"max_steps={args.max_steps}, random valid actions, auto-reset (BASELINE.json configs[1])",
             "envs_per_gpu": args.envs, "tower_height": args.tower_height, "max_steps": args.max_steps,
@@ -64,8 +90,9 @@ def _cpu_worker(job):
     from oracle.rendering import render_blocks_2d
     rng = np.random.default_rng(seed)
     xlim, ylim, img = (-3.0, 7.0), (0.0, 10.0), (64, 64)
-    t = task_def(tower_height)
-    env = AssemblyGym(shapes=[Shape(urdf_file="shapes/trapezoid.urdf", name="trapezoid")], obstacles=t["obstacles"],
+    # `tower_height`: an int (tower task, trapezoid library) or a task_spec() dict
+    t = tower_height if isinstance(tower_height, dict) else dict(task_def(tower_height), shapes=["trapezoid"])
+    env = AssemblyGym(shapes=[Shape(urdf_file=f"shapes/{nm}.urdf", name=nm) for nm in t["shapes"]], obstacles=t["obstacles"],
                       targets=t["targets"], reward_fct=sparse_reward, restrict_2d=True, max_steps=max_steps,
                       assembly_env=AssemblyEnv())
     steps, timed, warm = 0, 0.0, 0
@@ -124,7 +151,7 @@ def run_reference(args, rank, world):
     per_step = 4 * cores
     total_env_steps = per_step * args.steps
     t0 = time.perf_counter()
-    rate, steps = cpu_env_rate(cores, 150.0, args.tower_height, args.max_steps,
+    rate, steps = cpu_env_rate(cores, 150.0, task_spec(args), args.max_steps,
                                max_env_steps=max(8, total_env_steps // cores),
                                warm_env_steps=min(64, 4 * max(1, args.warmup)), min_s=8.0)
     wall = time.perf_counter() - t0
@@ -318,8 +345,8 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_cores or os.cpu_count() or 1
         t0 = time.perf_counter()
-        rate, steps = cpu_env_rate(cores, args.cpu_budget, args.tower_height, args.max_steps)
-        rate1, steps1 = cpu_env_rate(1, min(5.0, args.cpu_budget), args.tower_height, args.max_steps)
+        rate, steps = cpu_env_rate(cores, args.cpu_budget, task_spec(args), args.max_steps)
+        rate1, steps1 = cpu_env_rate(1, min(5.0, args.cpu_budget), task_spec(args), args.max_steps)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                     "one_core": {"value": rate1, "unit": UNIT, "sample": f"{steps1} env steps in one process"},
                     "sample": f"{steps} env steps of the restated reference CPU env (oracle/: numpy + HiGHS, "
@@ -327,15 +354,18 @@ def run_gpu(args, rank, local_rank, world):
                               f"{time.perf_counter() - t0:.1f} s wall on {cores} processes; same task and policy"}
 
     E, K, W = args.envs, args.steps, args.warmup
-    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=args.max_steps, device=local_rank)
+    spec = task_spec(args)
+    env = BatchedAssemblyGym(E, [f"shapes/{nm}.urdf" for nm in spec["shapes"]], max_steps=args.max_steps, device=local_rank)
     lib, h = env.lib, env.handle
-    env.reset(task_def(args.tower_height))
-    n_obs_tgt = (args.tower_height - 1) + 1
+    env.reset(dict(obstacles=spec["obstacles"], targets=spec["targets"]))
+    n_obs_tgt = len(spec["obstacles"]) + len(spec["targets"])
     dt = env.dt
     block_img = torch.empty((E, 1, 64, 64), dtype=torch.float32, device=dev)
     binary = torch.empty((E, 6), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    amax = 128
+    # capacity of the candidate list: (sum of faces over the library) x (10 ground offsets + free receiver faces)
+    # (trapezoid: 44 + 8 n candidates with n placed blocks)
+    amax = (128 if args.max_steps <= 10 else 256) if spec["shapes"] == ["trapezoid"] else 1024
     lib.bw_set_timing(h, 0)
 
     cand_ev = []
@@ -514,6 +544,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=1024, help="lock-step envs per GPU")
     ap.add_argument("--tower-height", type=int, default=2)
+    ap.add_argument("--task", default="tower", choices=["tower", "bridge"],
+                    help="tower: the tower_height task (headline); bridge: horizontal_bridge_setup (configs[4] shape)")
+    ap.add_argument("--num-obstacles", type=int, default=5, help="--task bridge: obstacle cubes to span")
+    ap.add_argument("--shapes", default="trapezoid,hexagon", help="--task bridge: block library (names under shapes/)")
     ap.add_argument("--max-steps", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline sampling")

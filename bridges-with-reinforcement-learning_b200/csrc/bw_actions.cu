@@ -183,8 +183,8 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             }
             const int t = lo;
             const int row = c_ilo[t] + (q - c_rowstart[t]);
-            const uint64_t bits = raster_row_posed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
-                                                   c_jhi[t], row);
+            const uint64_t bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t],
+                                                         c_jlo[t], c_jhi[t], row);
             if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
             if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
         }

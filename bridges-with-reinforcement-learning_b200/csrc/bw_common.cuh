@@ -267,6 +267,39 @@ __device__ inline uint64_t raster_row_posed(const Params &P, int n_faces, const 
     return (w >= 64) ? ~0ull : (((1ull << w) - 1) << lo);
 }
 
+// The same row mask for warps whose lanes hold rows of DIFFERENT posed shapes (enumerate_kernel): the two
+// directions of a face (v increasing / decreasing with the column) walk one instruction sequence with a signed
+// step instead of two divergent branches.  Same estimate, same exact tests, same result as raster_row_posed.
+__device__ inline uint64_t raster_row_posed_mixed(const Params &P, int n_faces, const double *nx, const double *nz,
+                                                  const double *cx, const double *cz, const double *inv_nx, int j_lo,
+                                                  int j_hi, int row) {
+    const double pz = P.ys[row];
+    int lo = j_lo, hi = j_hi;                 // surviving column interval [lo, hi]
+    for (int k = 0; k < n_faces && lo <= hi; k++) {
+        const double fnx = nx[k], fcx = cx[k];
+        const double vz = dmul(dsub(pz, cz[k]), nz[k]);
+        if (fnx == 0.0) {                     // the value does not depend on the column
+            if (!pixel_in_halfplane(P.xs[lo], fcx, fnx, vz)) hi = lo - 1;
+            continue;
+        }
+        const double g = (fcx - vz * inv_nx[k] - P.xlim0) * P.inv_step_x;
+        const bool inc = fnx > 0.0;           // inside = [lo, b] (inc) or [b, hi] (!inc)
+        const int step = inc ? 1 : -1;
+        const int near = inc ? lo : hi, far = inc ? hi : lo;
+        // b = estimated last inside column walking from `near` towards `far` (one beyond `near` = none)
+        const double gr = inc ? floor(g) : ceil(g);
+        int b = ((gr - (double)far) * (double)step >= 0.0) ? far
+              : (((gr - (double)near) * (double)step < 0.0) ? near - step : (int)gr);
+        while (b != far && pixel_in_halfplane(P.xs[b + step], fcx, fnx, vz)) b += step;
+        while ((b - near) * step >= 0 && !pixel_in_halfplane(P.xs[b], fcx, fnx, vz)) b -= step;
+        hi = inc ? b : hi;
+        lo = inc ? lo : b;
+    }
+    if (lo > hi) return 0;
+    const int w = hi - lo + 1;
+    return (w >= 64) ? ~0ull : (((1ull << w) - 1) << lo);
+}
+
 __device__ inline uint64_t raster_row(const Params &P, const ShapeDev &sh, const Pose &ps, int row) {
     PosedShape o;
     pose_shape(P, sh, ps, o);
