@@ -19,10 +19,24 @@ constexpr int ENUM_CHUNK = 64;        // candidates posed per pass (shared-memor
 // for the candidate (placement, bounds test, posed half-planes, pixel window) -- FP64 work that must
 // not be replicated over the lanes of a warp.  B: one thread per (candidate, image row inside its
 // window) evaluates the row's bit mask and the overlap with the block / obstacle rasters.
+//
+// CACHED: a candidate is (group, ground offset) or (group, target block, target face, offset) -- its pose, its
+// bounds flag and its raster depend on nothing but the block library and the pose of the target block, so they
+// survive from call to call (CandCache: one slot per possible candidate of an environment).  A block whose pose
+// or shape differs from the copy taken when its slots were filled (a reset, a new block) invalidates its slots
+// at the start of the call; ground slots live until the library or the offset tables change (host side).
+// Only the overlap with the current block / obstacle rasters is recomputed for a cached candidate.
+constexpr uint32_t SLOT_VALID = 0x80000000u, SLOT_BAD = 0x40000000u;
+
+__device__ __forceinline__ bool same_bits(double a, double b) {
+    return __double_as_longlong(a) == __double_as_longlong(b);
+}
+
+template <bool CACHED>
 __global__ void __launch_bounds__(ENUM_THREADS, 8)
 enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                  int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
-                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits) {
+                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, CandCache C) {
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     // block library and pixel nodes in shared memory; the helpers of bw_common.cuh read them through P
@@ -51,6 +65,9 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     __shared__ int8_t c_nf[ENUM_CHUNK], c_jlo[ENUM_CHUNK], c_jhi[ENUM_CHUNK], c_ilo[ENUM_CHUNK], c_bad[ENUM_CHUNK];
     __shared__ int c_rowstart[ENUM_CHUNK + 1];
     __shared__ int c_overlap[ENUM_CHUNK];
+    __shared__ int c_slot[ENUM_CHUNK];          // cache slot of the candidate (-1: none)
+    __shared__ uint8_t c_cached[ENUM_CHUNK];    // its slot was valid: raster rows are read, not computed
+    __shared__ unsigned s_inval;
 
     const int n = P.n_blocks[e];
     if (tid < n) {
@@ -98,6 +115,35 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         s_ngrp = g;
     }
     __syncthreads();
+    if (CACHED) {
+        // blocks that are not the ones their slots were filled for: drop those slots, remember the new block
+        if (tid == 0) s_inval = 0;
+        __syncthreads();
+        if (tid < n) {
+            const Pose cp = C.pose[(size_t)e * NB + tid];
+            const Pose p = s_pose[tid];
+            const bool same = same_bits(cp.x, p.x) && same_bits(cp.z, p.z) && same_bits(cp.c, p.c) &&
+                              same_bits(cp.s, p.s) && C.shape[(size_t)e * NB + tid] == s_shape[tid];
+            if (!same) {
+                C.pose[(size_t)e * NB + tid] = p;
+                C.shape[(size_t)e * NB + tid] = s_shape[tid];
+                atomicOr(&s_inval, 1u << tid);
+            }
+        }
+        __syncthreads();
+        unsigned inv = s_inval;
+        const int per_block = NF * n_offsets;
+        while (inv) {
+            const int b = __ffs(inv) - 1;
+            inv &= inv - 1;
+            for (int q = tid; q < s_ngrp * per_block; q += ENUM_THREADS) {
+                const int g = q / per_block, r = q - g * per_block;
+                C.meta[(size_t)e * C.slots + g * C.spg + n_ground + b * per_block + r] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    const bool env_full = n >= P.max_blocks;     // no placement possible: nothing is cached, nothing is valid
     const int per_group = n_ground + s_nfree * n_offsets;
     const int total = s_ngrp * per_group;
     const int count = min(total, amax);
@@ -116,39 +162,65 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             const int g = a / per_group, w = a - g * per_group;
             act.shape = s_grp_s[g];
             act.face = s_grp_f[g];
+            int slot = -1;
             if (w < n_ground) {
                 act.offset_x = ground[w];
+                slot = g * C.spg + w;
             } else {
                 const int k = (w - n_ground) / n_offsets, oi = (w - n_ground) - k * n_offsets;
                 act.target_block = s_free_b[k];
                 act.target_face = s_free_f[k];
                 act.offset_x = offsets[oi];
+                slot = g * C.spg + n_ground + (act.target_block * NF + act.target_face) * n_offsets + oi;
             }
             cand[(size_t)e * amax + a] = act;
-            Pose ps;
-            const int err = place_block(P, s_pose, s_shape, n, act, ps);
+            if (!CACHED || env_full) slot = -1;
             int rows = 0;
-            bool bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
-            if (!bad) {
-                const ShapeDev &sh = P.shapes[act.shape];
-                // collision_on_action: any vertex outside the window (gym_env.py:304-323)
-                for (int v = 0; v < sh.n_verts; v++) {
-                    double vx, vz;
-                    rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
-                    vx = dadd(vx, ps.x);
-                    vz = dadd(vz, ps.z);
-                    if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
+            bool bad = false, hit = false;
+            if (CACHED && slot >= 0) {
+                const uint32_t m = C.meta[(size_t)e * C.slots + slot];
+                if (m & SLOT_VALID) {
+                    hit = true;
+                    bad = (m & SLOT_BAD) != 0;
+                    rows = (int)(m & 0xffu);
+                    c_ilo[tid] = (int8_t)((m >> 8) & 0xffu);
                 }
-                PosedShape o;
-                pose_shape(P, sh, ps, o);
-                for (int k = 0; k < NF; k++) {
-                    c_nx[tid][k] = o.nx[k]; c_nz[tid][k] = o.nz[k]; c_cx[tid][k] = o.cx[k]; c_cz[tid][k] = o.cz[k];
-                    c_inx[tid][k] = o.inv_nx[k];
-                }
-                c_nf[tid] = (int8_t)o.n_faces;
-                c_jlo[tid] = (int8_t)o.j_lo; c_jhi[tid] = (int8_t)o.j_hi; c_ilo[tid] = (int8_t)o.i_lo;
-                if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
             }
+            if (!hit) {
+                Pose ps;
+                const int err = place_block(P, s_pose, s_shape, n, act, ps);
+                bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
+                int ilo = 0;
+                if (!bad) {
+                    const ShapeDev &sh = P.shapes[act.shape];
+                    // collision_on_action: any vertex outside the window (gym_env.py:304-323)
+                    for (int v = 0; v < sh.n_verts; v++) {
+                        double vx, vz;
+                        rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+                        vx = dadd(vx, ps.x);
+                        vz = dadd(vz, ps.z);
+                        if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
+                    }
+                    PosedShape o;
+                    pose_shape(P, sh, ps, o);
+                    for (int k = 0; k < NF; k++) {
+                        c_nx[tid][k] = o.nx[k]; c_nz[tid][k] = o.nz[k]; c_cx[tid][k] = o.cx[k]; c_cz[tid][k] = o.cz[k];
+                        c_inx[tid][k] = o.inv_nx[k];
+                    }
+                    c_nf[tid] = (int8_t)o.n_faces;
+                    c_jlo[tid] = (int8_t)o.j_lo; c_jhi[tid] = (int8_t)o.j_hi; c_ilo[tid] = (int8_t)o.i_lo;
+                    ilo = o.i_lo;
+                    if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
+                }
+                if (CACHED && slot >= 0) {
+                    if (err == 0)
+                        C.meta[(size_t)e * C.slots + slot] = SLOT_VALID | (bad ? SLOT_BAD : 0u) | ((uint32_t)ilo << 8) | (uint32_t)rows;
+                    else
+                        slot = -1;
+                }
+            }
+            c_slot[tid] = slot;
+            c_cached[tid] = hit ? 1 : 0;
             c_bad[tid] = bad ? 1 : 0;
             c_overlap[tid] = 0;
             c_rowstart[tid + 1] = rows;
@@ -183,8 +255,14 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             }
             const int t = lo;
             const int row = c_ilo[t] + (q - c_rowstart[t]);
-            const uint64_t bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t],
-                                                         c_jlo[t], c_jhi[t], row);
+            uint64_t bits;
+            if (CACHED && c_cached[t]) {
+                bits = C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row];
+            } else {
+                bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
+                                              c_jhi[t], row);
+                if (CACHED && c_slot[t] >= 0) C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row] = bits;
+            }
             if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
             if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
         }
@@ -196,9 +274,13 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
 
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      cudaStream_t stream) {
-    enumerate_kernel<<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                       d_valid, d_n_cand, d_action_bits);
+                      const CandCache &cache, cudaStream_t stream) {
+    if (cache.meta != nullptr && cache.slots > 0)
+        enumerate_kernel<true><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
+                                                                 d_valid, d_n_cand, d_action_bits, cache);
+    else
+        enumerate_kernel<false><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
+                                                                  d_valid, d_n_cand, d_action_bits, cache);
 }
 
 // create_block + collision_on_action for one hypothetical action per env (state untouched)

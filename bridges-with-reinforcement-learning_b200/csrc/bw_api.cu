@@ -42,6 +42,11 @@ struct bw_handle {
     double *d_ground = nullptr, *d_offsets = nullptr;
     double ground_cached[256], offsets_cached[256];   // host copies of what d_ground / d_offsets hold
     int n_ground_cached = -1, n_offsets_cached = -1;
+    // cache of candidate placements used by bw_enumerate_actions (bw_actions.cu, enumerate_kernel<true>)
+    CandCache cand;
+    int n_groups = 0;                // (shape, face) pairs with the target_faces bit: candidate groups
+    bool cand_dirty = true;          // library or offset tables changed: every slot is stale
+    size_t cand_budget = (size_t)4096 << 20;   // bytes; BW_CAND_CACHE_MB overrides, 0 disables the cache
     bw_block *d_qblocks = nullptr, *d_rblocks = nullptr;
     uint8_t *d_qflags = nullptr;
     ShapeDev *d_rshapes = nullptr;
@@ -140,6 +145,56 @@ static void default_marker(ShapeDev &d) {
     shape_to_dev(s, d);
 }
 
+// Sizes (and, when the block library or the offset tables changed, clears) the candidate cache of
+// bw_enumerate_actions.  Layout: per environment groups x (n_ground + max_blocks * NF * n_offsets) slots of
+// 512 B raster + 4 B flags.  A layout that does not fit the budget switches the cache off (plain kernel).
+static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
+    const int spg = n_ground + h->P.max_blocks * NF * n_offsets;
+    const int slots = h->n_groups * spg;
+    const size_t E = (size_t)h->P.E;
+    const size_t need = E * (size_t)slots * (IMG * sizeof(uint64_t) + sizeof(uint32_t)) + E * NB * (sizeof(Pose) + 1);
+    CandCache &c = h->cand;
+    if (slots <= 0 || need > h->cand_budget) {
+        if (c.meta) {
+            CU(cudaStreamSynchronize(h->stream));
+            void *old[4] = {c.meta, c.bits, c.pose, c.shape};
+            for (void *q : old) {
+                cudaFree(q);
+                for (size_t i = 0; i < h->allocs.size(); i++)
+                    if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
+            }
+        }
+        c = CandCache();
+        return BW_OK;
+    }
+    if (c.meta == nullptr || c.slots != slots || c.spg != spg) {
+        if (c.meta) {
+            CU(cudaStreamSynchronize(h->stream));
+            void *old[4] = {c.meta, c.bits, c.pose, c.shape};
+            for (void *q : old) {
+                cudaFree(q);
+                for (size_t i = 0; i < h->allocs.size(); i++)
+                    if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
+            }
+            c = CandCache();
+        }
+        CU(dev_alloc(h, &c.meta, E * slots, false));
+        CU(dev_alloc(h, &c.bits, E * slots * IMG, false));
+        CU(dev_alloc(h, &c.pose, E * NB, false));
+        CU(dev_alloc(h, &c.shape, E * NB, false));
+        c.slots = slots;
+        c.spg = spg;
+        h->cand_dirty = true;
+    }
+    if (h->cand_dirty) {
+        CU(cudaMemsetAsync(c.meta, 0, sizeof(uint32_t) * E * slots, h->stream));
+        CU(cudaMemsetAsync(c.pose, 0xff, sizeof(Pose) * E * NB, h->stream));      // no block has this pose
+        CU(cudaMemsetAsync(c.shape, 0xff, E * NB, h->stream));
+        h->cand_dirty = false;
+    }
+    return BW_OK;
+}
+
 extern "C" {
 
 int bw_abi_version(void) { return BW_ABI_VERSION; }
@@ -236,6 +291,7 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     if (cfg->collision_mode != 0 && cfg->collision_mode != 1) return fail(h, BW_ERR_INVALID, "collision_mode must be 0 or 1");
     P.collision_mode = cfg->collision_mode;
     P.screen = getenv("BW_NO_SCREEN") ? 0 : 1;     // tuning hook (tools/ only): solver without the mechanism screen
+    if (const char *mb = getenv("BW_CAND_CACHE_MB")) h->cand_budget = (size_t)strtoull(mb, nullptr, 10) << 20;
     P.collision_tol = cfg->collision_tol;
     for (int k = 0; k < 3; k++) { P.bounds_lo[k] = cfg->bounds_lo[k]; P.bounds_hi[k] = cfg->bounds_hi[k]; }
 
@@ -319,6 +375,11 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     h->P.n_shapes = n;
     h->smem_step = step_smem_bytes(h->P.max_blocks, h->P.max_itf, n);
     h->shapes_loaded = true;
+    h->n_groups = 0;
+    for (int i = 0; i < n; i++)
+        for (int f = 0; f < dev[i].n_faces; f++)
+            if ((dev[i].target_faces_mask >> f) & 1u) h->n_groups++;
+    h->cand_dirty = true;
     return BW_OK;
 }
 
@@ -582,16 +643,19 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
                          memcmp(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground) != 0)) {
         memcpy(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground);
         h->n_ground_cached = n_ground;
+        h->cand_dirty = true;
         CU(cudaMemcpyAsync(h->d_ground, h->ground_cached, sizeof(double) * n_ground, cudaMemcpyHostToDevice, h->stream));
     }
     if (n_offsets > 0 && (h->n_offsets_cached != n_offsets ||
                           memcmp(h->offsets_cached, h_offset_values, sizeof(double) * n_offsets) != 0)) {
         memcpy(h->offsets_cached, h_offset_values, sizeof(double) * n_offsets);
         h->n_offsets_cached = n_offsets;
+        h->cand_dirty = true;
         CU(cudaMemcpyAsync(h->d_offsets, h->offsets_cached, sizeof(double) * n_offsets, cudaMemcpyHostToDevice, h->stream));
     }
+    if (int rc = prepare_cand_cache(h, n_ground, n_offsets)) return rc;
     launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
-                     d_action_bits, h->stream);
+                     d_action_bits, h->cand, h->stream);
     h->launches++;
     CU(cudaGetLastError());
     return BW_OK;

@@ -26,9 +26,18 @@ void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_bl
 // bw_actions.cu
 void launch_query_placement(const Params &P, const bw_action *d_actions, double xl, double xh, double zl, double zh,
                             bw_block *d_blocks, uint8_t *d_flags, cudaStream_t stream);
+// cache of candidate placements (enumerate_kernel<true>): per environment `slots` = groups x `spg` slots, one per
+// (shape, face) group and ground offset / (target block, target face, offset)
+struct CandCache {
+    uint32_t *meta = nullptr;   // [E][slots] SLOT_VALID | SLOT_BAD | first window row << 8 | window rows
+    uint64_t *bits = nullptr;   // [E][slots][IMG] raster rows (only the window rows are meaningful)
+    Pose *pose = nullptr;       // [E][NB] pose and
+    uint8_t *shape = nullptr;   // [E][NB] shape of the block the slots of (block, *) were filled for
+    int32_t slots = 0, spg = 0;
+};
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      cudaStream_t stream);
+                      const CandCache &cache, cudaStream_t stream);
 void launch_select_random(const Params &P, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
                           int amax, uint64_t seed, bw_action *d_actions, int32_t *d_index, cudaStream_t stream);
 

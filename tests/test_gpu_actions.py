@@ -90,3 +90,55 @@ def test_hexagon_candidates_and_random_policy():
     valid = c["valid"].cpu().numpy()
     for e, idx in enumerate(i1.cpu().numpy()):
         assert idx >= 0 and valid[e, idx] == 1
+
+
+def test_candidate_cache_matches_plain_kernel(monkeypatch):
+    """bw_enumerate_actions keeps candidate placements and rasters between calls (enumerate_kernel<true>); a handle
+    created with BW_CAND_CACHE_MB=0 runs the plain kernel.  Same rollouts, same outputs: candidates, validity and
+    rasters of every call -- through auto-resets, a change of the offset table and a reset with pre-placed blocks."""
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    E, amax = 48, 512
+    urdfs = [H.URDF["trapezoid"], H.URDF["hexagon"]]
+    task = dict(obstacles=[(0.6, 0, 0.3), (1.2, 0, 0.3)], targets=[(2.4, 0, 0.3)])
+    cached = BatchedAssemblyGym(E, urdfs, max_steps=10)
+    monkeypatch.setenv("BW_CAND_CACHE_MB", "0")
+    plain = BatchedAssemblyGym(E, urdfs, max_steps=10)
+    monkeypatch.delenv("BW_CAND_CACHE_MB")
+    for env in (cached, plain):
+        env.reset(task)
+
+    def compare(offsets, tag):
+        a = cached.enumerate_actions(XG, offsets, amax=amax)
+        b = plain.enumerate_actions(XG, offsets, amax=amax)
+        cached.sync(); plain.sync()
+        n = a["n"].cpu().numpy()
+        assert np.array_equal(n, b["n"].cpu().numpy()), tag
+        sz = cached.dt["action"].itemsize
+        ca = a["cand"].cpu().numpy().reshape(E, amax, sz)
+        cb = b["cand"].cpu().numpy().reshape(E, amax, sz)
+        va, vb = a["valid"].cpu().numpy(), b["valid"].cpu().numpy()
+        ba, bb = a["bits"].cpu().numpy(), b["bits"].cpu().numpy()
+        for e in range(E):
+            assert np.array_equal(ca[e, :n[e]], cb[e, :n[e]]), (tag, e)
+            assert np.array_equal(va[e, :n[e]], vb[e, :n[e]]), (tag, e)
+            assert np.array_equal(ba[e, :n[e]], bb[e, :n[e]]), (tag, e)
+        return int(n.max()), int(va.sum())
+
+    n_max = n_valid = 0
+    for k in range(36):
+        offsets = (0.0,) if k < 24 else (0.0, 0.25)          # the offset table changes: every slot is stale
+        m, v = compare(offsets, k)
+        n_max, n_valid = max(n_max, m), n_valid + v
+        acts, _ = cached.select_random(seed=1000 + k)
+        acts = acts.clone()
+        cached.step(acts); plain.step(acts)
+        if k == 17:                                           # reset with pre-placed blocks, all environments
+            pre = dict(task, blocks=[(-1.5, 0.5, 1.0, 0.0, 1), (3.5, 0.4, 0.0, 1.0, 0)])     # (x, z, c, s, shape)
+            cached.reset(pre); plain.reset(pre)
+        else:
+            cached.reset_done(); plain.reset_done()
+    assert n_max > 150 and n_valid > 5000
+    oa, ob = cached.read_out(), plain.read_out()
+    assert np.array_equal(oa["n_blocks"], ob["n_blocks"])
+    cached.close(); plain.close()
