@@ -247,24 +247,43 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         __syncthreads();
         // ---- phase B: thread per (candidate, row of its window)
         const int npairs = c_rowstart[nchunk];
-        for (int q = tid; q < npairs; q += ENUM_THREADS) {
-            int lo = 0, hi = nchunk - 1;            // largest t with rowstart[t] <= q
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
+        // two pairs per trip: the loads of cached rows (global memory, possibly HBM) of both are in flight
+        // before either is used
+        for (int q0 = tid; q0 < npairs; q0 += 2 * ENUM_THREADS) {
+            int tt[2], rr[2];
+            uint64_t bb[2];
+            bool live[2], hit[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int q = q0 + u * ENUM_THREADS;
+                live[u] = q < npairs;
+                hit[u] = false;
+                tt[u] = 0; rr[u] = 0; bb[u] = 0;
+                if (live[u]) {
+                    int lo = 0, hi = nchunk - 1;            // largest t with rowstart[t] <= q
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
+                    }
+                    tt[u] = lo;
+                    rr[u] = c_ilo[lo] + (q - c_rowstart[lo]);
+                    hit[u] = CACHED && c_cached[lo];
+                    if (hit[u]) bb[u] = __ldcs(&C.bits[((size_t)e * C.slots + c_slot[lo]) * IMG + rr[u]]);
+                }
             }
-            const int t = lo;
-            const int row = c_ilo[t] + (q - c_rowstart[t]);
-            uint64_t bits;
-            if (CACHED && c_cached[t]) {
-                bits = C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row];
-            } else {
-                bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
-                                              c_jhi[t], row);
-                if (CACHED && c_slot[t] >= 0) C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row] = bits;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!live[u]) continue;
+                const int t = tt[u], row = rr[u];
+                uint64_t bits = bb[u];
+                if (!hit[u]) {
+                    bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
+                                                  c_jhi[t], row);
+                    if (CACHED && c_slot[t] >= 0) C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row] = bits;
+                }
+                if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
+                if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
             }
-            if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
-            if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
         }
         __syncthreads();
         if (tid < nchunk) valid[(size_t)e * amax + base + tid] = (!c_bad[tid] && !c_overlap[tid]) ? 1 : 0;
