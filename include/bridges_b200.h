@@ -228,7 +228,11 @@ int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_
  * the reference's generation order, Amax per env; d_n_cand[e] of them are meaningful.
  * d_valid[e,a] = 1 iff the candidate survives filter_actions (bounds test of
  * collision_on_action gym_env.py:304-323, no raster overlap with blocks / obstacles).
- * d_action_bits (optional): [E,Amax,64] u64, bit x of word r = pixel (row r, col x). */
+ * d_action_bits (optional): [E,Amax,64] u64, bit x of word r = pixel (row r, col x).
+ * The handle keeps the placement, bounds flag and raster rows of every possible candidate between
+ * calls (device memory: E x groups x (n_ground + max_blocks*6*n_offsets) x 516 B, allocated by the first
+ * call; results are identical to recomputing them).  The environment variable BW_CAND_CACHE_MB, read by
+ * bw_create, bounds that memory (default 4096; 0 = always recompute). */
 int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
                          const double *h_offset_values, int32_t n_offsets, int32_t amax,
                          bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits);
