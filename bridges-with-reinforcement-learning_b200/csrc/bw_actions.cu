@@ -59,14 +59,22 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     __shared__ uint8_t s_free_b[NB * NF], s_free_f[NB * NF];
     __shared__ uint8_t s_grp_s[BW_MAX_SHAPES * NF], s_grp_f[BW_MAX_SHAPES * NF];
     __shared__ int s_nfree, s_ngrp;
-    // per-chunk candidate tables
-    __shared__ double c_nx[ENUM_CHUNK][NF], c_nz[ENUM_CHUNK][NF], c_cx[ENUM_CHUNK][NF], c_cz[ENUM_CHUNK][NF],
-        c_inx[ENUM_CHUNK][NF];
-    __shared__ int8_t c_nf[ENUM_CHUNK], c_jlo[ENUM_CHUNK], c_jhi[ENUM_CHUNK], c_ilo[ENUM_CHUNK], c_bad[ENUM_CHUNK];
-    __shared__ int c_rowstart[ENUM_CHUNK + 1];
-    __shared__ int c_overlap[ENUM_CHUNK];
-    __shared__ int c_slot[ENUM_CHUNK];          // cache slot of the candidate (-1: none)
-    __shared__ uint8_t c_cached[ENUM_CHUNK];    // its slot was valid: raster rows are read, not computed
+    // A chunk is CHUNK consecutive candidates.  Only candidates that have to be posed and rasterised ("misses":
+    // all of them without the cache) need a row of the posed-face tables; a chunk ends early when it would
+    // hold more than MISS_CAP of them.
+    constexpr int CHUNK = CACHED ? 2 * ENUM_CHUNK : ENUM_CHUNK;
+    constexpr int MISS_CAP = ENUM_CHUNK;
+    constexpr int CPL = CHUNK / 32;             // candidates per lane in the row-count scan
+    __shared__ double c_nx[MISS_CAP][NF], c_nz[MISS_CAP][NF], c_cx[MISS_CAP][NF], c_cz[MISS_CAP][NF],
+        c_inx[MISS_CAP][NF];
+    __shared__ int8_t c_nf[MISS_CAP], c_jlo[MISS_CAP], c_jhi[MISS_CAP];
+    __shared__ int8_t c_ilo[CHUNK], c_bad[CHUNK];
+    __shared__ uint8_t c_mi[CHUNK];             // row of the posed-face tables (misses)
+    __shared__ int c_rowstart[CHUNK + 1];
+    __shared__ int c_overlap[CHUNK];
+    __shared__ int c_slot[CHUNK];               // cache slot of the candidate (-1: none)
+    __shared__ uint8_t c_cached[CHUNK];         // its slot was valid: raster rows are read, not computed
+    __shared__ int s_wmiss[ENUM_THREADS / 32], s_ncut;
     __shared__ unsigned s_inval;
 
     const int n = P.n_blocks[e];
@@ -152,17 +160,23 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
 
     // only the first `count` slots are meaningful (n_cand); the rest of the caller's buffers is left alone
-    for (int base = 0; base < count; base += ENUM_CHUNK) {
-        const int nchunk = min(ENUM_CHUNK, count - base);
-        // ---- phase A: thread per candidate
-        if (tid < nchunk) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    while (base < count) {
+        const int nch = min(CHUNK, count - base);
+        // ---- phase A0: thread per candidate -- the action, its cache slot, hit or miss
+        const bool active = tid < nch;
+        bw_action act;
+        act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
+        act.shape = 0; act.face = 0; act.offset_x = 0.0;
+        int slot = -1, rows = 0, ilo = 0;
+        bool bad = false, hit = false;
+        if (tid == 0) s_ncut = nch;
+        if (active) {
             const int a = base + tid;
-            bw_action act;
-            act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
             const int g = a / per_group, w = a - g * per_group;
             act.shape = s_grp_s[g];
             act.face = s_grp_f[g];
-            int slot = -1;
             if (w < n_ground) {
                 act.offset_x = ground[w];
                 slot = g * C.spg + w;
@@ -175,22 +189,33 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             }
             cand[(size_t)e * amax + a] = act;
             if (!CACHED || env_full) slot = -1;
-            int rows = 0;
-            bool bad = false, hit = false;
             if (CACHED && slot >= 0) {
                 const uint32_t m = C.meta[(size_t)e * C.slots + slot];
                 if (m & SLOT_VALID) {
                     hit = true;
                     bad = (m & SLOT_BAD) != 0;
                     rows = (int)(m & 0xffu);
-                    c_ilo[tid] = (int8_t)((m >> 8) & 0xffu);
+                    ilo = (int)((m >> 8) & 0xffu);
                 }
             }
-            if (!hit) {
+        }
+        // misses take the rows of the posed-face tables in candidate order; the chunk is cut in front of the
+        // candidate that would need row MISS_CAP (it starts the next chunk)
+        const bool miss = active && !hit;
+        const unsigned mb = __ballot_sync(0xffffffffu, miss);
+        if (lane == 0) s_wmiss[warp] = __popc(mb);
+        __syncthreads();
+        int before = __popc(mb & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; w++) before += s_wmiss[w];
+        const bool included = active && (before + (miss ? 1 : 0) <= MISS_CAP);
+        if (active && !included) atomicMin(&s_ncut, tid);
+        // ---- phase A1: the misses are posed (FP64 work that is uniform for a candidate: one thread each)
+        if (included) {
+            if (miss) {
+                const int mi = before;
                 Pose ps;
                 const int err = place_block(P, s_pose, s_shape, n, act, ps);
                 bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
-                int ilo = 0;
                 if (!bad) {
                     const ShapeDev &sh = P.shapes[act.shape];
                     // collision_on_action: any vertex outside the window (gym_env.py:304-323)
@@ -204,11 +229,11 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
                     PosedShape o;
                     pose_shape(P, sh, ps, o);
                     for (int k = 0; k < NF; k++) {
-                        c_nx[tid][k] = o.nx[k]; c_nz[tid][k] = o.nz[k]; c_cx[tid][k] = o.cx[k]; c_cz[tid][k] = o.cz[k];
-                        c_inx[tid][k] = o.inv_nx[k];
+                        c_nx[mi][k] = o.nx[k]; c_nz[mi][k] = o.nz[k]; c_cx[mi][k] = o.cx[k]; c_cz[mi][k] = o.cz[k];
+                        c_inx[mi][k] = o.inv_nx[k];
                     }
-                    c_nf[tid] = (int8_t)o.n_faces;
-                    c_jlo[tid] = (int8_t)o.j_lo; c_jhi[tid] = (int8_t)o.j_hi; c_ilo[tid] = (int8_t)o.i_lo;
+                    c_nf[mi] = (int8_t)o.n_faces;
+                    c_jlo[mi] = (int8_t)o.j_lo; c_jhi[mi] = (int8_t)o.j_hi;
                     ilo = o.i_lo;
                     if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
                 }
@@ -218,30 +243,43 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
                     else
                         slot = -1;
                 }
+                c_mi[tid] = (uint8_t)mi;
             }
+            c_ilo[tid] = (int8_t)ilo;
             c_slot[tid] = slot;
             c_cached[tid] = hit ? 1 : 0;
             c_bad[tid] = bad ? 1 : 0;
             c_overlap[tid] = 0;
             c_rowstart[tid + 1] = rows;
         }
+        __syncthreads();
+        const int nchunk = s_ncut;                  // candidates base .. base + nchunk - 1 are finished in this trip
         if (action_bits != nullptr) {   // rows outside the windows are zero
             uint64_t *dst = action_bits + ((size_t)e * amax + base) * IMG;
             for (int q = tid; q < nchunk * IMG; q += ENUM_THREADS) dst[q] = 0;
         }
-        __syncthreads();
         if (tid < 32) {
-            // inclusive scan of the row counts (two candidates per lane), c_rowstart[t + 1] = rows of 0..t
-            const int a0 = (2 * tid < nchunk) ? c_rowstart[2 * tid + 1] : 0;
-            const int a1 = (2 * tid + 1 < nchunk) ? c_rowstart[2 * tid + 2] : 0;
-            int inc = a0 + a1;
+            // inclusive scan of the row counts (CPL candidates per lane), c_rowstart[t + 1] = rows of 0..t
+            int av[CPL], sum = 0;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) {
+                const int idx = CPL * tid + j;
+                av[j] = (idx < nchunk) ? c_rowstart[idx + 1] : 0;
+                sum += av[j];
+            }
+            int inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int v = __shfl_up_sync(0xffffffffu, inc, o);
                 if (tid >= o) inc += v;
             }
-            if (2 * tid < nchunk) c_rowstart[2 * tid + 1] = inc - a1;
-            if (2 * tid + 1 < nchunk) c_rowstart[2 * tid + 2] = inc;
+            int run = inc - sum;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) {
+                const int idx = CPL * tid + j;
+                run += av[j];
+                if (idx < nchunk) c_rowstart[idx + 1] = run;
+            }
             if (tid == 0) c_rowstart[0] = 0;
         }
         __syncthreads();
@@ -252,12 +290,12 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         for (int q0 = tid; q0 < npairs; q0 += 2 * ENUM_THREADS) {
             int tt[2], rr[2];
             uint64_t bb[2];
-            bool live[2], hit[2];
+            bool live[2], hitv[2];
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int q = q0 + u * ENUM_THREADS;
                 live[u] = q < npairs;
-                hit[u] = false;
+                hitv[u] = false;
                 tt[u] = 0; rr[u] = 0; bb[u] = 0;
                 if (live[u]) {
                     int lo = 0, hi = nchunk - 1;            // largest t with rowstart[t] <= q
@@ -267,8 +305,8 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
                     }
                     tt[u] = lo;
                     rr[u] = c_ilo[lo] + (q - c_rowstart[lo]);
-                    hit[u] = CACHED && c_cached[lo];
-                    if (hit[u]) bb[u] = __ldcs(&C.bits[((size_t)e * C.slots + c_slot[lo]) * IMG + rr[u]]);
+                    hitv[u] = CACHED && c_cached[lo];
+                    if (hitv[u]) bb[u] = __ldcs(&C.bits[((size_t)e * C.slots + c_slot[lo]) * IMG + rr[u]]);
                 }
             }
 #pragma unroll
@@ -276,9 +314,10 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
                 if (!live[u]) continue;
                 const int t = tt[u], row = rr[u];
                 uint64_t bits = bb[u];
-                if (!hit[u]) {
-                    bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t], c_jlo[t],
-                                                  c_jhi[t], row);
+                if (!hitv[u]) {
+                    const int mi = c_mi[t];
+                    bits = raster_row_posed_mixed(P, c_nf[mi], c_nx[mi], c_nz[mi], c_cx[mi], c_cz[mi], c_inx[mi],
+                                                  c_jlo[mi], c_jhi[mi], row);
                     if (CACHED && c_slot[t] >= 0) C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row] = bits;
                 }
                 if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
@@ -288,6 +327,7 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         __syncthreads();
         if (tid < nchunk) valid[(size_t)e * amax + base + tid] = (!c_bad[tid] && !c_overlap[tid]) ? 1 : 0;
         __syncthreads();
+        base += nchunk;
     }
 }
 
