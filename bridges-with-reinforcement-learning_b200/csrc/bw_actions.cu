@@ -75,6 +75,8 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     __shared__ int c_slot[CHUNK];               // cache slot of the candidate (-1: none)
     __shared__ uint8_t c_cached[CHUNK];         // its slot was valid: raster rows are read, not computed
     __shared__ int s_wmiss[ENUM_THREADS / 32], s_ncut;
+    constexpr int OWNER_CAP = 2048;             // (candidate, row) pairs of a chunk with a direct owner entry
+    __shared__ uint8_t c_owner[OWNER_CAP];      // pair -> candidate of the chunk
     __shared__ unsigned s_inval;
 
     const int n = P.n_blocks[e];
@@ -277,6 +279,8 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
 #pragma unroll
             for (int j = 0; j < CPL; j++) {
                 const int idx = CPL * tid + j;
+                // the pairs run .. run + av[j] - 1 belong to candidate idx (phase B looks its pair up here)
+                for (int r = run; r < run + av[j] && r < OWNER_CAP; r++) c_owner[r] = (uint8_t)idx;
                 run += av[j];
                 if (idx < nchunk) c_rowstart[idx + 1] = run;
             }
@@ -298,10 +302,15 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
                 hitv[u] = false;
                 tt[u] = 0; rr[u] = 0; bb[u] = 0;
                 if (live[u]) {
-                    int lo = 0, hi = nchunk - 1;            // largest t with rowstart[t] <= q
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
+                    int lo = 0;                             // largest t with rowstart[t] <= q
+                    if (q < OWNER_CAP) {
+                        lo = c_owner[q];
+                    } else {
+                        int hi = nchunk - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
+                        }
                     }
                     tt[u] = lo;
                     rr[u] = c_ilo[lo] + (q - c_rowstart[lo]);
