@@ -57,3 +57,35 @@ def test_create_without_gpu_fails_loudly():
     assert rc != 0
     assert b"no CUDA device" in lib.bw_last_error(handle)
     lib.bw_destroy(handle)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package names it, and importing the whole package
+    (adapter, drop-in classes, rollout helpers) leaves it out of sys.modules."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "bridges-with-reinforcement-learning_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(d, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(d, f)
+    code = ("import sys; import bridges_b200, bridges_b200.lib, bridges_b200.envs.batched, bridges_b200.envs.gym_env, "
+            "bridges_b200.envs.assembly_env, bridges_b200.rollout, bridges_b200.sharding; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; "
+            "print('LOADED', bad)")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "LOADED []" in out.stdout, out.stdout
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU implementation behind the package: a missing libbridges_b200.so is an error, not a fallback."""
+    import subprocess
+    import sys
+    code = ("import os; os.environ['BRIDGES_B200_LIB'] = %r; from bridges_b200 import lib\n"
+            "try:\n    lib.load()\n    print('LOADED')\nexcept Exception as e:\n    print('RAISED', type(e).__name__)\n"
+            % str(tmp_path / "absent.so"))
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "RAISED" in out.stdout and "LOADED" not in out.stdout, out.stdout
