@@ -147,7 +147,20 @@ static void default_marker(ShapeDev &d) {
 
 // Sizes (and, when the block library or the offset tables changed, clears) the candidate cache of
 // bw_enumerate_actions.  Layout: per environment groups x (n_ground + max_blocks * NF * n_offsets) slots of
-// 512 B raster + 4 B flags.  A layout that does not fit the budget switches the cache off (plain kernel).
+// 512 B raster + 4 B flags.  A layout that does not fit the budget -- or the device memory that is left --
+// switches the cache off (plain kernel).
+static void release_cand_cache(bw_handle *h) {
+    CandCache &c = h->cand;
+    void *old[4] = {c.meta, c.bits, c.pose, c.shape};
+    for (void *q : old) {
+        if (!q) continue;
+        cudaFree(q);
+        for (size_t i = 0; i < h->allocs.size(); i++)
+            if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
+    }
+    c = CandCache();
+}
+
 static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
     const int spg = n_ground + h->P.max_blocks * NF * n_offsets;
     const int slots = h->n_groups * spg;
@@ -157,31 +170,26 @@ static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
     if (slots <= 0 || need > h->cand_budget) {
         if (c.meta) {
             CU(cudaStreamSynchronize(h->stream));
-            void *old[4] = {c.meta, c.bits, c.pose, c.shape};
-            for (void *q : old) {
-                cudaFree(q);
-                for (size_t i = 0; i < h->allocs.size(); i++)
-                    if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
-            }
+            release_cand_cache(h);
         }
-        c = CandCache();
         return BW_OK;
     }
     if (c.meta == nullptr || c.slots != slots || c.spg != spg) {
         if (c.meta) {
             CU(cudaStreamSynchronize(h->stream));
-            void *old[4] = {c.meta, c.bits, c.pose, c.shape};
-            for (void *q : old) {
-                cudaFree(q);
-                for (size_t i = 0; i < h->allocs.size(); i++)
-                    if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
-            }
-            c = CandCache();
+            release_cand_cache(h);
         }
-        CU(dev_alloc(h, &c.meta, E * slots, false));
-        CU(dev_alloc(h, &c.bits, E * slots * IMG, false));
-        CU(dev_alloc(h, &c.pose, E * NB, false));
-        CU(dev_alloc(h, &c.shape, E * NB, false));
+        cudaError_t e = dev_alloc(h, &c.meta, E * slots, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.bits, E * slots * IMG, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.pose, E * NB, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.shape, E * NB, false);
+        if (e != cudaSuccess) {
+            // no room for it next to the caller's own allocations: enumerate without the cache from now on
+            cudaGetLastError();
+            release_cand_cache(h);
+            h->cand_budget = 0;
+            return BW_OK;
+        }
         c.slots = slots;
         c.spg = spg;
         h->cand_dirty = true;
