@@ -30,3 +30,10 @@ def test_task_spec_and_config_name_the_workload():
     assert bridge["shapes"] == ["trapezoid", "hexagon"] and len(bridge["obstacles"]) == 5
     cfg = bench.config_dict(_args(task="bridge", max_steps=15), 8)
     assert "horizontal_bridge_setup(num_obstacles=5)" in cfg["workload"] and "x8" in cfg["parallelism"]
+
+
+def test_cpu_arm_steps_both_tasks():
+    """The CPU arm (restated reference env, oracle/) advances on the tower and on the bridge task."""
+    for spec, max_steps in ((2, 10), (bench.task_spec(_args(task="bridge", max_steps=15)), 15)):
+        steps, timed = bench._cpu_worker((1000, 20.0, spec, max_steps, 6, 1, 0.0))
+        assert steps >= 6 and timed > 0.0
