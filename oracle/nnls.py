@@ -67,7 +67,8 @@ def nnls_rays(R, b, tol=1e-11, max_iter=None):
         return s
 
     while iterations < max_iter:
-        res = b - (R[:, order] @ x[order] if order else 0.0)
+        # residual of the passive-set solution without touching R: Q [0; (Q^T b)_tail]
+        res = Qt[len(order):, :].T @ qb[len(order):]
         w = R.T @ res
         w[order] = -np.inf
         w[barred] = -np.inf
@@ -133,8 +134,8 @@ def nnls_rays(R, b, tol=1e-11, max_iter=None):
                     qb[i:i + 2] = G @ qb[i:i + 2]
                     U[i + 1, i] = 0.0
                 del order[k]
-    res = b - (R[:, order] @ x[order] if order else 0.0)
-    return NNLSResult(x, float(np.linalg.norm(res)), res, iterations, removals, chain)
+    res = Qt[len(order):, :].T @ qb[len(order):]
+    return NNLSResult(x, float(np.linalg.norm(qb[len(order):])), res, iterations, removals, chain)
 
 
 def equilibrium_residual_nnls(A, b, mu):
