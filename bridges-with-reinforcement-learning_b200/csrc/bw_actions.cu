@@ -157,7 +157,12 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     const int per_group = n_ground + s_nfree * n_offsets;
     const int total = s_ngrp * per_group;
     const int count = min(total, amax);
-    if (tid == 0) n_cand[e] = count;
+    if (tid == 0) {
+        n_cand[e] = count;
+        // generate_actions (actions.py:7-52) is unbounded: a list cut to the caller's capacity is reported
+        // (bw_candidate_overflow), never dropped silently
+        if (total > amax) atomicMax(P.cand_need, total);
+    }
     const double eps = 1e-6;
     const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
 
@@ -455,6 +460,10 @@ __global__ void select_random_kernel(Params P, const bw_action *__restrict__ can
             }
         }
         act = cand[(size_t)e * amax + chosen];
+    } else {
+        // no candidate left: the episode ends here (rollout_episode, successor_dqn.py:409-411); the no-op
+        // action leaves the flag alone and the next bw_reset_done starts the environment afresh
+        P.done[e] = 1;
     }
     actions[e] = act;
     if (index != nullptr) index[e] = chosen;

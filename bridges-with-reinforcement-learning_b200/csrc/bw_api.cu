@@ -19,6 +19,7 @@ struct bw_handle {
     bool own_stream = false;
     bool shapes_loaded = false;
     bool timing = false;
+    bool resets_unchecked = false;   // a bw_reset with tasks ran since the last look at P.reset_err
     bool force_staged = false;   // bw_set_host_transfer(h, 1): *_host calls always stage through device buffers
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int smem_step = 0;
@@ -316,6 +317,8 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     CU(dev_alloc(h, &P.done, E));
     CU(dev_alloc(h, &P.last_out, E));
     CU(dev_alloc(h, &P.su_valid, E));
+    CU(dev_alloc(h, &P.cand_need, 1));
+    CU(dev_alloc(h, &P.reset_err, 1));
     {
         std::vector<double> mu(E, cfg->mu);
         CU(cudaMemcpyAsync(P.mu, mu.data(), sizeof(double) * E, cudaMemcpyHostToDevice, h->stream));
@@ -363,9 +366,25 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     return BW_OK;
 }
 
+// tasks refused by reset_kernel since the last check (the kernel cannot return a status itself)
+static int check_reset_errors(bw_handle *h) {
+    int32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, h->P.reset_err, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (bad == 0) return BW_OK;
+    CU(cudaMemsetAsync(h->P.reset_err, 0, sizeof(int32_t), h->stream));
+    return fail(h, BW_ERR_INVALID, "reset: %d task(s) refused (pre-placed blocks exceed max_steps / BW_MAX_BLOCKS, "
+                                   "or a shape index / obstacle / target count out of range); those environments were left empty",
+                (int)bad);
+}
+
 int bw_sync(bw_handle *h) {
     if (!h) return BW_ERR_INVALID;
     CU(cudaStreamSynchronize(h->stream));
+    if (h->resets_unchecked) {
+        h->resets_unchecked = false;
+        return check_reset_errors(h);
+    }
     return BW_OK;
 }
 
@@ -379,6 +398,8 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     }
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(h->d_shapes, dev, sizeof(ShapeDev) * n, cudaMemcpyHostToDevice, h->stream));
+    // verdicts of the last step describe blocks of the old library
+    CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->P.n_shapes = n;
     h->smem_step = step_smem_bytes(h->P.max_blocks, h->P.max_itf, n);
@@ -419,6 +440,9 @@ int bw_set_mu(bw_handle *h, const double *h_mu) {
     if (!h || !h_mu) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(h->P.mu, h_mu, sizeof(double) * h->P.E, cudaMemcpyHostToDevice, h->stream));
+    // the released-block verdict of the last step was computed with the old coefficients: it must not
+    // stand in for the next step's frozen solve (step_kernel, prev_released_ok)
+    CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -460,6 +484,7 @@ int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
     launch_reset(h->P, d_tasks, d_mask, 0, h->stream);
     h->launches++;
     if (d_tasks != nullptr) {
+        h->resets_unchecked = true;
         // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
         launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr,
                     0, h->smem_step, h->stream);
@@ -474,14 +499,26 @@ int bw_reset_host(bw_handle *h, const bw_task *h_tasks, const uint8_t *h_mask) {
     CU(cudaSetDevice(h->cfg.device));
     const int E = h->P.E;
     if (h_tasks) {
+        for (int e = 0; e < E; e++) {
+            if (h_mask && !h_mask[e]) continue;
+            const bw_task &t = h_tasks[e];
+            if (t.n_blocks < 0 || t.n_blocks > h->P.max_blocks)
+                return fail(h, BW_ERR_CAPACITY, "task %d: %d pre-placed blocks, this handle holds %d (max_steps / BW_MAX_BLOCKS)",
+                            e, t.n_blocks, h->P.max_blocks);
+            if (t.n_obstacles < 0 || t.n_obstacles > BW_MAX_OBSTACLES || t.n_targets < 0 || t.n_targets > BW_MAX_TARGETS)
+                return fail(h, BW_ERR_CAPACITY, "task %d: obstacle / target count out of range", e);
+            for (int i = 0; i < t.n_blocks; i++)
+                if (t.blocks[i].shape < 0 || t.blocks[i].shape >= h->P.n_shapes)
+                    return fail(h, BW_ERR_INVALID, "task %d: pre-placed block %d has shape index %d, the library has %d shapes",
+                                e, i, t.blocks[i].shape, h->P.n_shapes);
+        }
         if (!h->d_tasks) CU(dev_alloc(h, &h->d_tasks, E));
         CU(cudaMemcpyAsync(h->d_tasks, h_tasks, sizeof(bw_task) * E, cudaMemcpyHostToDevice, h->stream));
     }
     if (h_mask) CU(cudaMemcpyAsync(h->d_mask, h_mask, E, cudaMemcpyHostToDevice, h->stream));
     int rc = bw_reset(h, h_tasks ? h->d_tasks : nullptr, h_mask ? h->d_mask : nullptr);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));
-    return BW_OK;
+    return bw_sync(h);
 }
 
 int bw_reset_done(bw_handle *h) {
@@ -666,6 +703,15 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
                      d_action_bits, h->cand, h->stream);
     h->launches++;
     CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_candidate_overflow(bw_handle *h, int32_t *h_needed) {
+    if (!h || !h_needed) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h_needed, h->P.cand_need, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(h->P.cand_need, 0, sizeof(int32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
 

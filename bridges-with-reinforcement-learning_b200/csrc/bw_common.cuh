@@ -88,6 +88,8 @@ struct Params {
     uint8_t *done;             // [E] last step returned terminated | truncated
     bw_step_out *last_out;     // [E] copy of the last step result (binary features of observe)
     uint8_t *su_valid;         // [E] last_out[e].stable_unfrozen describes the current blocks and supports
+    int32_t *cand_need;        // [1] largest untruncated candidate count an enumeration had to cut to `amax`
+    int32_t *reset_err;        // [1] environments whose reset task was refused (bad shape index / too many blocks)
 };
 
 // ---------------------------------------------------------------- placement (K1)

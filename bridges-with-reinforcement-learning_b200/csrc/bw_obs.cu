@@ -48,7 +48,14 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
                 tk.target_xz[i][0] = t.target_xz[i][0];
                 tk.target_xz[i][1] = t.target_xz[i][1];
             }
-            int nb = min(max(t.n_blocks, 0), P.max_blocks);
+            // a task this handle cannot hold (more pre-placed blocks than max_steps leaves room for, a shape
+            // index outside the library) is refused as a whole: the environment starts empty and the call
+            // that synchronises next reports it (bw_reset_host / bw_sync)
+            int nb = max(t.n_blocks, 0);
+            bool ok = nb <= P.max_blocks && t.n_obstacles >= 0 && t.n_obstacles <= BW_MAX_OBSTACLES &&
+                      t.n_targets >= 0 && t.n_targets <= BW_MAX_TARGETS;
+            for (int i = 0; ok && i < nb; i++) ok = t.blocks[i].shape >= 0 && t.blocks[i].shape < P.n_shapes;
+            if (!ok) { nb = 0; atomicAdd(P.reset_err, 1); }
             uint32_t sm = 0;
             for (int i = 0; i < nb; i++) {
                 Pose ps;

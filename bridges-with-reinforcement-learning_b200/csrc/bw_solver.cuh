@@ -651,7 +651,14 @@ struct Solver {
             bool changed = true;               // a contact changed its cone face in that step
 #pragma unroll 1
             for (int it = 0; it < MAX_NEWTON; it++) {
-                if (implied_by >= 0 && *sibling == implied_by) { status = 3; break; }
+                // one lane reads the flag and broadcasts it: the exit must be taken by the whole warp or not at
+                // all (the code below is full of full-mask shuffles), and the sibling may publish between two
+                // lanes' loads
+                if (implied_by >= 0) {
+                    int sv = (lane == 0) ? *sibling : 0;
+                    sv = __shfl_sync(FULL, sv, 0);
+                    if (sv == implied_by) { status = 3; break; }
+                }
                 BW_T0(t_a);
                 double gn2, rr2;
                 rows_pass(inv_rho, rhs, gn2, rr2);

@@ -124,6 +124,36 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n
 
 int step_smem_bytes(int max_blocks, int max_itf, int n_shapes) { return make_layout(max_blocks, max_itf, n_shapes).total; }
 
+// The optional image outputs of a step (bw_obs_out): the raster of all blocks as f32 [1,64,64] / u8 [64,64] /
+// bit-packed [64], from the CTA's shared copy `bits` (64 threads, 16-byte coalesced streaming stores).
+__device__ __forceinline__ void write_obs_images(const bw_obs_out &obs, const uint64_t *bits, int e, int tid) {
+    if (obs.block_img_f32 != nullptr) {
+        float4 *dst = reinterpret_cast<float4 *>(obs.block_img_f32 + (size_t)e * IMG * IMG);
+#pragma unroll 4
+        for (int i = 0; i < IMG * IMG / 4 / 64; i++) {
+            const int q = i * 64 + tid;            // float4 index: row = q / 16, nibble = q % 16
+            const unsigned nib = (unsigned)(bits[q >> 4] >> (4 * (q & 15))) & 0xfu;
+            __stcs(dst + q, make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f,
+                                        (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f));
+        }
+    }
+    if (obs.block_bits != nullptr) obs.block_bits[(size_t)e * IMG + tid] = bits[tid];
+    if (obs.block_img_u8 != nullptr) {
+        uint4 *dst = reinterpret_cast<uint4 *>(obs.block_img_u8 + (size_t)e * IMG * IMG);
+#pragma unroll
+        for (int i = 0; i < IMG * IMG / 16 / 64; i++) {
+            const int q = i * 64 + tid;            // uint4 index: row = q / 4, 16-pixel segment = q % 4
+            const unsigned seg = (unsigned)(bits[q >> 2] >> (16 * (q & 3))) & 0xffffu;
+            uint4 v;
+            v.x = (seg & 1u) | ((seg & 2u) << 7) | ((seg & 4u) << 14) | ((seg & 8u) << 21);
+            v.y = ((seg >> 4) & 1u) | (((seg >> 4) & 2u) << 7) | (((seg >> 4) & 4u) << 14) | (((seg >> 4) & 8u) << 21);
+            v.z = ((seg >> 8) & 1u) | (((seg >> 8) & 2u) << 7) | (((seg >> 8) & 4u) << 14) | (((seg >> 8) & 8u) << 21);
+            v.w = ((seg >> 12) & 1u) | (((seg >> 12) & 2u) << 7) | (((seg >> 12) & 4u) << 14) | (((seg >> 12) & 8u) << 21);
+            __stcs(dst + q, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 template <bool TWO>
 __global__ void __launch_bounds__(64)
@@ -236,13 +266,39 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     const int nbody = n + 1;
     const bool placed = sh_placed != 0;
     if (sh_error != 0) {
+        // a refused action (invalid indices / environment full) leaves the state alone, but the caller's
+        // buffers are still written -- the unchanged observation -- and the episode is flagged as over, so a
+        // lock-step loop neither reads stale memory nor stalls on this environment
         if (tid == 0) {
+            const bw_step_out prev = P.last_out[e];
             bw_step_out o;
             memset(&o, 0, sizeof(o));
             o.error = (uint8_t)sh_error;
             o.n_blocks = n_old;
+            o.n_interfaces = prev.n_interfaces;
+            o.stable = prev.stable; o.stable_unfrozen = prev.stable_unfrozen;
+            o.residual = prev.residual; o.residual_unfrozen = prev.residual_unfrozen;
+            o.collision = prev.collision; o.collision_block = prev.collision_block;
+            o.collision_obstacle = prev.collision_obstacle; o.collision_floor = prev.collision_floor;
+            o.collision_boundary = prev.collision_boundary;
+            o.n_targets_reached = prev.n_targets_reached;
+            for (int t = 0; t < BW_MAX_TARGETS; t++) o.distance_to_targets[t] = prev.distance_to_targets[t];
+            o.terminated = 1;
+            o.truncated = (uint8_t)(P.max_steps > 0 && n_old >= P.max_steps);
             out[e] = o;
+            P.done[e] = 1;
+            if (binary != nullptr) {
+                float *bf = binary + (size_t)e * 6;
+                bf[0] = (float)prev.stable; bf[1] = (float)prev.collision; bf[2] = (float)prev.collision_block;
+                bf[3] = (float)prev.collision_obstacle; bf[4] = (float)prev.collision_floor;
+                bf[5] = (float)prev.collision_boundary;
+            }
         }
+        sh_bits[tid] = old_bits;
+        __syncthreads();
+#ifndef BW_PROFILE
+        write_obs_images(obs, sh_bits, e, tid);
+#endif
         return;
     }
 
@@ -634,7 +690,10 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                 else stable = (status != 2) && (res <= P.stable_tol);
             }
         }
-        if (lane == 0) { sh_verdict[warp] = stable; __threadfence_block(); }
+        // only a DECIDED verdict may cut the sibling's solve short: a solve that ran out of stages (status 2,
+        // the reference's stable=None) says nothing about the other problem (the reference evaluates the two
+        // independently, gym_env.py:325-333)
+        if (lane == 0 && status != 2) { sh_verdict[warp] = stable; __threadfence_block(); }
 #ifdef BW_PROFILE
         if (lane == 0) {
             sh_prof_solve[warp] = clock64() - prof_t[2];
@@ -800,36 +859,9 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         }
     }
 #endif
-#ifdef BW_PROFILE
-    if (false)
-#else
-    if (block_img != nullptr)
+#ifndef BW_PROFILE
+    write_obs_images(obs, sh_bits, e, tid);
 #endif
-    {
-        float4 *dst = reinterpret_cast<float4 *>(block_img + (size_t)e * IMG * IMG);
-#pragma unroll 4
-        for (int i = 0; i < IMG * IMG / 4 / 64; i++) {
-            const int q = i * 64 + tid;            // float4 index: row = q / 16, nibble = q % 16
-            const unsigned nib = (unsigned)(sh_bits[q >> 4] >> (4 * (q & 15))) & 0xfu;
-            __stcs(dst + q, make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f,
-                                        (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f));
-        }
-    }
-    if (obs.block_bits != nullptr) obs.block_bits[(size_t)e * IMG + tid] = sh_bits[tid];
-    if (obs.block_img_u8 != nullptr) {
-        uint4 *dst = reinterpret_cast<uint4 *>(obs.block_img_u8 + (size_t)e * IMG * IMG);
-#pragma unroll
-        for (int i = 0; i < IMG * IMG / 16 / 64; i++) {
-            const int q = i * 64 + tid;            // uint4 index: row = q / 4, 16-pixel segment = q % 4
-            const unsigned seg = (unsigned)(sh_bits[q >> 2] >> (16 * (q & 3))) & 0xffffu;
-            uint4 v;
-            v.x = (seg & 1u) | ((seg & 2u) << 7) | ((seg & 4u) << 14) | ((seg & 8u) << 21);
-            v.y = ((seg >> 4) & 1u) | (((seg >> 4) & 2u) << 7) | (((seg >> 4) & 4u) << 14) | (((seg >> 4) & 8u) << 21);
-            v.z = ((seg >> 8) & 1u) | (((seg >> 8) & 2u) << 7) | (((seg >> 8) & 4u) << 14) | (((seg >> 8) & 8u) << 21);
-            v.w = ((seg >> 12) & 1u) | (((seg >> 12) & 2u) << 7) | (((seg >> 12) & 4u) << 14) | (((seg >> 12) & 8u) << 21);
-            __stcs(dst + q, v);
-        }
-    }
 }
 
 void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,

@@ -119,7 +119,7 @@ class BatchedAssemblyGym:
     def set_shapes(self, shapes):
         """`shapes`: objects with `.tables` (envs.assembly_env.Shape), ShapeTables or urdf paths."""
         descs = (L.bw_shape_desc * len(shapes))()
-        self.shape_tables = []
+        self.shape_tables, self._target_masks = [], []
         for i, s in enumerate(shapes):
             if isinstance(s, str):
                 tables, tf, rf = load_shape_tables(s), None, None
@@ -129,6 +129,7 @@ class BatchedAssemblyGym:
                 tables, tf, rf = s.tables, s._target_faces_2d, s._receiving_faces_2d
             self.shape_tables.append(tables)
             descs[i] = shape_desc(tables, tf, rf)
+            self._target_masks.append(int(descs[i].target_faces_mask))
         self._check(self.lib.bw_load_shapes(self.handle, descs, len(shapes)))
 
     def set_mu(self, mu):
@@ -204,7 +205,12 @@ class BatchedAssemblyGym:
                 actions = self.actions_array(actions)
             self._actions.copy_(torch.from_numpy(actions.view(np.uint8).reshape(-1)), non_blocking=False)
             d_act = self._actions
-        d_mask = self._to_device_bytes(np.asarray(mask, dtype=np.uint8)) if mask is not None else None
+        mask_on_device = isinstance(mask, torch.Tensor) and mask.is_cuda
+        if mask_on_device:
+            d_mask = mask.to(torch.uint8).contiguous()
+            self._keep = d_mask                      # same stream as torch: alive until the next call is enough
+        else:
+            d_mask = self._to_device_bytes(np.asarray(mask, dtype=np.uint8)) if mask is not None else None
         obs = None
         if block_img is not None or binary is not None or block_u8 is not None or block_bits is not None:
             obs = L.bw_obs_out(block_img.data_ptr() if block_img is not None else None,
@@ -213,7 +219,7 @@ class BatchedAssemblyGym:
                                block_bits.data_ptr() if block_bits is not None else None)
         self._check(self.lib.bw_step(self.handle, d_act.data_ptr(), d_mask.data_ptr() if d_mask is not None else None,
                                      self._out.data_ptr(), C.byref(obs) if obs is not None else None))
-        if d_mask is not None:
+        if d_mask is not None and not mask_on_device:
             self.sync()
         return self._out
 
@@ -299,6 +305,21 @@ class BatchedAssemblyGym:
             self.handle, g.ctypes.data, g.size, o.ctypes.data, o.size, amax, c["cand"].data_ptr(),
             c["valid"].data_ptr(), c["n"].data_ptr(), c["bits"].data_ptr() if with_bits else None))
         return c
+
+    def candidate_overflow(self):
+        """Largest candidate count an `enumerate_actions` call since the last query had to cut to its `amax`
+        (0: every list was complete).  Synchronises."""
+        need = C.c_int32(0)
+        self._check(self.lib.bw_candidate_overflow(self.handle, C.byref(need)))
+        return int(need.value)
+
+    def max_candidates(self, n_ground, n_offsets=1):
+        """Upper bound of the candidate count of one environment (generate_actions, actions.py:7-52): every
+        (shape, target face) group offers the ground offsets plus every face of every placed block."""
+        groups = sum(bin(self._target_masks[i]).count("1") for i in range(len(self.shape_tables)))
+        faces = max(len(t.normals) for t in self.shape_tables)
+        cap = int(self.max_steps) if self.max_steps else L.BW_MAX_BLOCKS
+        return groups * (n_ground + max(cap - 1, 0) * faces * n_offsets)
 
     def select_random(self, seed, cand=None):
         c = cand or self._cand

@@ -132,6 +132,7 @@ SIGNATURES = {
     "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_observe_host": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_enumerate_actions": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "bw_candidate_overflow": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bw_expand_bits": (C.c_int, [_H, _P, C.c_int64, _P]),
     "bw_select_random": (C.c_int, [_H, _P, _P, _P, C.c_int32, C.c_uint64, _P, _P]),
     "bw_get_state": (C.c_int, [_H, _P, _P]),

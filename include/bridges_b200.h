@@ -236,10 +236,16 @@ int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_
 int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
                          const double *h_offset_values, int32_t n_offsets, int32_t amax,
                          bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits);
+/* generate_actions is unbounded, the buffers above hold amax candidates per environment: lists that did not
+ * fit are cut to amax (d_n_cand[e] = amax) and remembered.  *h_needed = the largest untruncated count any
+ * environment had since the last query (0 = every list was complete); synchronises and resets the mark. */
+int bw_candidate_overflow(bw_handle *h, int32_t *h_needed);
 /* expand bit rasters [n,64] u64 -> [n,1,64,64] f32 */
 int bw_expand_bits(bw_handle *h, const uint64_t *d_bits, int64_t n, float *d_img);
 /* synthetic policy for benchmarks/tests: pick for every env a uniformly random valid candidate
- * (counter-based hash of seed, env, step); envs without a valid candidate get shape = -1. */
+ * (counter-based hash of seed, env, step); envs without a valid candidate get shape = -1 and are flagged as
+ * done (rollout_episode ends the episode when no candidate is left, successor_dqn.py:409-411), so that the
+ * next bw_reset_done starts them afresh. */
 int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
                      int32_t amax, uint64_t seed, bw_action *d_actions, int32_t *d_index);
 

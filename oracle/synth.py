@@ -35,12 +35,13 @@ def library():
             Shape(urdf_file="shapes/cube1.urdf", name="cube")]
 
 
-def random_assembly(rng, shapes, max_blocks=15, xlim=(-3.0, 7.0), ylim=(0.0, 10.0), tries=40, scale=1.0):
-    """Returns the list of Actions of one random valid rollout (no stability filter).
+def random_assembly(rng, shapes, max_blocks=15, xlim=(-3.0, 7.0), ylim=(0.0, 10.0), tries=40, scale=1.0, min_blocks=1):
+    """Returns the list of Actions of one random valid rollout (no stability filter), min_blocks..max_blocks long
+    (shorter when no further block can be placed).
     `scale` shrinks the offsets for the small shapes of the library (block.urdf, small_cube.urdf, ...)."""
     env = AssemblyGym(shapes=shapes, targets=[], obstacles=[], reward_fct=sparse_reward, restrict_2d=True,
                       assembly_env=AssemblyEnv(stability=None))
-    n_blocks = int(rng.integers(1, max_blocks + 1))
+    n_blocks = int(rng.integers(min_blocks, max_blocks + 1))
     actions = []
     occupied = set()
     for k in range(n_blocks):

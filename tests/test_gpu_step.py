@@ -116,22 +116,25 @@ def test_targets_quirk_max_steps_and_invalid_actions():
     assert list(env.read_out()["error"]) == [2, 2]      # max_steps = 2 blocks is the capacity
 
 
-@pytest.mark.parametrize("N,max_blocks,max_steps,seed", [(160, 12, None, 2024), (96, 10, 10, 7)])
-def test_random_assemblies_verdicts_residuals_forces(N, max_blocks, max_steps, seed):
+@pytest.mark.parametrize("N,max_blocks,max_steps,seed,min_blocks",
+                         [(160, 12, None, 2024, 1), (96, 10, 10, 7, 1), (112, 15, None, 515, 12), (64, 15, 15, 33, 13)])
+def test_random_assemblies_verdicts_residuals_forces(N, max_blocks, max_steps, seed, min_blocks):
     """max_steps=None sizes the kernel for 16 blocks (two matrix rows per lane), max_steps=10 selects the
-    one-row-per-lane solver instantiation: both are checked."""
+    one-row-per-lane solver instantiation: both are checked.  The last two cases are the top of BASELINE.json
+    configs[3] (13-15 blocks: more than 36 matrix rows, i.e. the second row of a lane in `Solver<true>`), with the
+    16-block capacity and with max_steps=15."""
     from oracle import stability as ost
     from oracle import synth
     rng = np.random.default_rng(seed)
     shapes = synth.library()
-    plans = [synth.random_assembly(rng, shapes, max_blocks=max_blocks) for _ in range(N)]
+    plans = [synth.random_assembly(rng, shapes, max_blocks=max_blocks, min_blocks=min_blocks) for _ in range(N)]
     mus = [synth.MUS[i % 3] for i in range(N)]
     env = _gpu_env(N, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"], max_steps=max_steps)
     env.set_mu(mus)
     env.reset(dict())
     oenvs = [H.oracle_env(["trapezoid", "hexagon", "cube1"], mu=mus[i]) for i in range(N)]
     from oracle.gym_env import Action as OAction
-    n_band = n_checked = n_stable = n_forces = n_residuals = 0
+    n_band = n_checked = n_stable = n_forces = n_residuals = n_rows_over_36 = 0
     for k in range(max(len(p) for p in plans)):
         acts = [(p[k].target_block, p[k].target_face, p[k].shape, p[k].face, p[k].offset_x, p[k].offset_y)
                 if k < len(p) else None for p in plans]
@@ -146,6 +149,7 @@ def test_random_assemblies_verdicts_residuals_forces(N, max_blocks, max_steps, s
             r_frozen, r_unfrozen = H.residuals(oenvs[e])
             o = out[e]
             assert o["n_interfaces"] == len(oenvs[e].assembly_env.cra_assembly.interfaces)
+            n_rows_over_36 += 3 * (k + 1) > 36 and r_unfrozen is not None
             for got, want, r_gpu, r_or in ((o["stable"], frozen, o["residual"], r_frozen),
                                            (o["stable_unfrozen"], unfrozen, o["residual_unfrozen"], r_unfrozen)):
                 if r_or is not None and BAND[0] < r_or < BAND[1]:
@@ -185,6 +189,8 @@ def test_random_assemblies_verdicts_residuals_forces(N, max_blocks, max_steps, s
             assert (b["x"], b["z"], b["c"], b["s"]) == blk.pose
         assert np.array_equal(env.bits_to_bool(bits[e]), render_blocks_2d(ob, H.XLIM, H.YLIM, H.IMG))
     assert n_checked > 500 and n_stable > 50 and n_forces > 15 and n_residuals > 300
+    if min_blocks > 10:
+        assert n_rows_over_36 > N, n_rows_over_36      # released solves with 13-15 free blocks (39-45 rows)
     assert n_band <= 0.01 * n_checked            # size of the excluded band
 
 

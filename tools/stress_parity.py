@@ -10,5 +10,5 @@ seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 for N, max_blocks, max_steps, seed in ((256, 14, None, seed0), (256, 15, None, seed0 + 1), (192, 10, 10, seed0 + 2),
                                        (192, 10, 10, seed0 + 3)):
     t0 = time.perf_counter()
-    run(N, max_blocks, max_steps, seed)
+    run(N, max_blocks, max_steps, seed, 1)
     print(f"ok N={N} max_blocks={max_blocks} max_steps={max_steps} seed={seed}  {time.perf_counter() - t0:.1f} s", flush=True)

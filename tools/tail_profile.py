@@ -5,14 +5,27 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from bridges_b200.envs.batched import BatchedAssemblyGym
 from bench import task_def, X_GROUND
+from bench import bridge_def
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=10)
-env.reset(task_def(2))
+CASE = sys.argv[2] if len(sys.argv) > 2 else "tower2"
+if CASE == "bridge":       # BASELINE.json configs[4] shape: horizontal_bridge_setup(5), trapezoid + hexagon, max_steps 15
+    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf"], max_steps=15)
+    env.reset(bridge_def(5))
+    AMAX = 1024
+elif CASE == "tower4":     # configs[2] shape
+    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=15)
+    env.reset(task_def(4))
+    AMAX = 256
+else:
+    env = BatchedAssemblyGym(E, ["shapes/trapezoid.urdf"], max_steps=10)
+    env.reset(task_def(2))
+    AMAX = 128
+print("case", CASE, "E", E)
 rows = []
 subs = []
 img = torch.zeros((E, 1, 64, 64), dtype=torch.float32, device='cuda')
 for i in range(60):
-    env.enumerate_actions(X_GROUND, (0.0,), amax=128, with_bits=False)
+    env.enumerate_actions(X_GROUND, (0.0,), amax=AMAX, with_bits=False)
     acts, _ = env.select_random(seed=i)
     env.step(acts, block_img=img)
     out = env.read_out()
