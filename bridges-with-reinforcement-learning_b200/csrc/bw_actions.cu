@@ -36,8 +36,10 @@ template <bool CACHED>
 __global__ void __launch_bounds__(ENUM_THREADS, 8)
 enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                  int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
-                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, CandCache C) {
+                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, CandCache C,
+                 const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid) {
     const int e = blockIdx.x;
+    if (mask != nullptr && mask[e] == 0) return;
     const int tid = threadIdx.x;
     // block library and pixel nodes in shared memory; the helpers of bw_common.cuh read them through P
     __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
@@ -168,7 +170,7 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
 
     // only the first `count` slots are meaningful (n_cand); the rest of the caller's buffers is left alone
     const int lane = tid & 31, warp = tid >> 5;
-    int base = 0;
+    int base = 0, nval = 0;
     while (base < count) {
         const int nch = min(CHUNK, count - base);
         // ---- phase A0: thread per candidate -- the action, its cache slot, hit or miss
@@ -339,21 +341,23 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
             }
         }
         __syncthreads();
-        if (tid < nchunk) valid[(size_t)e * amax + base + tid] = (!c_bad[tid] && !c_overlap[tid]) ? 1 : 0;
-        __syncthreads();
+        const bool keep = tid < nchunk && !c_bad[tid] && !c_overlap[tid];
+        if (tid < nchunk) valid[(size_t)e * amax + base + tid] = keep ? 1 : 0;
+        nval += __syncthreads_count(keep);
         base += nchunk;
     }
+    if (n_valid != nullptr && tid == 0) n_valid[e] = nval;
 }
 
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      const CandCache &cache, cudaStream_t stream) {
+                      const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask, int32_t *d_n_valid) {
     if (cache.meta != nullptr && cache.slots > 0)
         enumerate_kernel<true><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                                 d_valid, d_n_cand, d_action_bits, cache);
+                                                                 d_valid, d_n_cand, d_action_bits, cache, d_mask, d_n_valid);
     else
         enumerate_kernel<false><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                                  d_valid, d_n_cand, d_action_bits, cache);
+                                                                  d_valid, d_n_cand, d_action_bits, cache, d_mask, d_n_valid);
 }
 
 // create_block + collision_on_action for one hypothetical action per env (state untouched)

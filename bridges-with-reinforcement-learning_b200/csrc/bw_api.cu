@@ -48,6 +48,12 @@ struct bw_handle {
     int n_groups = 0;                // (shape, face) pairs with the target_faces bit: candidate groups
     bool cand_dirty = true;          // library or offset tables changed: every slot is stale
     size_t cand_budget = (size_t)4096 << 20;   // bytes; BW_CAND_CACHE_MB overrides, 0 disables the cache
+    // fused rollout (bw_rollout_*): candidate buffers and the arguments of generate_actions
+    RolloutBufs roll;
+    bool roll_configured = false;
+    double roll_ground[256], roll_offsets[256];
+    int roll_n_ground = 0, roll_n_offsets = 0;
+    int32_t roll_step = 0;
     bw_block *d_qblocks = nullptr, *d_rblocks = nullptr;
     uint8_t *d_qflags = nullptr;
     ShapeDev *d_rshapes = nullptr;
@@ -206,6 +212,9 @@ static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
 
 extern "C" {
 
+static int upload_offset_tables(bw_handle *h, const double *h_x_discr_ground, int n_ground, const double *h_offset_values,
+                                int n_offsets);
+
 int bw_abi_version(void) { return BW_ABI_VERSION; }
 
 void bw_config_default(bw_config *cfg) {
@@ -317,6 +326,9 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     CU(dev_alloc(h, &P.done, E));
     CU(dev_alloc(h, &P.last_out, E));
     CU(dev_alloc(h, &P.su_valid, E));
+    CU(dev_alloc(h, &P.warm_y, (size_t)E * 2 * NB * 3));
+    CU(dev_alloc(h, &P.warm_ok, (size_t)E * 2));
+    P.warm_start = getenv("BW_NO_WARM") ? 0 : 1;   // tuning hook (tools/ only): every solve from y = 0
     CU(dev_alloc(h, &P.cand_need, 1));
     CU(dev_alloc(h, &P.reset_err, 1));
     {
@@ -400,6 +412,7 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     CU(cudaMemcpyAsync(h->d_shapes, dev, sizeof(ShapeDev) * n, cudaMemcpyHostToDevice, h->stream));
     // verdicts of the last step describe blocks of the old library
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
+    CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->P.n_shapes = n;
     h->smem_step = step_smem_bytes(h->P.max_blocks, h->P.max_itf, n);
@@ -443,6 +456,7 @@ int bw_set_mu(bw_handle *h, const double *h_mu) {
     // the released-block verdict of the last step was computed with the old coefficients: it must not
     // stand in for the next step's frozen solve (step_kernel, prev_released_ok)
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
+    CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -453,6 +467,7 @@ int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask) {
     CU(cudaMemcpyAsync(h->P.static_mask, h_mask, sizeof(uint32_t) * h->P.E, cudaMemcpyHostToDevice, h->stream));
     // the verdicts of the last step no longer describe these supports
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
+    CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -683,7 +698,18 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
         return fail(h, BW_ERR_CAPACITY, "at most 256 ground offsets / block offsets");
     if ((n_ground > 0 && !h_x_discr_ground) || (n_offsets > 0 && !h_offset_values)) return BW_ERR_INVALID;
     CU(cudaSetDevice(h->cfg.device));
-    // the offset tables rarely change between calls: upload only when they do
+    if (int rc = upload_offset_tables(h, h_x_discr_ground, n_ground, h_offset_values, n_offsets)) return rc;
+    if (int rc = prepare_cand_cache(h, n_ground, n_offsets)) return rc;
+    launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
+                     d_action_bits, h->cand, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+// the offset tables rarely change between calls: upload only when they do
+static int upload_offset_tables(bw_handle *h, const double *h_x_discr_ground, int n_ground, const double *h_offset_values,
+                                int n_offsets) {
     if (n_ground > 0 && (h->n_ground_cached != n_ground ||
                          memcmp(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground) != 0)) {
         memcpy(h->ground_cached, h_x_discr_ground, sizeof(double) * n_ground);
@@ -698,10 +724,125 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
         h->cand_dirty = true;
         CU(cudaMemcpyAsync(h->d_offsets, h->offsets_cached, sizeof(double) * n_offsets, cudaMemcpyHostToDevice, h->stream));
     }
-    if (int rc = prepare_cand_cache(h, n_ground, n_offsets)) return rc;
-    launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
-                     d_action_bits, h->cand, h->stream);
-    h->launches++;
+    return BW_OK;
+}
+
+// ---- fused lock-step rollout -------------------------------------------------------------------------------
+int bw_rollout_configure(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
+                         int32_t n_offsets, int32_t amax, int32_t env_id_base) {
+    if (!h || amax <= 0) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    if (n_ground < 0 || n_ground > 256 || n_offsets < 0 || n_offsets > 256)
+        return fail(h, BW_ERR_CAPACITY, "at most 256 ground offsets / block offsets");
+    if ((n_ground > 0 && !h_x_discr_ground) || (n_offsets > 0 && !h_offset_values)) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t E = (size_t)h->P.E;
+    RolloutBufs &R = h->roll;
+    if (R.cand == nullptr || R.amax != amax) {
+        if (R.cand != nullptr) {
+            CU(cudaStreamSynchronize(h->stream));
+            void *old[3] = {R.cand, R.valid, R.bits};
+            for (void *q : old) {
+                cudaFree(q);
+                for (size_t i = 0; i < h->allocs.size(); i++)
+                    if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
+            }
+        }
+        CU(dev_alloc(h, &R.cand, E * amax));
+        CU(dev_alloc(h, &R.valid, E * amax));
+        CU(dev_alloc(h, &R.bits, E * amax * IMG, false));
+        if (R.n_cand == nullptr) {
+            CU(dev_alloc(h, &R.n_cand, E));
+            CU(dev_alloc(h, &R.n_valid, E));
+            CU(dev_alloc(h, &R.actions, E));
+            CU(dev_alloc(h, &R.has_action, E));
+            CU(dev_alloc(h, &R.stuck, E));
+        }
+        R.amax = amax;
+    }
+    R.env_id_base = env_id_base;
+    if (n_ground > 0) memcpy(h->roll_ground, h_x_discr_ground, sizeof(double) * n_ground);
+    if (n_offsets > 0) memcpy(h->roll_offsets, h_offset_values, sizeof(double) * n_offsets);
+    h->roll_n_ground = n_ground;
+    h->roll_n_offsets = n_offsets;
+    h->roll_configured = true;
+    return BW_OK;
+}
+
+// candidates of the current states into the rollout buffers; environments without any candidate (other than fresh
+// ones) are reset and enumerated once more
+static int rollout_enumerate(bw_handle *h, bw_transition *d_slots) {
+    RolloutBufs &R = h->roll;
+    if (int rc = upload_offset_tables(h, h->roll_ground, h->roll_n_ground, h->roll_offsets, h->roll_n_offsets)) return rc;
+    if (int rc = prepare_cand_cache(h, h->roll_n_ground, h->roll_n_offsets)) return rc;
+    launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
+                     R.n_cand, R.bits, h->cand, h->stream, nullptr, R.n_valid);
+    launch_rollout_finalize(h->P, R, d_slots, h->stream);
+    launch_reset(h->P, nullptr, R.stuck, 1, h->stream);
+    launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
+                     R.n_cand, R.bits, h->cand, h->stream, R.stuck, R.n_valid);
+    h->launches += 4;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_rollout_begin(bw_handle *h, bw_rollout_view *out) {
+    if (!h) return BW_ERR_INVALID;
+    if (!h->roll_configured) return fail(h, BW_ERR_STATE, "bw_rollout_configure must be called first");
+    CU(cudaSetDevice(h->cfg.device));
+    if (int rc = rollout_enumerate(h, nullptr)) return rc;
+    if (out) {
+        const RolloutBufs &R = h->roll;
+        out->cand = R.cand; out->valid = R.valid; out->n_cand = R.n_cand; out->n_valid = R.n_valid;
+        out->action_bits = R.bits; out->amax = R.amax; out->reserved0 = 0;
+    }
+    return BW_OK;
+}
+
+static int rollout_iteration(bw_handle *h, const int32_t *d_index, int random_policy, uint64_t seed, bw_transition *d_slots,
+                             const bw_obs_out *obs) {
+    RolloutBufs &R = h->roll;
+    launch_rollout_pick(h->P, R, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
+    launch_step(h->P, R.actions, R.has_action, h->d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr,
+                nullptr, 0, h->smem_step, h->stream);
+    launch_rollout_record(h->P, R, h->d_out, d_slots, h->stream);
+    launch_reset(h->P, nullptr, nullptr, 1, h->stream);           // finished episodes start afresh (their task is kept)
+    h->launches += 4;
+    h->roll_step++;
+    return rollout_enumerate(h, d_slots);
+}
+
+int bw_rollout_commit(bw_handle *h, const int32_t *d_index, bw_transition *d_slots, const bw_obs_out *obs) {
+    if (!h || !d_index || !d_slots) return BW_ERR_INVALID;
+    if (!h->roll_configured) return fail(h, BW_ERR_STATE, "bw_rollout_configure / bw_rollout_begin must be called first");
+    CU(cudaSetDevice(h->cfg.device));
+    return rollout_iteration(h, d_index, 0, 0, d_slots, obs);
+}
+
+int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transition *d_ring, int64_t capacity, int64_t start) {
+    if (!h || !d_ring || n_steps < 0 || start < 0) return BW_ERR_INVALID;
+    if (!h->roll_configured) return fail(h, BW_ERR_STATE, "bw_rollout_configure / bw_rollout_begin must be called first");
+    const int64_t E = h->P.E;
+    if (capacity < E || capacity % E != 0 || start % E != 0)
+        return fail(h, BW_ERR_INVALID, "ring capacity and start must be multiples of num_envs");
+    CU(cudaSetDevice(h->cfg.device));
+    for (int32_t k = 0; k < n_steps; k++) {
+        bw_transition *slots = d_ring + (start + (int64_t)k * E) % capacity;
+        if (int rc = rollout_iteration(h, nullptr, 1, seed, slots, nullptr)) return rc;
+    }
+    return BW_OK;
+}
+
+int bw_unpack_transitions(bw_handle *h, const bw_transition *d_ring, const int64_t *d_indices, int64_t n, float *d_block,
+                          float *d_action, float *d_next_block, float *d_binary, float *d_next_binary, float *d_reward,
+                          float *d_lin_reward, uint8_t *d_done) {
+    if (!h || !d_ring || n < 0) return BW_ERR_INVALID;
+    CU(cudaSetDevice(h->cfg.device));
+    if (n > 0) {
+        launch_unpack_transitions(d_ring, d_indices, n, d_block, d_action, d_next_block, d_binary, d_next_binary, d_reward,
+                                  d_lin_reward, d_done, h->stream);
+        h->launches++;
+    }
     CU(cudaGetLastError());
     return BW_OK;
 }

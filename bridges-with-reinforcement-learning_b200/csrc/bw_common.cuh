@@ -88,6 +88,12 @@ struct Params {
     uint8_t *done;             // [E] last step returned terminated | truncated
     bw_step_out *last_out;     // [E] copy of the last step result (binary features of observe)
     uint8_t *su_valid;         // [E] last_out[e].stable_unfrozen describes the current blocks and supports
+    // dual iterates of the last feasible solves, per block (physical units: y * ||weights||), the starting
+    // points of the next step's solves (step_kernel phase 3)
+    double *warm_y;            // [E][2][NB][3]: 0 = supports as step() leaves them, 1 = last block released
+    uint8_t *warm_ok;          // [E][2] the entry holds the iterate of a solve that ended feasible
+    int32_t warm_start;        // 0: every solve starts from y = 0 (tuning hook BW_NO_WARM)
+    int32_t pad_ws;
     int32_t *cand_need;        // [1] largest untruncated candidate count an enumeration had to cut to `amax`
     int32_t *reset_err;        // [1] environments whose reset task was refused (bad shape index / too many blocks)
 };

@@ -37,7 +37,29 @@ struct CandCache {
 };
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      const CandCache &cache, cudaStream_t stream);
+                      const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask = nullptr,
+                      int32_t *d_n_valid = nullptr);
+
+// bw_rollout.cu: the kernels around step / enumerate / reset of one lock-step rollout iteration
+struct RolloutBufs {
+    bw_action *cand = nullptr;       // [E][amax]
+    uint8_t *valid = nullptr;        // [E][amax]
+    int32_t *n_cand = nullptr;       // [E]
+    int32_t *n_valid = nullptr;      // [E]
+    uint64_t *bits = nullptr;        // [E][amax][IMG]
+    bw_action *actions = nullptr;    // [E] chosen actions (input of the step kernel)
+    uint8_t *has_action = nullptr;   // [E] step mask
+    uint8_t *stuck = nullptr;        // [E] live environment without a candidate: reset + enumerated again
+    int32_t amax = 0, env_id_base = 0;
+};
+void launch_rollout_pick(const Params &P, const RolloutBufs &R, const int32_t *d_index, int random_policy, uint64_t seed,
+                         int32_t step, bw_transition *d_slots, cudaStream_t stream);
+void launch_rollout_record(const Params &P, const RolloutBufs &R, const bw_step_out *d_out, bw_transition *d_slots,
+                           cudaStream_t stream);
+void launch_rollout_finalize(const Params &P, const RolloutBufs &R, bw_transition *d_slots, cudaStream_t stream);
+void launch_unpack_transitions(const bw_transition *d_ring, const int64_t *d_indices, int64_t n, float *d_block,
+                               float *d_action, float *d_next_block, float *d_binary, float *d_next_binary,
+                               float *d_reward, float *d_lin_reward, uint8_t *d_done, cudaStream_t stream);
 void launch_select_random(const Params &P, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
                           int amax, uint64_t seed, bw_action *d_actions, int32_t *d_index, cudaStream_t stream);
 

@@ -86,6 +86,8 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
         for (int i = 0; i < BW_MAX_TARGETS; i++) o.distance_to_targets[i] = INFINITY;
         P.last_out[e] = o;
         P.su_valid[e] = (s_n == 0);       // pre-placed blocks: the evaluation that follows sets it
+        P.warm_ok[2 * e] = 0;
+        P.warm_ok[2 * e + 1] = 0;
     }
     if (tid < NB) P.face_occ[(size_t)e * NB + tid] = 0;
     __syncthreads();

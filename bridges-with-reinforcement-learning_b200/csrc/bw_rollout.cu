@@ -1,0 +1,209 @@
+// The kernels around step / enumerate / reset of one lock-step rollout iteration (bw_rollout_* in
+// include/bridges_b200.h): the batched form of rollout_episode (robotoddler/training/successor_dqn.py:365-475).
+//
+//   pick      policy choice -> chosen action, first half of the transition record (state raster, action raster,
+//             binary features of the state before); the built-in policy draws a uniformly random valid candidate
+//   record    second half after the step kernel: next-state raster, rewards, verdicts, termination
+//   finalize  after the candidates of the next state are known: done |= "no candidate left"
+//             (successor_dqn.py:409-411); such environments are flagged for a reset
+//   unpack    packed records -> the learner's float tensors (ReplayBuffer.sample, replay_memory.py:30-40)
+//
+// Records are 1.6 KB (three bit-packed rasters + scalars) instead of 3 x 16 KB float images: the rollout writes
+// 1.6 MB per 1024-environment iteration, nothing here is bound by anything but launch latency.
+#include "bw_common.cuh"
+#include "bw_kernels.cuh"
+
+namespace bw {
+
+static_assert(sizeof(bw_transition) == 1608, "bw_transition layout");
+
+__device__ __forceinline__ uint64_t rmix64(uint64_t x) {   // splitmix64, as select_random_kernel
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint8_t binary_bits(const bw_step_out &o) {    // get_state_features, successor_dqn.py:53-60
+    return (uint8_t)((o.stable ? 1 : 0) | (o.collision ? 2 : 0) | (o.collision_block ? 4 : 0) |
+                     (o.collision_obstacle ? 8 : 0) | (o.collision_floor ? 16 : 0) | (o.collision_boundary ? 32 : 0));
+}
+
+// One CTA of 64 threads per environment (thread = image row for the raster copies).
+__global__ void __launch_bounds__(64)
+rollout_pick_kernel(Params P, RolloutBufs R, const int32_t *__restrict__ index, int random_policy, uint64_t seed,
+                    int32_t step, bw_transition *__restrict__ slots) {
+    const int e = blockIdx.x, tid = threadIdx.x;
+    const int amax = R.amax;
+    const int cnt = R.n_cand[e], nvalid = R.n_valid[e];
+    const uint8_t *vrow = R.valid + (size_t)e * amax;
+    __shared__ int s_strip[64];
+    __shared__ int s_choice;
+    int choice = -1;
+    if (nvalid > 0) {
+        if (random_policy) {
+            // k-th valid candidate, k uniform: every thread counts its strip of the mask, the owner of k walks it
+            const int per = (cnt + 63) >> 6, lo = tid * per, hi = min(lo + per, cnt);
+            int c = 0;
+            for (int a = lo; a < hi; a++) c += vrow[a];
+            s_strip[tid] = c;
+            __syncthreads();
+            if (tid == 0) {
+                const uint64_t r = rmix64(seed ^ rmix64((uint64_t)(R.env_id_base + e) * 0x632BE59BD9B4E019ull + (uint64_t)step));
+                int k = (int)(r % (uint64_t)nvalid);
+                int t = 0;
+                while (t < 63 && k >= s_strip[t]) { k -= s_strip[t]; t++; }
+                int a = t * per;
+                for (;; a++) {
+                    if (vrow[a]) {
+                        if (k == 0) break;
+                        k--;
+                    }
+                }
+                s_choice = a;
+            }
+            __syncthreads();
+            choice = s_choice;
+        } else {
+            choice = index[e];
+            if (choice < 0 || choice >= cnt || !vrow[choice]) choice = -1;     // refused: treated like "no candidate"
+        }
+    }
+    bw_transition &T = slots[e];
+    if (choice < 0) {
+        if (tid == 0) {
+            bw_action a;
+            a.target_block = -1; a.target_face = 0; a.shape = -1; a.face = 0; a.offset_x = 0.0; a.offset_y = 0.0;
+            a.frozen = 0; a.reserved0 = 0;
+            R.actions[e] = a;
+            R.has_action[e] = 0;
+            T.valid = 0;
+            T.done = 1;
+            T.env = R.env_id_base + e;
+            T.step = step;
+            P.done[e] = 1;              // nothing to place: the episode is over (successor_dqn.py:409-411)
+        }
+        return;
+    }
+    T.block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
+    T.action_bits[tid] = R.bits[((size_t)e * amax + choice) * IMG + tid];
+    if (tid == 0) {
+        const bw_action a = R.cand[(size_t)e * amax + choice];
+        R.actions[e] = a;
+        R.has_action[e] = 1;
+        T.action = a;
+        T.binary = binary_bits(P.last_out[e]);
+        T.env = R.env_id_base + e;
+        T.step = step;
+        T.valid = 1;
+        T.n_next_candidates = 0;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+rollout_record_kernel(Params P, RolloutBufs R, const bw_step_out *__restrict__ out, bw_transition *__restrict__ slots) {
+    const int e = blockIdx.x, tid = threadIdx.x;
+    if (!R.has_action[e]) return;
+    bw_transition &T = slots[e];
+    T.next_block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
+    if (tid == 0) {
+        const bw_step_out o = out[e];
+        T.reward = o.reward;
+        T.lin_reward = o.lin_reward;
+        T.next_binary = binary_bits(o);
+        T.terminated = o.terminated;
+        T.truncated = o.truncated;
+        T.stable = o.stable;
+        T.stable_unfrozen = o.stable_unfrozen;
+        T.done = (uint8_t)(o.terminated | o.truncated);
+        if (o.error) { T.valid = 0; T.done = 1; }      // a refused action is not a transition (the step ended the episode)
+    }
+}
+
+// thread per environment, after the enumeration of the next states
+__global__ void rollout_finalize_kernel(Params P, RolloutBufs R, bw_transition *__restrict__ slots) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.E) return;
+    // finished episodes were reset before the enumeration: their candidates are those of a fresh environment and
+    // say nothing about the recorded transition
+    const int nv = R.n_valid[e];
+    uint8_t stuck = 0;
+    if (slots != nullptr) {
+        bw_transition &T = slots[e];
+        if (T.valid && !T.done) {
+            T.n_next_candidates = nv;
+            if (nv == 0) { T.done = 1; stuck = 1; }
+        } else if (!T.valid && nv == 0) {
+            stuck = 1;
+        }
+    } else if (nv == 0) {
+        stuck = 1;
+    }
+    // a fresh environment always has its ground candidates; one without any is reset and enumerated again
+    if (stuck && P.n_blocks[e] == 0) stuck = 0;
+    R.stuck[e] = stuck;
+    if (stuck) P.done[e] = 1;
+}
+
+void launch_rollout_pick(const Params &P, const RolloutBufs &R, const int32_t *d_index, int random_policy, uint64_t seed,
+                         int32_t step, bw_transition *d_slots, cudaStream_t stream) {
+    rollout_pick_kernel<<<P.E, 64, 0, stream>>>(P, R, d_index, random_policy, seed, step, d_slots);
+}
+
+void launch_rollout_record(const Params &P, const RolloutBufs &R, const bw_step_out *d_out, bw_transition *d_slots,
+                           cudaStream_t stream) {
+    rollout_record_kernel<<<P.E, 64, 0, stream>>>(P, R, d_out, d_slots);
+}
+
+void launch_rollout_finalize(const Params &P, const RolloutBufs &R, bw_transition *d_slots, cudaStream_t stream) {
+    rollout_finalize_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, R, d_slots);
+}
+
+// One CTA of 256 threads per sampled record: three 16 KB images out (float4 streaming stores), scalars by thread 0.
+__global__ void __launch_bounds__(256)
+unpack_transitions_kernel(const bw_transition *__restrict__ ring, const int64_t *__restrict__ indices, int64_t n,
+                          float *__restrict__ block, float *__restrict__ action, float *__restrict__ next_block,
+                          float *__restrict__ binary, float *__restrict__ next_binary, float *__restrict__ reward,
+                          float *__restrict__ lin_reward, uint8_t *__restrict__ done) {
+    const int64_t i = blockIdx.x;
+    if (i >= n) return;
+    const bw_transition &T = ring[indices ? indices[i] : i];
+    __shared__ uint64_t s_bits[3][IMG];
+    const int tid = threadIdx.x;
+    if (tid < IMG) s_bits[0][tid] = T.block_bits[tid];
+    else if (tid < 2 * IMG) s_bits[1][tid - IMG] = T.action_bits[tid - IMG];
+    else if (tid < 3 * IMG) s_bits[2][tid - 2 * IMG] = T.next_block_bits[tid - 2 * IMG];
+    __syncthreads();
+    float *dst[3] = {block, action, next_block};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (dst[k] == nullptr) continue;
+        float4 *d4 = reinterpret_cast<float4 *>(dst[k] + (size_t)i * IMG * IMG);
+#pragma unroll
+        for (int q0 = 0; q0 < IMG * IMG / 4; q0 += 256) {
+            const int q = q0 + tid;                 // float4 index: row = q / 16, nibble = q % 16
+            const unsigned nib = (unsigned)(s_bits[k][q >> 4] >> (4 * (q & 15))) & 0xfu;
+            __stcs(d4 + q, make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                                       (nib & 8u) ? 1.0f : 0.0f));
+        }
+    }
+    if (tid < 6) {
+        if (binary) binary[i * 6 + tid] = (float)((T.binary >> tid) & 1u);
+        if (next_binary) next_binary[i * 6 + tid] = (float)((T.next_binary >> tid) & 1u);
+    }
+    if (tid == 0) {
+        if (reward) reward[i] = T.reward;
+        if (lin_reward) lin_reward[i] = T.lin_reward;
+        if (done) done[i] = T.done;
+    }
+}
+
+void launch_unpack_transitions(const bw_transition *d_ring, const int64_t *d_indices, int64_t n, float *d_block,
+                               float *d_action, float *d_next_block, float *d_binary, float *d_next_binary,
+                               float *d_reward, float *d_lin_reward, uint8_t *d_done, cudaStream_t stream) {
+    if (n <= 0) return;
+    unpack_transitions_kernel<<<(unsigned)n, 256, 0, stream>>>(d_ring, d_indices, n, d_block, d_action, d_next_block,
+                                                               d_binary, d_next_binary, d_reward, d_lin_reward, d_done);
+}
+
+}  // namespace bw

@@ -285,7 +285,9 @@ struct Solver {
     // of the block (one own load feeds three FMAs), the 3x3 diagonal block is factorised redundantly
     // by all lanes from six shuffled values, and each lane finishes its three entries with a 3x3
     // triangular solve.  m is a multiple of 3, so the right-hand-side row m lies below every block.
+    template <bool TW>
     __device__ void factor_and_solve(double inv_rho) {
+        constexpr bool TWO = TW;                           // (shadows the class parameter inside this function)
         const int nrows = m + 1;
         const double sqrt_rho = fast_rsqrt(inv_rho);
         const int i0 = lane, i1 = lane + 32;
@@ -612,11 +614,18 @@ struct Solver {
 
     // returns status: 0 feasible (r <= r_exit), 1 stalled at r* > 0, 2 not converged,
     // 3 verdict implied by the sibling solve (released-block equilibrium => frozen-block equilibrium)
-    __device__ int solve(double &r_out, int &iters_out) {
+    // warm = true: y holds a starting point (the dual iterate of an earlier solve on (almost) the same rows,
+    // see step_kernel); the proximal-point iteration converges from any start, a good one saves Newton steps.
+    __device__ int solve(double &r_out, int &iters_out, bool warm = false) {
+        if (!warm) {
 #pragma unroll 1
-        for (int i = lane; i < m; i += 32) y[i] = 0.0;
+            for (int i = lane; i < m; i += 32) y[i] = 0.0;
 #pragma unroll 1
-        for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;      // g = A^T y is kept up to date
+            for (int c = lane; c < 2 * nc; c += 32) g[c] = 0.0;  // g = A^T y is kept up to date
+        } else {
+            __syncwarp();
+            at_times(y, g);
+        }
 #pragma unroll 1
         for (int c = lane; c < nc; c += 32) typ[c] = 255;
         // row envelope of H = A J A^T (and of its Cholesky factor, which only fills inside it): the rows of
@@ -681,7 +690,10 @@ struct Solver {
                 __syncwarp();
                 BW_ACC(1, t_b);
                 BW_T0(t_c);
-                factor_and_solve(inv_rho);
+                // systems of up to 31 rows (10 free blocks) take the one-row-per-lane form even in the 16-block
+                // instantiation: the second row of a lane would be all predicated-off instructions
+                if (TWO && m + 1 > 32) factor_and_solve<true>(inv_rho);
+                else factor_and_solve<false>(inv_rho);
                 BW_ACC(2, t_c);
                 BW_T0(t_d);
                 // phi'(t) = grad.d + f.h - P_K(g + t h).h - t d.d / rho   (piecewise linear, decreasing).

@@ -207,6 +207,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __shared__ long long sh_prof_f[3];
 #endif
     __shared__ double sh_lin[2];
+    __shared__ double sh_warm[2][3 * NB];   // starting points of the two solves (dual iterates of the last step)
     __shared__ uint64_t sh_bits[IMG];      // raster of all blocks after this step
     __shared__ uint64_t sh_newbits[IMG];   // raster of the new block alone
     __shared__ double s_inv_nx[NF];        // 1 / n_x of the new block's posed faces (raster crossing estimate)
@@ -657,6 +658,34 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         __syncwarp();
         int stable, status = 0, iters = 0;
         double res = 0.0;
+        // warm starts only along real steps (an evaluation with Action.shape = -1 may follow arbitrary
+        // freeze / unfreeze calls) and never for the force read-back, whose iterates must not depend on history.
+        // Starting point of the FROZEN solve: the dual iterate of the last feasible solve over (almost) the same
+        // rows -- the previous step's released one when that was feasible (exactly these rows; the solve is then
+        // skipped altogether below) else its frozen one (these rows minus the block released now).  Rows without
+        // a stored value start at 0.  The values are parked in shared memory (the screen below uses the problem's
+        // own arrays as scratch) before either warp can store new ones.  The RELEASED solve always starts from
+        // y = 0: on the piles that stay in equilibrium it needs two Newton steps from there and more from the
+        // previous iterate (measured: profiles/README.md, round 2), and the hard released systems are the ones
+        // without equilibrium, which the mechanism screen decides.
+        const bool keep_y = placed && save_itf == nullptr && P.warm_start != 0;
+        bool warm = false;
+        if (keep_y && warp == 0) {
+            const bool ok0 = P.warm_ok[2 * e] != 0, ok1 = P.warm_ok[2 * e + 1] != 0;
+            const int src = ok1 ? 1 : (ok0 ? 0 : -1);
+            if (src >= 0) {
+                if (is_free) {
+                    const double *wy = P.warm_y + (((size_t)e * 2 + src) * NB + lane) * 3;
+                    const double inb = 1.0 / nb;
+                    sh_warm[warp][3 * myrow] = wy[0] * inb;
+                    sh_warm[warp][3 * myrow + 1] = wy[1] * inb;
+                    sh_warm[warp][3 * myrow + 2] = wy[2] * inb;
+                }
+                warm = true;
+            }
+        }
+        bool have_y = false;                       // S.y holds the iterate of a solve that ended feasible
+        __syncthreads();
         if (overflow) {
             stable = 0; status = 2; res = 1.0;
         } else if (nitf == 0) {
@@ -666,6 +695,12 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             stable = 1;
         } else if (warp == 0 && placed && prev_released_ok && !want_forces) {
             stable = 1; status = 4; res = prev_released_res;
+            // the released solve of the previous step ran on exactly these rows: its iterate is this problem's
+            if (warm) {
+#pragma unroll 1
+                for (int i = lane; i < S.m; i += 32) S.y[i] = sh_warm[warp][i];
+            }
+            have_y = warm;
         } else {
             bool certified = false;
 #ifdef BW_PROFILE
@@ -683,17 +718,33 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             if (certified) {
                 stable = 0; status = 5; res = nan("");   // rigid-mechanism certificate: no equilibrium, no solve
             } else {
-                status = S.solve(res, iters);
+                if (warm) {
+#pragma unroll 1
+                    for (int i = lane; i < S.m; i += 32) S.y[i] = sh_warm[warp][i];
+                }
+                status = S.solve(res, iters, warm);
                 // out of stages with a residual already under the verdict threshold: converged within the margin
                 if (status == 2 && res <= P.stable_tol) status = 0;
                 if (status == 3) { stable = S.implied_by; res = nan(""); }
                 else stable = (status != 2) && (res <= P.stable_tol);
+                have_y = (status == 0);
             }
         }
         // only a DECIDED verdict may cut the sibling's solve short: a solve that ran out of stages (status 2,
         // the reference's stable=None) says nothing about the other problem (the reference evaluates the two
         // independently, gym_env.py:325-333)
         if (lane == 0 && status != 2) { sh_verdict[warp] = stable; __threadfence_block(); }
+        if (keep_y) {
+            // keep the iterate for the next step (per block, physical units); anything else invalidates the entry
+            __syncwarp();
+            if (have_y && lane < NB) {
+                double *wy = P.warm_y + (((size_t)e * 2 + warp) * NB + lane) * 3;
+                wy[0] = is_free ? S.y[3 * myrow] * nb : 0.0;
+                wy[1] = is_free ? S.y[3 * myrow + 1] * nb : 0.0;
+                wy[2] = is_free ? S.y[3 * myrow + 2] * nb : 0.0;
+            }
+            if (lane == 0) P.warm_ok[2 * e + warp] = have_y ? 1 : 0;
+        }
 #ifdef BW_PROFILE
         if (lane == 0) {
             sh_prof_solve[warp] = clock64() - prof_t[2];

@@ -14,7 +14,7 @@ BW_MAX_OBSTACLES = 8
 BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
-BW_ABI_VERSION = 3
+BW_ABI_VERSION = 4
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")
@@ -83,6 +83,21 @@ class bw_interface(C.Structure):
                 ("fn0", C.c_double), ("ft0", C.c_double), ("fn1", C.c_double), ("ft1", C.c_double)]
 
 
+class bw_transition(C.Structure):
+    _fields_ = [("block_bits", C.c_uint64 * BW_IMG), ("action_bits", C.c_uint64 * BW_IMG),
+                ("next_block_bits", C.c_uint64 * BW_IMG), ("action", bw_action),
+                ("reward", C.c_float), ("lin_reward", C.c_float), ("env", C.c_int32), ("step", C.c_int32),
+                ("n_next_candidates", C.c_int32),
+                ("binary", C.c_uint8), ("next_binary", C.c_uint8), ("done", C.c_uint8), ("terminated", C.c_uint8),
+                ("truncated", C.c_uint8), ("stable", C.c_uint8), ("stable_unfrozen", C.c_uint8), ("valid", C.c_uint8),
+                ("reserved", C.c_uint8 * 4)]
+
+
+class bw_rollout_view(C.Structure):
+    _fields_ = [("cand", C.c_void_p), ("valid", C.c_void_p), ("n_cand", C.c_void_p), ("n_valid", C.c_void_p),
+                ("action_bits", C.c_void_p), ("amax", C.c_int32), ("reserved0", C.c_int32)]
+
+
 # numpy views of the same layouts (for bulk transfers)
 def np_dtypes():
     import numpy as np
@@ -103,10 +118,18 @@ def np_dtypes():
     interface = np.dtype([("body_a", "<i4"), ("body_b", "<i4"), ("face_a", "<i4"), ("face_b", "<i4"),
                           ("nx", "<f8"), ("nz", "<f8"), ("p0x", "<f8"), ("p0z", "<f8"), ("p1x", "<f8"),
                           ("p1z", "<f8"), ("fn0", "<f8"), ("ft0", "<f8"), ("fn1", "<f8"), ("ft1", "<f8")])
+    transition = np.dtype([("block_bits", "<u8", (BW_IMG,)), ("action_bits", "<u8", (BW_IMG,)),
+                           ("next_block_bits", "<u8", (BW_IMG,)), ("action", action),
+                           ("reward", "<f4"), ("lin_reward", "<f4"), ("env", "<i4"), ("step", "<i4"),
+                           ("n_next_candidates", "<i4"),
+                           ("binary", "u1"), ("next_binary", "u1"), ("done", "u1"), ("terminated", "u1"),
+                           ("truncated", "u1"), ("stable", "u1"), ("stable_unfrozen", "u1"), ("valid", "u1"),
+                           ("reserved", "u1", (4,))])
+    assert transition.itemsize == C.sizeof(bw_transition) == 1608
     assert action.itemsize == C.sizeof(bw_action) and step_out.itemsize == C.sizeof(bw_step_out)
     assert block.itemsize == C.sizeof(bw_block) and task.itemsize == C.sizeof(bw_task)
     assert interface.itemsize == C.sizeof(bw_interface)
-    return dict(action=action, step_out=step_out, block=block, task=task, interface=interface)
+    return dict(action=action, step_out=step_out, block=block, task=task, interface=interface, transition=transition)
 
 
 # every symbol include/bridges_b200.h declares: name -> (restype, argtypes)
@@ -135,6 +158,11 @@ SIGNATURES = {
     "bw_candidate_overflow": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bw_expand_bits": (C.c_int, [_H, _P, C.c_int64, _P]),
     "bw_select_random": (C.c_int, [_H, _P, _P, _P, C.c_int32, C.c_uint64, _P, _P]),
+    "bw_rollout_configure": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "bw_rollout_begin": (C.c_int, [_H, C.POINTER(bw_rollout_view)]),
+    "bw_rollout_commit": (C.c_int, [_H, _P, _P, C.POINTER(bw_obs_out)]),
+    "bw_rollout_random": (C.c_int, [_H, C.c_int32, C.c_uint64, _P, C.c_int64, C.c_int64]),
+    "bw_unpack_transitions": (C.c_int, [_H, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bw_get_state": (C.c_int, [_H, _P, _P]),
     "bw_get_raster_bits": (C.c_int, [_H, _P, _P]),
     "bw_copy_raster_bits": (C.c_int, [_H, _P, _P]),

@@ -5,8 +5,9 @@ task (BASELINE.json configs[1] / configs[2]), success rate against wall-clock ti
 This is NOT robotoddler's learner (out of scope): it only shows the
 pieces of this repository working together the way `successor_dqn.py` would use them -- lock-step
 environments, the candidate kernel, one batched Q-network pass per step (`rollout.q_network_policy`,
-the network has the reference's 5-argument signature, models/cv.py:76-105), bit-packed transitions on
-the device -- with the simplest possible learning rule (regression of Q(s, a) on Monte-Carlo returns).
+the network has the reference's 5-argument signature, models/cv.py:76-105), the fused rollout
+(`bw_rollout_begin` / `bw_rollout_commit`) with its packed transition records on the device -- with the simplest
+possible learning rule (regression of Q(s, a) on Monte-Carlo returns).
 
     python examples/train_tower.py --tower-height 2 --envs 1024 --iters 30
 """
@@ -25,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 from bench import X_GROUND, task_def                                  # noqa: E402
 from bridges_b200.envs.batched import BatchedAssemblyGym              # noqa: E402
-from bridges_b200.rollout import q_network_policy                     # noqa: E402
+from bridges_b200.rollout import FusedRollout, q_network_policy, record_column   # noqa: E402
 
 
 class QNet(nn.Module):
@@ -44,46 +45,31 @@ class QNet(nn.Module):
         return self.head(torch.cat([x, binary], dim=1)).squeeze(1), None, None
 
 
-def collect(env, policy, steps, gamma):
-    """`steps` lock-step environment steps; returns time-major tensors and Monte-Carlo returns of the
-    transitions whose episode ended inside the chunk."""
-    E, dev = env.num_envs, env.device
-    rec = dict(block=[], action=[], binary=[], reward=[], done=[], has=[])
-    binary = env.observe(block=False, binary=True)["binary"]
+def collect(roll, policy, steps, gamma):
+    """`steps` lock-step iterations of the fused rollout around `policy`; returns the packed records of the
+    transitions whose episode ended inside the chunk with their Monte-Carlo returns."""
+    E, dev = roll.env.num_envs, roll.env.device
+    recs = []
     for _ in range(steps):
-        cand = env.enumerate_actions(X_GROUND, (0.0,), amax=128, with_bits=True)
-        actions, index = policy(env, cand)
-        has = index >= 0
-        rec["block"].append(env.raster_bits_device())
-        rec["action"].append(cand["bits"][torch.arange(E, device=dev), index.clamp(min=0).long()].clone())
-        rec["binary"].append(binary)
-        nxt = torch.empty_like(binary)
-        out_dev = env.step(actions, binary=nxt)
-        out = env.read_out(out_dev)
-        done = torch.from_numpy((out["terminated"] | out["truncated"]).astype(bool)).to(dev) | ~has
-        rec["reward"].append(torch.from_numpy(out["reward"].copy()).to(dev))
-        rec["done"].append(done)
-        rec["has"].append(has)
-        env.reset_done()
-        if bool((~has).any()):
-            env.reset(None, mask=(~has).to(torch.uint8).cpu().numpy())
-        fresh = torch.tensor([1.0, 0, 0, 0, 0, 0], device=dev).expand(E, 6)
-        binary = torch.where(done[:, None], fresh, nxt)
-    T = steps
-    reward, done, has = torch.stack(rec["reward"]), torch.stack(rec["done"]), torch.stack(rec["has"])
+        recs.append(roll.step(policy(roll.env, roll.candidates())).clone())
+    R = torch.stack(recs)                                             # [T, E, REC] uint8
+    reward, done = record_column(R, "reward"), record_column(R, "done") != 0
+    has = record_column(R, "valid") != 0
     ret = torch.zeros_like(reward)
     complete = torch.zeros_like(done)
     g = torch.zeros(E, device=dev)
     c = torch.zeros(E, dtype=torch.bool, device=dev)
-    for t in range(T - 1, -1, -1):
+    for t in range(steps - 1, -1, -1):
         g = torch.where(done[t], reward[t], reward[t] + gamma * g)
         c = done[t] | c
         ret[t], complete[t] = g, c
     keep = (complete & has).reshape(-1)
-    flat = lambda xs: torch.stack(xs).reshape(T * E, *xs[0].shape[1:])[keep]
-    episodes = int(done.sum())
-    success = int((done & (reward >= 1.0)).sum())
-    return dict(block=flat(rec["block"]), action=flat(rec["action"]), binary=flat(rec["binary"]),
+    flat = R.reshape(steps * E, -1)[keep]
+    binary = record_column(flat, "binary")
+    episodes = int((done & has).sum())
+    success = int((done & has & (reward >= 1.0)).sum())
+    return dict(block=record_column(flat, "block_bits"), action=record_column(flat, "action_bits"),
+                binary=((binary[:, None] >> torch.arange(6, device=dev)) & 1).float(),
                 ret=ret.reshape(-1)[keep]), episodes, success
 
 
@@ -104,6 +90,7 @@ def main():
     env.reset(task_def(args.tower_height))
     dev = env.device
     feats = env.observe(block=False, binary=False, obstacle=True, reward=True)
+    roll = FusedRollout(env, X_GROUND, (0.0,), amax=128 if args.max_steps <= 10 else 256, chunk_steps=1)
     net = QNet().to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     buf = None
@@ -114,7 +101,7 @@ def main():
     for it in range(args.iters):
         eps = max(0.05, 0.9 * (0.85 ** it))
         policy = q_network_policy(net, feats["reward"], feats["obstacle"], epsilon=eps, seed=it)
-        data, episodes, success = collect(env, policy, args.chunk, args.gamma)
+        data, episodes, success = collect(roll, policy, args.chunk, args.gamma)
         env_steps += args.chunk * args.envs
         buf = data if buf is None else {k: torch.cat([buf[k], data[k]])[-400000:] for k in data}
         n = buf["ret"].numel()
@@ -133,7 +120,8 @@ def main():
             loss_v = float(loss.detach())
         # greedy evaluation
         env.reset(task_def(args.tower_height))
-        _, ev_episodes, ev_success = collect(env, q_network_policy(net, feats["reward"], feats["obstacle"]),
+        roll.begin()
+        _, ev_episodes, ev_success = collect(roll, q_network_policy(net, feats["reward"], feats["obstacle"]),
                                              args.max_steps + 2, args.gamma)
         row = dict(iter=it, wall_s=time.perf_counter() - t0, env_steps=env_steps, epsilon=eps, loss=loss_v,
                    explore_success=success / max(episodes, 1), greedy_success=ev_success / max(ev_episodes, 1),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 3
+#define BW_ABI_VERSION 4
 
 /* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
 #define BW_MAX_BLOCKS 16
@@ -248,6 +248,67 @@ int bw_expand_bits(bw_handle *h, const uint64_t *d_bits, int64_t n, float *d_img
  * next bw_reset_done starts them afresh. */
 int bw_select_random(bw_handle *h, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
                      int32_t amax, uint64_t seed, bw_action *d_actions, int32_t *d_index);
+
+/* ---- fused lock-step rollout: rollout_episode (successor_dqn.py:365-475) for E environments at once, with the
+ * transitions (Transition, successor_dqn.py:27-44) written as packed records into a caller-owned device ring that
+ * plays the part of ReplayBuffer.memory (robotoddler/utils/replay_memory.py:10-43).  One iteration =
+ *     policy picks one valid candidate per environment  ->  step + stabilities_freezing + lin_reward  ->
+ *     record  ->  auto-reset of finished episodes  ->  candidates of the next states (generate_actions +
+ *     get_action_features + filter_actions)  ->  done |= "no candidate left" (successor_dqn.py:409-411)
+ * as a fixed sequence of kernels on the handle's stream: no host synchronisation, no per-step host work besides
+ * the launches.  Rasters stay bit-packed (bit x of word r = pixel (row r, column x)). */
+typedef struct {
+    uint64_t block_bits[BW_IMG];       /* block_features: render_blocks_2d of the state before the step */
+    uint64_t action_bits[BW_IMG];      /* action_features: raster of the chosen candidate */
+    uint64_t next_block_bits[BW_IMG];  /* next_block_features */
+    bw_action action;                  /* the chosen Action */
+    float reward;                      /* sparse_reward (gym_env.py:11-22) */
+    float lin_reward;                  /* successor_dqn.py:397-401 */
+    int32_t env;                       /* global environment index (env_id_base + e) */
+    int32_t step;                      /* rollout iteration counter of the handle */
+    int32_t n_next_candidates;         /* valid candidates of the next state (meaningful when the episode goes on) */
+    uint8_t binary;                    /* binary_features of the state before, bit k = feature k (stable, collision,
+                                          collision_block, _obstacle, _floor, _boundary) */
+    uint8_t next_binary;
+    uint8_t done;                      /* terminated | truncated | no candidate left in the next state */
+    uint8_t terminated, truncated;
+    uint8_t stable, stable_unfrozen;   /* stabilities_freezing() of the new state */
+    uint8_t valid;                     /* 0: this environment had no candidate in this iteration: not a transition */
+    uint8_t reserved[4];
+} bw_transition;                       /* 1608 bytes */
+
+/* device views of the candidate buffers the handle keeps for the rollout (valid until the next rollout call) */
+typedef struct {
+    const bw_action *cand;       /* [E,amax] in generate_actions order */
+    const uint8_t *valid;        /* [E,amax] filter_actions mask */
+    const int32_t *n_cand;       /* [E] */
+    const int32_t *n_valid;      /* [E] */
+    const uint64_t *action_bits; /* [E,amax,64] */
+    int32_t amax;
+    int32_t reserved0;
+} bw_rollout_view;
+
+/* arguments of generate_actions for the rollout; allocates the handle-owned candidate buffers.
+ * env_id_base: added to the environment index in the records (rank * E on a sharded run). */
+int bw_rollout_configure(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
+                         int32_t n_offsets, int32_t amax, int32_t env_id_base);
+/* candidates of the CURRENT states (first call, or after bw_reset / bw_step changed them behind the rollout's
+ * back; bw_rollout_commit leaves the candidates of the next states behind by itself).  out may be NULL. */
+int bw_rollout_begin(bw_handle *h, bw_rollout_view *out);
+/* one iteration with the caller's policy: d_index[e] = index of the chosen candidate of environment e (ignored
+ * where n_valid[e] = 0).  d_slots: E records (record e belongs to environment e).  obs: optional observation
+ * outputs of the step as in bw_step (device pointers), may be NULL. */
+int bw_rollout_commit(bw_handle *h, const int32_t *d_index, bw_transition *d_slots, const bw_obs_out *obs);
+/* n_steps iterations with the built-in uniformly random policy (the synthetic policy of the benchmarks).  The
+ * records of iteration k go to d_ring[(start + k*E + e) % capacity]; capacity must be a multiple of E. */
+int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transition *d_ring, int64_t capacity,
+                      int64_t start);
+/* ReplayBuffer.sample(stack_tensors=True) for packed records: expands the records d_ring[d_indices[i]] into the
+ * learner's tensors; any output may be NULL.  Images [n,1,64,64] f32, binary [n,6] f32, reward / lin_reward [n]
+ * f32, done [n] u8. */
+int bw_unpack_transitions(bw_handle *h, const bw_transition *d_ring, const int64_t *d_indices, int64_t n,
+                          float *d_block, float *d_action, float *d_next_block, float *d_binary, float *d_next_binary,
+                          float *d_reward, float *d_lin_reward, uint8_t *d_done);
 
 /* ---- state read-back (adapters, checkpointing, tests) ------------------------------ */
 int bw_get_state(bw_handle *h, bw_block *h_blocks /*[E,BW_MAX_BLOCKS]*/, int32_t *h_n_blocks /*[E]*/);

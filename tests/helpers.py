@@ -76,7 +76,8 @@ def bits_of(img):
 
 def replay_worker(job):
     """job: dict(shapes, obstacles, targets, mu, max_steps, actions=[tuple | None per lock-step iteration],
-    x_ground, offsets, cand_steps=set of iterations at which the candidate list / filter mask is wanted too).
+    x_ground, offsets, cand_steps=set of iterations at which the candidate list / filter mask is wanted too,
+    reset_after=iterations after which the environment is reset although its episode did not end by itself).
     The environment is reset after every iteration that ended its episode (terminated | truncated) or offered
     no action (None) -- what `reset_done` does on the GPU.  Returns one dict per iteration."""
     from oracle import actions as oact
@@ -111,7 +112,7 @@ def replay_worker(job):
                    bits=bits_of(o_render(blocks, XLIM, YLIM, IMG)), new_bits=bits_of(o_render(blocks[-1:], XLIM, YLIM, IMG)),
                    pose=blocks[-1].pose)
         out.append(rec)
-        if terminated or truncated:
+        if terminated or truncated or k in job.get("reset_after", ()):
             obs, _ = env.reset()
     return out
 
