@@ -1007,6 +1007,32 @@ int bw_render_blocks_host(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n
     return BW_OK;
 }
 
+int bw_contains_2d_host(bw_handle *h, const bw_shape_desc *h_shape, const bw_block *h_block, const double *h_points_xz,
+                        int64_t n, uint8_t *h_inside) {
+    if (!h || !h_shape || !h_points_xz || !h_inside || n < 0) return BW_ERR_INVALID;
+    if (!shape_ok(*h_shape)) return fail(h, BW_ERR_INVALID, "shape: bad face/vertex count or mass data");
+    if (n == 0) return BW_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    ShapeDev sd;
+    shape_to_dev(*h_shape, sd);
+    Pose ps;
+    ps.x = h_block ? h_block->x : 0.0; ps.z = h_block ? h_block->z : 0.0;
+    ps.c = h_block ? h_block->c : 1.0; ps.s = h_block ? h_block->s : 0.0;
+    double *d_pts = nullptr;
+    uint8_t *d_in = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void **>(&d_pts), sizeof(double) * 2 * n, h->stream));
+    CU(cudaMallocAsync(reinterpret_cast<void **>(&d_in), n, h->stream));
+    CU(cudaMemcpyAsync(d_pts, h_points_xz, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    launch_contains_points(sd, ps, d_pts, n, d_in, h->stream);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_inside, d_in, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaFreeAsync(d_pts, h->stream));
+    CU(cudaFreeAsync(d_in, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
 int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h_n_itf) {
     if (!h || !h_itf || !h_n_itf || variant < 0 || variant > 1) return BW_ERR_INVALID;
     if (int rc = need_shapes(h)) return rc;

@@ -20,6 +20,8 @@ void launch_observe(const Params &P, float *d_block_img, float *d_binary, float 
                     cudaStream_t stream);
 void launch_expand_bits(const uint64_t *d_bits, int64_t n, float *d_img, cudaStream_t stream);
 
+void launch_contains_points(const ShapeDev &sh, const Pose &ps, const double *d_pts, int64_t n, uint8_t *d_inside,
+                            cudaStream_t stream);
 void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_block *d_blocks, int n_blocks,
                           uint64_t *d_bits, cudaStream_t stream);
 

@@ -157,6 +157,30 @@ render_blocks_kernel(Params P, const ShapeDev *__restrict__ shapes, const bw_blo
     bits[row] = acc;
 }
 
+// Shape.contains_2d (assembly_env.py:126-137) for arbitrary points: inside iff every half-plane value
+// (p - c).n, evaluated with individually rounded operations like the rasters, is <= 0
+__global__ void contains_points_kernel(ShapeDev sh, Pose ps, const double *__restrict__ pts, int64_t n,
+                                       uint8_t *__restrict__ inside) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = pts[2 * i], pz = pts[2 * i + 1];
+    bool in = true;
+    for (int k = 0; k < sh.n_faces; k++) {
+        double nx, nz, ax, az;
+        rot(ps.c, ps.s, sh.face_nx[k], sh.face_nz[k], nx, nz);
+        rot(ps.c, ps.s, sh.face_cx[k], sh.face_cz[k], ax, az);
+        const double cx = dadd(ax, ps.x), cz = dadd(az, ps.z);
+        in = in && (dadd(dmul(dsub(px, cx), nx), dmul(dsub(pz, cz), nz)) <= 0.0);
+    }
+    inside[i] = in ? 1 : 0;
+}
+
+void launch_contains_points(const ShapeDev &sh, const Pose &ps, const double *d_pts, int64_t n, uint8_t *d_inside,
+                            cudaStream_t stream) {
+    if (n <= 0) return;
+    contains_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sh, ps, d_pts, n, d_inside);
+}
+
 void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_block *d_blocks, int n_blocks,
                           uint64_t *d_bits, cudaStream_t stream) {
     render_blocks_kernel<<<1, 64, 0, stream>>>(P, d_shapes, d_blocks, n_blocks, d_bits);

@@ -82,6 +82,11 @@ class Shape:
             x, z = self._xz(p)
             yield [x, z]
 
+    def contains_2d(self, points):
+        """assembly_env.py:126-137, evaluated by the CUDA library (same arithmetic as the rasters)."""
+        from ..utils.rendering import contains_2d
+        return contains_2d(self, points)
+
     def get_face_frame_2d(self, face):
         c = self._xz(self.tables.centers[face])
         n = self._dir(self.tables.normals[face])

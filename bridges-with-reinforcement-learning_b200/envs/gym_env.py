@@ -68,6 +68,16 @@ def hard_tower_setup():
     return dict(shapes=[trapezoid, cube], targets=[[0, 0, 0.5], [0, 0, 5.5]], obstacles=[[0, 0, 2.0]])
 
 
+def connecting_setup():
+    """gym_env.py:91-99."""
+    rectangle = Shape(urdf_file='shapes/block.urdf', name="rectangle", receiving_faces_2d=[3], target_faces_2d=[0])
+    cube = Shape(urdf_file='shapes/cube1.urdf', name="cube", receiving_faces_2d=[3], target_faces_2d=[1])
+    targets = [[np.random.uniform(0.4, 0.6), 0, 0.175] for _ in range(3)]
+    obstacles = [[np.random.uniform(0.4, 0.47), 0, np.random.uniform(0.025, 0.125)],
+                 [np.random.uniform(0.53, 0.6), 0, np.random.uniform(0.025, 0.125)]]
+    return dict(shapes=[rectangle, cube], obstacles=obstacles, targets=targets)
+
+
 def tower_height_setup(tower_height=2, square_size=0.6):
     """The `--tower_height=k` task named by BASELINE.json (absent from the reference snapshot;
     definition: SURVEY.md section 8(d).3)."""

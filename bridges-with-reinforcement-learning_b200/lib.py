@@ -166,6 +166,7 @@ SIGNATURES = {
     "bw_get_state": (C.c_int, [_H, _P, _P]),
     "bw_get_raster_bits": (C.c_int, [_H, _P, _P]),
     "bw_copy_raster_bits": (C.c_int, [_H, _P, _P]),
+    "bw_contains_2d_host": (C.c_int, [_H, C.POINTER(bw_shape_desc), _P, _P, C.c_int64, _P]),
     "bw_get_forces": (C.c_int, [_H, C.c_int32, _P, _P]),
     "bw_get_target_state": (C.c_int, [_H, _P, _P, _P]),
     "bw_query_placement_host": (C.c_int, [_H, _P, _P, _P, _P, _P]),

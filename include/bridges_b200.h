@@ -329,6 +329,11 @@ int bw_query_placement_host(bw_handle *h, const bw_action *h_actions, const doub
  * blocks[i].shape indexes h_shapes; h_bits[64], bit x of word r = pixel (row r, col x) */
 int bw_render_blocks_host(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n_shapes, const bw_block *h_blocks,
                           int32_t n_blocks, const double *xlim2, const double *ylim2, uint64_t *h_bits);
+/* Shape.contains_2d / Block.contains_2d (assembly_env.py:126-137) for n arbitrary points (x, z): h_inside[i] = 1 iff
+ * the point lies in every half-plane of the shape posed at h_block (NULL = the unposed shape of the library file).
+ * The drop-in render_blocks_2d uses it for image sizes other than 64 x 64 (rendering.py:105-113). */
+int bw_contains_2d_host(bw_handle *h, const bw_shape_desc *h_shape, const bw_block *h_block, const double *h_points_xz,
+                        int64_t n, uint8_t *h_inside);
 /* interfaces and min-norm contact forces of the last step / evaluation (frozen variant) */
 /* variant 0: supports as in the last step's verdict (new block frozen); 1: last block released */
 int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf /*[E,BW_MAX_INTERFACES]*/, int32_t *h_n_itf /*[E]*/);

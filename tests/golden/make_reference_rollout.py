@@ -1,4 +1,4 @@
-"""Generates tests/golden/reference_rollout_trace.json: the reference's UNMODIFIED `rollout_episode`
+"""Generates tests/golden/reference_rollout_trace.json.gz: the reference's UNMODIFIED `rollout_episode`
 (robotoddler/training/successor_dqn.py:365-475), `EpsilonGreedy`, `generate_actions` / `filter_actions`
 (robotoddler/utils/actions.py), `SuccessorMLP` (robotoddler/models/cv.py:76-105), `ReplayBuffer` and
 `train_policy_net` (successor_dqn.py:157-277) are imported from /root/reference and run for a few episodes with the
@@ -84,14 +84,20 @@ class RecordingGym(ogym.AssemblyGym):
         TRACE.append(dict(op="stabilities_freezing", result=[bool(out[0]), bool(out[1])]))
         return out
 
+    _nested = False
+
     def create_block(self, action):
         b = super().create_block(action)
-        TRACE.append(dict(op="create_block", action=act(action), block=blk(b),
-                          vertices_2d=[[fx(x), fx(z)] for x, z in b.vertices_2d]))
+        if not self._nested:                # (the oracle's collision_on_action poses the block through create_block)
+            TRACE.append(dict(op="create_block", action=act(action), block=blk(b)))
         return b
 
     def collision_on_action(self, action, xlim, ylim):
-        out = super().collision_on_action(action, xlim, ylim)
+        self._nested = True
+        try:
+            out = super().collision_on_action(action, xlim, ylim)
+        finally:
+            self._nested = False
         TRACE.append(dict(op="collision_on_action", action=act(action), xlim=[fx(v) for v in xlim],
                           ylim=[fx(v) for v in ylim], result=bool(out)))
         return out
@@ -107,6 +113,29 @@ def recording_render(blocks, xlim, ylim, img_size=(512, 512)):
 
 def _not_part_of_the_env(*a, **k):
     raise NotImplementedError("plotting helper: not used by rollout_episode(log_images=False)")
+
+
+class Frame(tuple):
+    """The oracle keeps the face frame of assembly_env.py:118-124 as a (point, normal) pair of the xz-plane and
+    unpacks it as such; the reference's callers read compas' Frame attributes.  This pair offers both."""
+
+    @property
+    def point(self):
+        return [self[0][0], 0.0, self[0][1]]
+
+    @property
+    def normal(self):
+        return [self[1][0], 0.0, self[1][1]]
+
+    @property
+    def xaxis(self):
+        return [self[1][1], 0.0, -self[1][0]]
+
+    zaxis = normal
+
+
+_plain_frame = oae.Shape.get_face_frame_2d
+oae.Shape.get_face_frame_2d = lambda self, face: Frame(_plain_frame(self, face))
 
 
 def install_modules():
@@ -189,9 +218,10 @@ def main():
                            setup="horizontal_bridge_setup(num_obstacles=1)", seed=3, episodes=3),
                xlim=[fx(v) for v in xlim], ylim=[fx(v) for v in ylim], x_discr_ground=[fx(v) for v in x_discr_ground],
                calls=TRACE, transitions=episodes, train_losses=losses)
-    path = os.path.join(HERE, "reference_rollout_trace.json")
-    with open(path, "w") as fh:
-        json.dump(doc, fh, separators=(",", ":"))
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "reference_rollout_trace.json.gz")
+    import gzip
+    with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as fh:
+        fh.write(json.dumps(doc, separators=(",", ":")).encode())
     ops = {}
     for c in TRACE:
         ops[c["op"]] = ops.get(c["op"], 0) + 1
