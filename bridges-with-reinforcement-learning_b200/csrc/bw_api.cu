@@ -23,6 +23,7 @@ struct bw_handle {
     bool force_staged = false;   // bw_set_host_transfer(h, 1): *_host calls always stage through device buffers
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int smem_step = 0;
+    int n_sm = 148, smem_per_sm = 233472;
     int64_t launches = 0;
     char err[512] = {0};
     // owned device buffers
@@ -60,6 +61,39 @@ struct bw_handle {
     uint64_t *d_rbits = nullptr;
     double *d_rxs = nullptr, *d_rys = nullptr;
 };
+
+// Shared-memory layout of the step kernel.  A launch that fits the GPU in one wave keeps everything in shared memory
+// (two packed matrices, block library, pixel nodes): its length is the slowest environment's solve, nothing else
+// matters.  With more environments than CTA slots the kernel is bound by how many latency-bound CTAs an SM holds:
+// the two problems then share one packed matrix and the library stays in global memory when that buys a slot.
+// BW_SHARE_H=0/1 overrides the choice (tuning hook, tools/ only).
+static void choose_step_layout(bw_handle *h, int n_shapes) {
+    Params &P = h->P;
+    auto slots = [&](int bytes) {
+        const int per_cta = bytes + 2560 /* static */ + 1024 /* reserved per CTA */;
+        int c = h->smem_per_sm / per_cta;
+        if (c > 8) c = 8;                        // 128 registers x 64 threads
+        return c * h->n_sm;
+    };
+    const int full = step_smem_bytes(P.max_blocks, P.max_itf, n_shapes, false, true);
+    bool share = false, lib = true;
+    // (measured, profiles/README.md round 2: at 1.4 waves the turn-taking costs more than the extra slots give --
+    // 6.42 against 6.73 M env steps/s on the bridge task at 1024 environments -- from two waves on it pays:
+    // 2.19 against 2.69 ms per pass of the 65,536-assembly sweep)
+    if (P.E >= 2 * slots(full)) {
+        const int lean = step_smem_bytes(P.max_blocks, P.max_itf, n_shapes, true, true);
+        const int leaner = step_smem_bytes(P.max_blocks, P.max_itf, n_shapes, true, false);
+        if (slots(lean) > slots(full)) share = true;
+        if (slots(leaner) > slots(lean)) { share = true; lib = false; }
+    }
+    if (const char *ov = getenv("BW_SHARE_H")) {
+        share = atoi(ov) != 0;
+        lib = !(share && atoi(ov) >= 2);
+    }
+    P.share_h = share ? 1 : 0;
+    P.lib_in_smem = lib ? 1 : 0;
+    h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf, n_shapes, share, lib);
+}
 
 static int fail(bw_handle *h, int code, const char *fmt, ...) {
     if (h) {
@@ -331,6 +365,18 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     P.warm_start = getenv("BW_NO_WARM") ? 0 : 1;   // tuning hook (tools/ only): every solve from y = 0
     CU(dev_alloc(h, &P.cand_need, 1));
     CU(dev_alloc(h, &P.reset_err, 1));
+    {   // CTA order of the step kernel: the first launch takes the environments in index order
+        CU(dev_alloc(h, &P.order_cnt, 3 * ORDER_KEYS));
+        CU(dev_alloc(h, &P.order_q, (size_t)3 * ORDER_KEYS * E, false));
+        std::vector<int32_t> ident(E);
+        for (int i = 0; i < E; i++) ident[i] = i;
+        const int32_t all = E;
+        CU(cudaMemcpyAsync(P.order_q, ident.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->stream));   // queue 0, class 0
+        CU(cudaMemcpyAsync(P.order_cnt, &all, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        P.order_phase = 0;
+        P.order_on = getenv("BW_NO_ORDER") ? 0 : 1;   // tuning hook (tools/ only): CTA i = environment i
+    }
     {
         std::vector<double> mu(E, cfg->mu);
         CU(cudaMemcpyAsync(P.mu, mu.data(), sizeof(double) * E, cudaMemcpyHostToDevice, h->stream));
@@ -371,8 +417,14 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     }
     // the step kernel keeps the block library in shared memory: sized for the largest library here,
     // re-sized for the actual one by bw_load_shapes
-    h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf, BW_MAX_SHAPES);
-    CU(configure_step(h->smem_step));
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, cfg->device));
+        h->n_sm = prop.multiProcessorCount;
+        h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    }
+    choose_step_layout(h, BW_MAX_SHAPES);
+    CU(configure_step(step_smem_bytes(P.max_blocks, P.max_itf, BW_MAX_SHAPES, false, true)));   // the largest layout
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
@@ -415,7 +467,7 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->P.n_shapes = n;
-    h->smem_step = step_smem_bytes(h->P.max_blocks, h->P.max_itf, n);
+    choose_step_layout(h, n);
     h->shapes_loaded = true;
     h->n_groups = 0;
     for (int i = 0; i < n; i++)

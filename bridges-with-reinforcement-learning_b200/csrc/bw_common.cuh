@@ -19,6 +19,7 @@ constexpr int NV = BW_MAX_VERTS;           // 6
 constexpr int IMG = BW_IMG;                // 64
 constexpr int MAXITF = BW_MAX_INTERFACES;  // 48
 constexpr int MAXC = 2 * MAXITF;           // contact points
+constexpr int ORDER_KEYS = 32;             // cost classes of the step kernel's CTA order
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -94,6 +95,20 @@ struct Params {
     uint8_t *warm_ok;          // [E][2] the entry holds the iterate of a solve that ended feasible
     int32_t warm_start;        // 0: every solve starts from y = 0 (tuning hook BW_NO_WARM)
     int32_t pad_ws;
+    // CTA -> environment order of the step kernel: the environments queue up for the NEXT launch by expected
+    // cost (key = 2 * blocks + "the frozen solve cannot be skipped", heaviest first), so that the long solves
+    // start with the first wave of CTAs and the short ones fill in behind them.  Three queues in rotation:
+    // launch t reads queue t % 3, fills queue (t + 1) % 3 and clears the counters of queue (t + 2) % 3.
+    int32_t *order_cnt;        // [3][ORDER_KEYS]
+    int32_t *order_q;          // [3][ORDER_KEYS][E]
+    int32_t order_phase;       // queue read by the next launch (host side, advanced by launch_step)
+    int32_t order_on;          // 0: CTA i = environment i (tuning hook BW_NO_ORDER)
+    // shared-memory diet of multi-wave launches (more environments than CTA slots): the two problems of an
+    // environment share one packed matrix and take turns (share_h), the block library and the pixel nodes stay in
+    // global memory (lib_in_smem = 0) -- both buy resident CTAs per SM, which is what a latency-bound kernel needs
+    // once there is more than one wave of work
+    int32_t share_h;
+    int32_t lib_in_smem;
     int32_t *cand_need;        // [1] largest untruncated candidate count an enumeration had to cut to `amax`
     int32_t *reset_err;        // [1] environments whose reset task was refused (bad shape index / too many blocks)
 };

@@ -105,6 +105,7 @@ struct Solver {
     // this problem
     double *y, *yk, *d, *b, *g, *h, *f, *invd;
     double *L;               // packed lower triangle, rows 0..m; row m carries the right-hand side
+    unsigned *adjm;          // [NBODY] scratch of the mechanism screen
     uint8_t *typ;
     int8_t *rowbase;         // body -> first row or -1 (support)
     uint8_t *freebody;       // free block index -> body
@@ -466,13 +467,12 @@ struct Solver {
     // (tools/solver_lab.py: an LP on the aggregated 3-row systems catches the same cases).
     // All sets are examined in one pass: lane = (set, boundary contact point) work item, at most a few
     // chunks of 32 items (a tower has two boundary contact points per set).
-    // Scratch: g, h, f (rays), invd (bodies of a contact), L (contact adjacency masks of the bodies),
+    // Scratch: g, h, f (rays), invd (bodies of a contact), adjm (contact adjacency masks of the bodies),
     // y, yk, d (work items).
     __device__ bool screen(const double *body, double invL0) {
         constexpr double EPS = 1e-10, DELTA = 1e-5;
         if (nc > 64) return false;
         uint8_t *cba = reinterpret_cast<uint8_t *>(invd), *cbb = cba + nc;
-        unsigned *adjm = reinterpret_cast<unsigned *>(L);               // [NBODY] free-free contact adjacency (68 B <= the 80 B of a 1-block L)
         if (lane < NBODY) adjm[lane] = 0u;
         __syncwarp();
 #pragma unroll 1

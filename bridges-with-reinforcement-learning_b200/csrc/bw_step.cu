@@ -61,7 +61,7 @@ void upload_step_tables() {
 // ------------------------------------------------------------------ shared memory layout
 struct Layout {
     // offsets in bytes from the start of dynamic shared memory
-    int pose, body, faces, pairs, contacts_G, contacts_ab, adj, prob[2], shapes, grid, total;
+    int pose, body, faces, pairs, contacts_G, contacts_ab, adj, prob[2], hshared, shapes, grid, total;
     int MM, MC, HS;
 };
 
@@ -71,7 +71,9 @@ struct ProbOff {  // offsets inside one problem block
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
+// with_h = false: the packed matrix is not part of the problem block (the two problems of the environment share
+// one, see Params::share_h); o.H is then meaningless
+__host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS, bool with_h = true) {
     ProbOff o;
     int p = 0;
     o.y = p; p += MM * 8;
@@ -82,7 +84,7 @@ __host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
     o.g = p; p += 2 * MC * 8;
     o.h = p; p += 2 * MC * 8;
     o.f = p; p += 2 * MC * 8;
-    o.H = p; p += HS * 8;
+    o.H = p; p += with_h ? HS * 8 : 0;
     o.typ = p; p += align16(MC);
     o.rowbase = p; p += align16(NBODY);
     o.freebody = p; p += align16(NB);
@@ -94,7 +96,8 @@ __host__ __device__ inline ProbOff prob_layout(int MM, int MC, int HS) {
 constexpr int BODY_DOUBLES = 8;   // comx, comz, weight, depth, xmin, xmax, zmin, zmax
 constexpr int FACE_DOUBLES = 8;   // nx, nz, cx, cz, e0x, e0z, e1x, e1z
 
-__host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n_shapes) {
+__host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n_shapes, bool share_h = false,
+                                              bool lib_in_smem = true) {
     Layout L;
     L.MM = 3 * max_blocks;
     L.MC = 2 * max_itf;
@@ -105,9 +108,11 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n
     L.contacts_G = p; p += L.MC * 12 * 8;
     L.contacts_ab = p; p += align16(2 * L.MC);
     L.adj = p; p += align16(NBODY + 1) + align16(2 * L.MC);
-    ProbOff po = prob_layout(L.MM, L.MC, L.HS);
+    ProbOff po = prob_layout(L.MM, L.MC, L.HS, !share_h);
     L.prob[0] = p; p += po.size;
     L.prob[1] = p; p += po.size;
+    L.hshared = p;
+    if (share_h) p += align16(L.HS * 8);
     // faces + pair scratch are dead once the contacts are assembled: they alias the
     // H matrices (the first bytes of problem 0 are y.. vectors which are initialised later)
     L.faces = L.prob[0];
@@ -115,14 +120,17 @@ __host__ __device__ inline Layout make_layout(int max_blocks, int max_itf, int n
     int scratch_end = L.pairs + NPAIR * 16 + align16(NPAIR * 2);
     if (scratch_end > p) p = scratch_end;
     p = align16(p);
-    // block library and pixel nodes: read many times per step, kept next to the problem data
-    L.shapes = p; p += align16(n_shapes * (int)sizeof(ShapeDev));
-    L.grid = p; p += 2 * IMG * 8;
+    // block library and pixel nodes: read many times per step, kept next to the problem data (unless the launch
+    // trades them for one more resident CTA per SM, Params::lib_in_smem)
+    L.shapes = p; p += lib_in_smem ? align16(n_shapes * (int)sizeof(ShapeDev)) : 0;
+    L.grid = p; p += lib_in_smem ? 2 * IMG * 8 : 0;
     L.total = align16(p);
     return L;
 }
 
-int step_smem_bytes(int max_blocks, int max_itf, int n_shapes) { return make_layout(max_blocks, max_itf, n_shapes).total; }
+int step_smem_bytes(int max_blocks, int max_itf, int n_shapes, bool share_h, bool lib_in_smem) {
+    return make_layout(max_blocks, max_itf, n_shapes, share_h, lib_in_smem).total;
+}
 
 // The optional image outputs of a step (bw_obs_out): the raster of all blocks as f32 [1,64,64] / u8 [64,64] /
 // bit-packed [64], from the CTA's shared copy `bits` (64 threads, 16-byte coalesced streaming stores).
@@ -154,6 +162,15 @@ __device__ __forceinline__ void write_obs_images(const bw_obs_out &obs, const ui
     }
 }
 
+// the environment joins the queue of the next launch (exactly once per launch, on every exit path)
+__device__ __forceinline__ void enqueue_next(const Params &P, int e, int n_blocks, bool frozen_solve_needed) {
+    if (!P.order_on) return;
+    const int key = min(ORDER_KEYS - 1, 2 * n_blocks + (frozen_solve_needed ? 1 : 0));
+    const int nxt = (P.order_phase + 1) % 3;
+    const int pos = atomicAdd(&P.order_cnt[nxt * ORDER_KEYS + key], 1);
+    P.order_q[((size_t)nxt * ORDER_KEYS + key) * P.E + pos] = e;
+}
+
 // ------------------------------------------------------------------ the kernel
 template <bool TWO>
 __global__ void __launch_bounds__(64)
@@ -163,17 +180,42 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     float *__restrict__ block_img = obs.block_img_f32;
     float *__restrict__ binary = obs.binary;
     extern __shared__ __align__(16) unsigned char smem[];
-    const int e = blockIdx.x;
-    if (mask != nullptr && mask[e] == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Layout L = make_layout(PG.max_blocks, PG.max_itf, PG.n_shapes);
+    int e = blockIdx.x;
+    if (PG.order_on) {
+        // heaviest environments first: ticket blockIdx.x into the queue filled by the previous launch
+        __shared__ int sh_env;
+        if (warp == 0) {
+            const int c = PG.order_cnt[PG.order_phase * ORDER_KEYS + (ORDER_KEYS - 1 - lane)];   // lane 0 = heaviest class
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const unsigned ahead = __ballot_sync(FULL, inc > (int)blockIdx.x);
+            const int cls = ahead ? __ffs(ahead) - 1 : 0;
+            const int before = __shfl_sync(FULL, inc - c, cls);
+            if (lane == 0)
+                sh_env = ahead ? PG.order_q[((size_t)PG.order_phase * ORDER_KEYS + (ORDER_KEYS - 1 - cls)) * PG.E + ((int)blockIdx.x - before)]
+                               : (int)blockIdx.x;
+            if (blockIdx.x == 0) PG.order_cnt[((PG.order_phase + 2) % 3) * ORDER_KEYS + lane] = 0;
+        }
+        __syncthreads();
+        e = sh_env;
+    }
+    if (mask != nullptr && mask[e] == 0) {
+        if (tid == 0) enqueue_next(PG, e, PG.n_blocks[e], !(PG.su_valid[e] != 0 && PG.last_out[e].stable_unfrozen != 0));
+        return;
+    }
+    const Layout L = make_layout(PG.max_blocks, PG.max_itf, PG.n_shapes, PG.share_h != 0, PG.lib_in_smem != 0);
     // P = the handle's parameters with the block library and the pixel nodes redirected to the
     // shared-memory copies made below (every helper of bw_common.cuh reads them through P)
     Params P = PG;
-    P.shapes = reinterpret_cast<const ShapeDev *>(smem + L.shapes);
-    P.xs = reinterpret_cast<const double *>(smem + L.grid);
-    P.ys = P.xs + IMG;
-    {
+    if (PG.lib_in_smem) {
+        P.shapes = reinterpret_cast<const ShapeDev *>(smem + L.shapes);
+        P.xs = reinterpret_cast<const double *>(smem + L.grid);
+        P.ys = P.xs + IMG;
         const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
         uint64_t *dst = reinterpret_cast<uint64_t *>(smem + L.shapes);
         const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
@@ -208,6 +250,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #endif
     __shared__ double sh_lin[2];
     __shared__ double sh_warm[2][3 * NB];   // starting points of the two solves (dual iterates of the last step)
+    __shared__ unsigned sh_adjm[2][NBODY + 1];   // mechanism screen: contact adjacency of the free blocks
+    __shared__ int sh_hlock;                // share_h: 1 while a solve owns the shared packed matrix
     __shared__ uint64_t sh_bits[IMG];      // raster of all blocks after this step
     __shared__ uint64_t sh_newbits[IMG];   // raster of the new block alone
     __shared__ double s_inv_nx[NF];        // 1 / n_x of the new block's posed faces (raster crossing estimate)
@@ -237,7 +281,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         s_pose[tid] = P.pose[(size_t)e * NB + tid];
         s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
     }
-    if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; }
+    if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; sh_hlock = 0; }
     if (tid < 4) sh_coll[tid] = 0;
     // stabilities_freezing()[1] of the previous step (all of today's free blocks were free and in
     // equilibrium): the frozen solve of this step has the same rows plus contacts to a new support,
@@ -288,6 +332,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             o.truncated = (uint8_t)(P.max_steps > 0 && n_old >= P.max_steps);
             out[e] = o;
             P.done[e] = 1;
+            enqueue_next(P, e, 0, false);           // flagged as over: the next launch sees it after a reset
             if (binary != nullptr) {
                 float *bf = binary + (size_t)e * 6;
                 bf[0] = (float)prev.stable; bf[1] = (float)prev.collision; bf[2] = (float)prev.collision_block;
@@ -608,7 +653,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     }
     {
         const uint32_t vmask = (warp == 0) ? smask : (n > 0 ? (smask & ~(1u << (n - 1))) : smask);
-        const ProbOff po = prob_layout(L.MM, L.MC, L.HS);
+        const ProbOff po = prob_layout(L.MM, L.MC, L.HS, PG.share_h == 0);
         unsigned char *pb = smem + L.prob[warp];
         Solver<TWO> S;
         S.G = s_G; S.c_a = s_ca; S.c_b = s_cb; S.adj_ptr = s_adj_ptr; S.adj = s_adj;
@@ -620,7 +665,9 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         S.h = reinterpret_cast<double *>(pb + po.h);
         S.f = reinterpret_cast<double *>(pb + po.f);
         S.invd = reinterpret_cast<double *>(pb + po.invd);
-        S.L = reinterpret_cast<double *>(pb + po.H);
+        // share_h: one packed matrix for both problems of the environment (the solves take turns, see below)
+        S.L = reinterpret_cast<double *>(PG.share_h ? smem + L.hshared : pb + po.H);
+        S.adjm = sh_adjm[warp];
         S.typ = pb + po.typ;
         S.rowbase = reinterpret_cast<int8_t *>(pb + po.rowbase);
         S.freebody = pb + po.freebody;
@@ -722,7 +769,34 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #pragma unroll 1
                     for (int i = lane; i < S.m; i += 32) S.y[i] = sh_warm[warp][i];
                 }
-                status = S.solve(res, iters, warm);
+                // share_h: the two solves of the environment use one packed matrix and take turns.  The warp that
+                // waits keeps an eye on its sibling's verdict: most of the time that verdict decides its own problem
+                // too (released equilibrium => frozen equilibrium, no frozen equilibrium => no released one) and
+                // the second solve never starts.
+                bool mine = true;
+                if (PG.share_h) {
+                    int got = 0;
+                    if (lane == 0) {
+                        while (true) {
+                            if (S.implied_by >= 0 && *S.sibling == S.implied_by) { got = 2; break; }
+                            if (atomicCAS(&sh_hlock, 0, 1) == 0) { got = 1; break; }
+                            __nanosleep(200);
+                        }
+                        // the sibling may have published between the check and the lock
+                        if (got == 1 && S.implied_by >= 0 && *S.sibling == S.implied_by) { atomicExch(&sh_hlock, 0); got = 2; }
+                    }
+                    got = __shfl_sync(FULL, got, 0);
+                    mine = (got == 1);
+                }
+                if (mine) {
+                    status = S.solve(res, iters, warm);
+                    if (PG.share_h) {
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); atomicExch(&sh_hlock, 0); }
+                    }
+                } else {
+                    status = 3;
+                }
                 // out of stages with a residual already under the verdict threshold: converged within the margin
                 if (status == 2 && res <= P.stable_tol) status = 0;
                 if (status == 3) { stable = S.implied_by; res = nan(""); }
@@ -881,6 +955,11 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         out[e] = o;
         P.last_out[e] = o;
         P.su_valid[e] = 1;
+        {   // expected cost of this environment in the next launch: one more block unless the episode ended; its
+            // frozen solve is skipped when the released verdict of this step was "stable"
+            const bool over = placed && (o.terminated || o.truncated);
+            enqueue_next(P, e, over ? 0 : (placed ? n + 1 : n), !over && !stable_unfrozen);
+        }
         if (binary != nullptr) {
             float *bf = binary + (size_t)e * 6;   // get_state_features, successor_dqn.py:53-60
             bf[0] = (float)stable_frozen; bf[1] = (float)o.collision; bf[2] = (float)o.collision_block;
@@ -915,7 +994,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #endif
 }
 
-void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
+void launch_step(Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
                  const bw_obs_out &obs, bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes,
                  cudaStream_t stream) {
     // 3 rows per free block + the right-hand side row: one row per lane up to 10 blocks
@@ -923,6 +1002,7 @@ void launch_step(const Params &P, const bw_action *d_actions, const uint8_t *d_m
         step_kernel<false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
     else
         step_kernel<true><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
+    P.order_phase = (P.order_phase + 1) % 3;     // the queue this launch filled is the next one's order
 }
 
 cudaError_t configure_step(int smem_bytes) {

@@ -14,14 +14,16 @@ for ln in open(sass):
         lines.append(cur)
 # region table from the sources: function starts
 import os
-ROOT = "/root/repo/bridges-with-reinforcement-learning_b200/csrc/"
+ROOT = os.environ.get("BW_SRC_ROOT", "/root/repo/bridges-with-reinforcement-learning_b200/csrc/")
 def regions_of(fname):
     out = []
     for i, t in enumerate(open(ROOT + fname).read().splitlines(), 1):
         m = re.match(r"\s*(?:template.*)?__device__.*?\b(\w+)\(", t)
         if m and "{" in t or (m and not t.strip().endswith(";")):
             out.append((i, m.group(1)))
-        m2 = re.match(r"\s*// -+ (phase \d[^\n]*|posed bodies[^\n]*)", t)
+        if re.match(r"\s*step_kernel\(", t):                      # the kernel's own prologue: state loads, CTA order
+            out.append((i, "kernel prologue (state loads)"))
+        m2 = re.match(r"\s*// -+ (phase \d[^\n]*|posed bodies[^\n]*|collision flags[^\n]*|raster update[^\n]*)", t)
         if m2:
             out.append((i, m2.group(1)[:40]))
     return out
