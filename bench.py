@@ -329,19 +329,21 @@ def measure_workload(job, wargs, K, W, steady_seconds, with_e2e_variants=True):
             cand_ev.append((a, b))
         return acts
 
-    # ---- warm-up (also brings the env population to its steady-state mix of block counts)
+    # ---- warm-up (also brings the env population to its steady-state mix of block counts).  Everything that makes
+    # the GPU wait -- the first NCCL collective (communicator set-up), the start of the nvidia-smi sampler -- happens
+    # BEFORE it, so that the barrier in front of the timed steps is a few microseconds and the clocks stay up
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    stats = []
+    sampler = ClockSampler(job.local_rank)
+    job.barrier()
+    sampler.start()
     for i in range(max(W, 3 * wargs.max_steps)):
         acts = choose_actions(i)
         env.step(acts, block_img=block_img, binary=binary)
         env.reset_done()
-    job.barrier()
+    launches0 = env.kernel_launches()
 
     # ---- device-timed loop: exactly K steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    stats = []
-    sampler = ClockSampler(job.local_rank)
-    launches0 = env.kernel_launches()
-    sampler.start()
     job.barrier()
     wall0 = time.perf_counter()
     for i in range(K):
@@ -351,7 +353,7 @@ def measure_workload(job, wargs, K, W, steady_seconds, with_e2e_variants=True):
         ev[i][0].record()
         env.step(acts, block_img=block_img, binary=binary)
         ev[i][1].record()
-        if i % max(1, K // 16) == 0:
+        if i % max(4, K // 16) == 0:
             stats.append(env._out.clone())
         env.reset_done()
     job.barrier()
