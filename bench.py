@@ -489,7 +489,9 @@ def measure_workload(job, wargs, K, W, steady_seconds, with_e2e_variants=True):
                       "mean_newton_iters_per_step": float(outs["newton_iters"].mean()),
                       "stable_frac": float(outs["stable"].mean()), "terminated_frac": float(outs["terminated"].mean()),
                       "solver_not_converged": int(((outs["solver_status"] & 3) != 0).sum()),
-                      "verdicts_implied_frac": float(((outs["solver_status"] & 4) != 0).mean() + ((outs["solver_status"] & 8) != 0).mean()) / 2},
+                      "verdicts_implied_frac": float(((outs["solver_status"] & 4) != 0).mean() + ((outs["solver_status"] & 8) != 0).mean()) / 2,
+                      "verdicts_by_lp_frac": float(((outs["solver_status"] & 16) != 0).mean() + ((outs["solver_status"] & 32) != 0).mean()) / 2,
+                      "mean_lp_pivots_per_step": float(outs["lp_pivots"].mean()), "max_lp_pivots": int(outs["lp_pivots"].max())},
         "with_candidate_stage": {"value": world * E * K / (t_dev + t_cand), "unit": UNIT,
                                  "candidate_ms_per_step": 1e3 * t_cand / K, "amax": amax,
                                  "note": "step + enumerate/filter kernel (candidates with bit rasters and validity "

@@ -9,6 +9,7 @@
 
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
+#include "bw_lp.cuh"
 
 using namespace bw;
 
@@ -18,6 +19,7 @@ struct bw_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     bool shapes_loaded = false;
+    bool lp_enabled = false;   // stored bases allocated and BW_NO_LP not set
     bool timing = false;
     bool resets_unchecked = false;   // a bw_reset with tasks ran since the last look at P.reset_err
     bool force_staged = false;   // bw_set_host_transfer(h, 1): *_host calls always stage through device buffers
@@ -93,6 +95,8 @@ static void choose_step_layout(bw_handle *h, int n_shapes) {
     P.share_h = share ? 1 : 0;
     P.lib_in_smem = lib ? 1 : 0;
     h->smem_step = step_smem_bytes(P.max_blocks, P.max_itf, n_shapes, share, lib);
+    // the LP path works in the memory of the two Newton problems (they never run at the same time)
+    P.lp_on = (h->lp_enabled && lp_bytes(P.max_blocks, P.max_itf) <= step_problem_bytes(P.max_blocks, P.max_itf, share)) ? 1 : 0;
 }
 
 static int fail(bw_handle *h, int code, const char *fmt, ...) {
@@ -363,6 +367,15 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     CU(dev_alloc(h, &P.warm_y, (size_t)E * 2 * NB * 3));
     CU(dev_alloc(h, &P.warm_ok, (size_t)E * 2));
     P.warm_start = getenv("BW_NO_WARM") ? 0 : 1;   // tuning hook (tools/ only): every solve from y = 0
+    {   // stored bases of the LP verdict path (bw_lp.cuh); BW_NO_LP: tuning hook (tools/ only)
+        const int mm = 3 * P.max_blocks;
+        P.lp_stride = (mm * mm + 1) & ~1;
+        CU(dev_alloc(h, &P.lp_meta, E));
+        CU(dev_alloc(h, &P.lp_binv, (size_t)E * P.lp_stride, false));
+        CU(dev_alloc(h, &P.lp_ids, (size_t)E * 3 * NB, false));
+        h->lp_enabled = getenv("BW_NO_LP") == nullptr;
+        if (getenv("BW_LP_STATS")) CU(dev_alloc(h, &P.lp_stats, 32));   // tuning hook (tools/ only)
+    }
     CU(dev_alloc(h, &P.cand_need, 1));
     CU(dev_alloc(h, &P.reset_err, 1));
     {   // CTA order of the step kernel: the first launch takes the environments in index order
@@ -465,6 +478,7 @@ int bw_load_shapes(bw_handle *h, const bw_shape_desc *h_shapes, int32_t n) {
     // verdicts of the last step describe blocks of the old library
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
+    CU(cudaMemsetAsync(h->P.lp_meta, 0, (size_t)h->P.E * sizeof(LpMeta), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->P.n_shapes = n;
     choose_step_layout(h, n);
@@ -509,6 +523,7 @@ int bw_set_mu(bw_handle *h, const double *h_mu) {
     // stand in for the next step's frozen solve (step_kernel, prev_released_ok)
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
+    CU(cudaMemsetAsync(h->P.lp_meta, 0, (size_t)h->P.E * sizeof(LpMeta), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }
@@ -520,6 +535,17 @@ int bw_set_static_mask(bw_handle *h, const uint32_t *h_mask) {
     // the verdicts of the last step no longer describe these supports
     CU(cudaMemsetAsync(h->P.su_valid, 0, h->P.E, h->stream));
     CU(cudaMemsetAsync(h->P.warm_ok, 0, (size_t)h->P.E * 2, h->stream));
+    CU(cudaMemsetAsync(h->P.lp_meta, 0, (size_t)h->P.E * sizeof(LpMeta), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BW_OK;
+}
+
+int bw_debug_lp_stats(bw_handle *h, uint64_t *h_stats /*[32]*/) {
+    if (!h || !h_stats) return BW_ERR_INVALID;
+    memset(h_stats, 0, 32 * sizeof(uint64_t));
+    if (h->P.lp_stats == nullptr) return BW_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h_stats, h->P.lp_stats, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return BW_OK;
 }

@@ -57,6 +57,8 @@ struct Pose {
     double x, z, c, s;
 };
 
+struct LpMeta;   // bw_lp.cuh
+
 // everything a kernel needs about the handle (passed by value)
 struct Params {
     int32_t E;
@@ -109,6 +111,13 @@ struct Params {
     // once there is more than one wave of work
     int32_t share_h;
     int32_t lib_in_smem;
+    // warm-started LP verdicts of real steps (bw_lp.cuh): the optimal basis of the released problem of the last step
+    int32_t lp_on;             // 0: every verdict by the screen + Newton path (tuning hook BW_NO_LP)
+    int32_t lp_stride;         // doubles per environment in lp_binv: (3 max_blocks)^2 rounded up to an even count
+    LpMeta *lp_meta;           // [E]
+    double *lp_binv;           // [E][lp_stride] basis inverse, row stride 3 max_blocks
+    uint16_t *lp_ids;          // [E][3 NB] basic columns: LP_ART or pair index << 2 | contact point << 1 | ray sign
+    unsigned long long *lp_stats;   // [32] counters of the LP path (tools/ only; see bw_debug_lp_stats)
     int32_t *cand_need;        // [1] largest untruncated candidate count an enumeration had to cut to `amax`
     int32_t *reset_err;        // [1] environments whose reset task was refused (bad shape index / too many blocks)
 };

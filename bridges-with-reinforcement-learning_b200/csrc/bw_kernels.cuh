@@ -8,6 +8,8 @@ namespace bw {
 void upload_step_tables();
 int step_smem_bytes(int max_blocks, int max_itf, int n_shapes, bool share_h, bool lib_in_smem);
 cudaError_t configure_step(int smem_bytes);
+int step_problem_bytes(int max_blocks, int max_itf, bool share_h);   // memory of the two Newton problems
+int lp_bytes(int max_blocks, int max_itf);                           // what the LP path needs of it
 void launch_step(Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
                  const bw_obs_out &obs, bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes,
                  cudaStream_t stream);

@@ -88,6 +88,10 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
         P.su_valid[e] = (s_n == 0);       // pre-placed blocks: the evaluation that follows sets it
         P.warm_ok[2 * e] = 0;
         P.warm_ok[2 * e + 1] = 0;
+        if (P.lp_meta != nullptr) {       // LpMeta (16 bytes) all zero: no basis
+            reinterpret_cast<unsigned long long *>(P.lp_meta)[2 * e] = 0ull;
+            reinterpret_cast<unsigned long long *>(P.lp_meta)[2 * e + 1] = 0ull;
+        }
     }
     if (tid < NB) P.face_occ[(size_t)e * NB + tid] = 0;
     __syncthreads();

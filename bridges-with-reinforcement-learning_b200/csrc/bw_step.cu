@@ -17,6 +17,7 @@
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
 #include "bw_solver.cuh"
+#include "bw_lp.cuh"
 
 namespace bw {
 
@@ -132,6 +133,13 @@ int step_smem_bytes(int max_blocks, int max_itf, int n_shapes, bool share_h, boo
     return make_layout(max_blocks, max_itf, n_shapes, share_h, lib_in_smem).total;
 }
 
+int step_problem_bytes(int max_blocks, int max_itf, bool share_h) {
+    const Layout L = make_layout(max_blocks, max_itf, 1, share_h, true);
+    const ProbOff po = prob_layout(L.MM, L.MC, L.HS, !share_h);
+    return 2 * po.size + (share_h ? align16(L.HS * 8) : 0);
+}
+int lp_bytes(int max_blocks, int max_itf) { return lp_layout(3 * max_blocks, 2 * max_itf).size; }
+
 // The optional image outputs of a step (bw_obs_out): the raster of all blocks as f32 [1,64,64] / u8 [64,64] /
 // bit-packed [64], from the CTA's shared copy `bits` (64 threads, 16-byte coalesced streaming stores).
 __device__ __forceinline__ void write_obs_images(const bw_obs_out &obs, const uint64_t *bits, int e, int tid) {
@@ -171,9 +179,23 @@ __device__ __forceinline__ void enqueue_next(const Params &P, int e, int n_block
     P.order_q[((size_t)nxt * ORDER_KEYS + key) * P.E + pos] = e;
 }
 
+// statistics of the LP path (only when the handle asked for them: bw_debug_lp_stats)
+//   [0..1] runs (frozen, released)  [2..3] feasible  [4..5] infeasible  [6..7] not certified
+//   [8 + why] reasons of "not certified": 1 pivot cap, 2 no pivot row, 3 primal residual, 4 / 5 dual certificate, 6 setup
+//   [16] pivots, [17] largest pivot count, [18] pivots of runs from an empty basis, [19] such runs, [20] rows of all runs
+__device__ __forceinline__ void lp_count(const Params &P, const Lp &lp, int res, int which) {
+    if (P.lp_stats == nullptr || lp.lane != 0) return;
+    atomicAdd(&P.lp_stats[which], 1ull);
+    atomicAdd(&P.lp_stats[(res == LP_FEASIBLE ? 2 : (res == LP_INFEASIBLE ? 4 : 6)) + which], 1ull);
+    if (res == LP_NONE) atomicAdd(&P.lp_stats[8 + (lp.why & 7)], 1ull);
+    atomicAdd(&P.lp_stats[16], (unsigned long long)lp.pivots);
+    atomicMax(&P.lp_stats[17], (unsigned long long)lp.pivots);
+    atomicAdd(&P.lp_stats[20], (unsigned long long)lp.m);
+}
+
 // ------------------------------------------------------------------ the kernel
 template <bool TWO>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 8)
 step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
             bw_step_out *__restrict__ out, bw_obs_out obs, bw_interface *__restrict__ save_itf,
             int32_t *__restrict__ save_nitf, int save_variant) {
@@ -247,6 +269,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __shared__ long long sh_prof_solve[2];
     __shared__ long long sh_prof_sub[2][6];
     __shared__ long long sh_prof_f[3];
+    __shared__ long long sh_prof_lp[8];   // LP path: copy-in, setup, run, copy-out | duals + pricing, column + ratio, update, certificate
 #endif
     __shared__ double sh_lin[2];
     __shared__ double sh_warm[2][3 * NB];   // starting points of the two solves (dual iterates of the last step)
@@ -257,6 +280,11 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __shared__ double s_inv_nx[NF];        // 1 / n_x of the new block's posed faces (raster crossing estimate)
     __shared__ double sh_dist[BW_MAX_TARGETS];
     __shared__ int sh_coll[4];             // collision with: blocks, obstacles, floor, bounds
+    __shared__ uint8_t sh_pair_itf[NPAIR]; // body pair -> interface index (0xFF: none); identity of the LP's columns
+    __shared__ uint8_t sh_itf_pair[MAXITF];
+    __shared__ int sh_lp_res[2];           // verdicts of the LP path (LP_NONE: the problem goes to screen + Newton)
+    __shared__ double sh_lp_r[2];
+    __shared__ int sh_lp_piv;
 
 #ifdef BW_PROFILE
     long long prof_t[8];
@@ -276,6 +304,15 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     }
     const bw_action act = actions[e];
     const int n_old = P.n_blocks[e];
+    // the LP path's stored basis: its header now, its rows on their way into L2 (they are read after the interfaces)
+    LpMeta lp_meta0;
+    lp_meta0.mask = 0u; lp_meta0.m = 0; lp_meta0.feasible = 0; lp_meta0.L0 = 0.0;
+    if (PG.lp_on && act.shape >= 0) {
+        lp_meta0 = PG.lp_meta[e];
+        const char *rows = reinterpret_cast<const char *>(PG.lp_binv + (size_t)e * PG.lp_stride);
+        const int bytes = (int)lp_meta0.m * 3 * PG.max_blocks * 8;
+        for (int off = tid * 128; off < bytes; off += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + off));
+    }
     const uint64_t old_bits = P.block_bits[(size_t)e * IMG + tid];   // image row tid, used after the placement
     if (tid < n_old) {
         s_pose[tid] = P.pose[(size_t)e * NB + tid];
@@ -283,6 +320,12 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     }
     if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; sh_hlock = 0; }
     if (tid < 4) sh_coll[tid] = 0;
+    if (tid < 2) sh_lp_res[tid] = LP_NONE;
+    if (tid == 2) sh_lp_piv = 0;
+#ifdef BW_PROFILE
+    if (tid < 8) sh_prof_lp[tid] = 0;
+#endif
+    for (int q = tid; q < NPAIR; q += 64) sh_pair_itf[q] = 0xFF;
     // stabilities_freezing()[1] of the previous step (all of today's free blocks were free and in
     // equilibrium): the frozen solve of this step has the same rows plus contacts to a new support,
     // so that equilibrium still holds -- no solve needed
@@ -554,6 +597,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                 const int idx = base + (warp == 1 ? sh_cnt[r][0] : 0) + (int)((hitmask >> (8 + 8 * r)) & 0xff);
                 const int A = c_pair_a[p], B = c_pair_b[p];
                 const int fa = s_pair_faces[p] >> 3, fb = s_pair_faces[p] & 7;
+                sh_pair_itf[p] = (uint8_t)idx;
+                sh_itf_pair[idx] = (uint8_t)p;
                 const double *FA = s_face + (A * NF + fa) * FACE_DOUBLES;
                 const double nx = FA[0], nz = FA[1], cx = FA[2], cz = FA[3];
                 const double tx = nz, tz = -nx;
@@ -645,12 +690,99 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __syncthreads();
 
     BW_STAMP(2);
-    // ---------------- phase 3: two equilibrium problems, one warp each
     uint32_t smask = P.static_mask[e];
     if (placed) {
         if (n >= 2) smask &= ~(1u << (n - 2));   // unfreeze_block(n-2), gym_env.py:235-236
         smask |= 1u << (n - 1);                  // action.frozen = True; freeze_block(n-1)
     }
+    // ---------------- phase 3a: the verdicts of a real step as warm-started linear programmes (bw_lp.cuh).
+    // The two problems run one after the other on warp 0 in the memory of the two Newton problems (the basis
+    // inverse takes most of it); both start from the basis the released problem of the previous step ended
+    // with.  The frozen problem first -- unless the previous released verdict already implies it -- and the
+    // released one only if the frozen one has an equilibrium (no frozen equilibrium => no released one; the
+    // episode ends there).  All threads copy the stored rows in and the final ones out.
+    const bool lp_try = PG.lp_on != 0 && placed && save_itf == nullptr && !overflow && nitf > 0 && n >= 1;
+    if (lp_try) {
+        const LpOff lo = lp_layout(L.MM, L.MC);
+        unsigned char *lb = smem + L.prob[0];
+        const LpMeta meta = lp_meta0;
+        double *gB = PG.lp_binv + (size_t)e * PG.lp_stride;
+        uint16_t *gI = PG.lp_ids + (size_t)e * 3 * NB;
+        const uint32_t allmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+        const uint32_t freeF = allmask & ~smask, freeR = freeF | (1u << (n - 1));
+        Lp lp;
+        lp.G = s_G; lp.c_a = s_ca; lp.c_b = s_cb; lp.adj_ptr = s_adj_ptr; lp.adj = s_adj;
+        lp.Binv = reinterpret_cast<double *>(lb + lo.binv);
+        lp.xB = reinterpret_cast<double *>(lb + lo.xb);
+        lp.pi = reinterpret_cast<double *>(lb + lo.pi);
+        lp.w = reinterpret_cast<double *>(lb + lo.w);
+        lp.b = reinterpret_cast<double *>(lb + lo.b);
+        lp.f = reinterpret_cast<double *>(lb + lo.f);
+        lp.ids = reinterpret_cast<uint16_t *>(lb + lo.ids);
+        lp.pos = lb + lo.pos;
+        lp.rowbase = reinterpret_cast<int8_t *>(lb + lo.rowbase);
+        lp.freebody = lb + lo.freebody;
+        lp.MS = L.MM;
+        lp.nc = nc;
+        lp.lane = lane;
+        lp.mu = P.mu[e];
+        const double r_exit = fmin(P.stable_tol, 1e-6);
+        const double z_inf = fmax(1e-5, 7.0 * P.stable_tol);
+        // frozen problem: decided without a solve when nothing is free or the previous released verdict implies it
+        const bool need_F = freeF != 0u && !prev_released_ok;
+        int resF = LP_FEASIBLE;
+#ifdef BW_PROFILE
+        long long lpt = clock64();
+#define BW_LP_STAMP(i) if (tid == 0) { const long long now_ = clock64(); sh_prof_lp[i] += now_ - lpt; lpt = now_; }
+#else
+#define BW_LP_STAMP(i)
+#endif
+#pragma unroll 1
+        for (int which = need_F ? 0 : 1; which < 2; which++) {
+            const uint32_t fm = which ? freeR : freeF;
+            Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * L.MM, tid, 64);
+            __syncthreads();
+            BW_LP_STAMP(0);
+            if (warp == 0) {
+                int res = LP_NONE;
+                double r = 0.0;
+                const bool ready = lp.setup(fm, n, s_body, meta, gI, sh_pair_itf, sh_L0);
+#ifdef BW_PROFILE
+                if (tid == 0) { const long long now_ = clock64(); sh_prof_lp[1] += now_ - lpt; lpt = now_; }
+#endif
+                if (ready) res = lp.run(r_exit, z_inf, r);
+                if (which == 1 && res != LP_NONE) lp.store(PG.lp_meta + e, gI, freeR, sh_itf_pair, res == LP_FEASIBLE, sh_L0);
+                if (lane == 0) { sh_lp_res[which] = res; sh_lp_r[which] = r; sh_lp_piv += lp.pivots; }
+                lp_count(PG, lp, res, which);
+#ifdef BW_PROFILE
+                if (tid == 0 && ready) for (int q = 0; q < 4; q++) sh_prof_lp[4 + q] += lp.tp[q];
+#endif
+            }
+            __syncthreads();
+            BW_LP_STAMP(2);
+            if (which == 0) {
+                resF = sh_lp_res[0];
+                if (resF != LP_FEASIBLE) break;
+            } else if (sh_lp_res[1] != LP_NONE) {
+                Lp::store_rows(gB, lp.Binv, 3 * __popc(freeR) * L.MM, tid, 64);
+                BW_LP_STAMP(3);
+            }
+        }
+        if (resF == LP_INFEASIBLE && tid == 0) { sh_lp_res[1] = LP_INFEASIBLE; sh_lp_r[1] = nan(""); }
+        // an answer the LP could not certify: both problems go to the Newton path; without a final released basis the
+        // next step starts from an empty one
+        if (tid == 0) {
+            const bool failed = (need_F && sh_lp_res[0] == LP_NONE) || (resF == LP_FEASIBLE && sh_lp_res[1] == LP_NONE);
+            if (failed) { sh_lp_res[0] = LP_NONE; sh_lp_res[1] = LP_NONE; }
+            if (failed || resF != LP_FEASIBLE) {
+                LpMeta none;
+                none.mask = 0u; none.m = 0; none.feasible = 0; none.L0 = 0.0;
+                PG.lp_meta[e] = none;
+            }
+        }
+        __syncthreads();
+    }
+    // ---------------- phase 3: two equilibrium problems, one warp each
     {
         const uint32_t vmask = (warp == 0) ? smask : (n > 0 ? (smask & ~(1u << (n - 1))) : smask);
         const ProbOff po = prob_layout(L.MM, L.MC, L.HS, PG.share_h == 0);
@@ -705,6 +837,11 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         __syncwarp();
         int stable, status = 0, iters = 0;
         double res = 0.0;
+#ifdef BW_PROFILE
+        for (int q = 0; q < 6; q++) S.acc_t[q] = 0;
+        for (int q = 0; q < 3; q++) S.acc_f[q] = 0;
+        S.t_screen = 0;
+#endif
         // warm starts only along real steps (an evaluation with Action.shape = -1 may follow arbitrary
         // freeze / unfreeze calls) and never for the force read-back, whose iterates must not depend on history.
         // Starting point of the FROZEN solve: the dual iterate of the last feasible solve over (almost) the same
@@ -748,6 +885,11 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                 for (int i = lane; i < S.m; i += 32) S.y[i] = sh_warm[warp][i];
             }
             have_y = warm;
+        } else if (sh_lp_res[warp] != LP_NONE) {
+            // certified by the LP path: a basic solution with ||b - A f|| <= stable_tol, or a Farkas vector
+            stable = (sh_lp_res[warp] == LP_FEASIBLE);
+            status = 6;
+            res = sh_lp_r[warp];
         } else {
             bool certified = false;
 #ifdef BW_PROFILE
@@ -923,7 +1065,10 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         o.stable = (uint8_t)stable_frozen;
         o.stable_unfrozen = (uint8_t)stable_unfrozen;
         o.solver_status = (uint8_t)((sh_status[0] == 2 ? 1 : 0) | (sh_status[1] == 2 ? 2 : 0) |
-                                    (sh_status[0] >= 3 ? 4 : 0) | (sh_status[1] >= 3 ? 8 : 0));
+                                    ((sh_status[0] >= 3 && sh_status[0] != 6) ? 4 : 0) |
+                                    ((sh_status[1] >= 3 && sh_status[1] != 6) ? 8 : 0) |
+                                    (sh_status[0] == 6 ? 16 : 0) | (sh_status[1] == 6 ? 32 : 0));
+        o.lp_pivots = (uint8_t)min(255, sh_lp_piv);
         o.residual = sh_res[0];
         o.residual_unfrozen = sh_res[1];
         o.newton_iters = sh_iters[0] + sh_iters[1];
@@ -986,6 +1131,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             for (int q = 0; q < 6; q++) dbg[16 + q] = (float)sh_prof_sub[0][q];
             dbg[22] = (float)sh_iters[0]; dbg[23] = (float)sh_iters[1];
             for (int q = 0; q < 3; q++) dbg[24 + q] = (float)sh_prof_f[q];
+            for (int q = 0; q < 8; q++) dbg[32 + q] = (float)sh_prof_lp[q];
+            dbg[40] = (float)sh_lp_piv;
         }
     }
 #endif

@@ -351,5 +351,11 @@ class BatchedAssemblyGym:
         self._check(self.lib.bw_get_forces(self.handle, variant, itf.ctypes.data, n.ctypes.data))
         return itf, n
 
+    def lp_stats(self):
+        """counters of the LP verdict path (all zero unless BW_LP_STATS was set when the handle was made)"""
+        st = np.zeros(32, dtype=np.uint64)
+        self._check(self.lib.bw_debug_lp_stats(self.handle, st.ctypes.data))
+        return st
+
     def kernel_launches(self):
         return int(self.lib.bw_kernel_launches(self.handle))

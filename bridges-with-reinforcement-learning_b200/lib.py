@@ -14,7 +14,7 @@ BW_MAX_OBSTACLES = 8
 BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
-BW_ABI_VERSION = 4
+BW_ABI_VERSION = 5
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")
@@ -68,7 +68,7 @@ class bw_step_out(C.Structure):
                 ("collision_block", C.c_uint8), ("collision_obstacle", C.c_uint8), ("collision_floor", C.c_uint8),
                 ("collision_boundary", C.c_uint8), ("terminated", C.c_uint8), ("truncated", C.c_uint8),
                 ("solver_status", C.c_uint8), ("error", C.c_uint8), ("n_targets_reached", C.c_uint8),
-                ("reserved1", C.c_uint8 * 4)]
+                ("lp_pivots", C.c_uint8), ("reserved1", C.c_uint8 * 3)]
 
 
 class bw_obs_out(C.Structure):
@@ -110,7 +110,7 @@ def np_dtypes():
                          ("stable", "u1"), ("stable_unfrozen", "u1"), ("collision", "u1"), ("collision_block", "u1"),
                          ("collision_obstacle", "u1"), ("collision_floor", "u1"), ("collision_boundary", "u1"),
                          ("terminated", "u1"), ("truncated", "u1"), ("solver_status", "u1"), ("error", "u1"),
-                         ("n_targets_reached", "u1"), ("reserved1", "u1", (4,))])
+                         ("n_targets_reached", "u1"), ("lp_pivots", "u1"), ("reserved1", "u1", (3,))])
     block = np.dtype([("x", "<f8"), ("z", "<f8"), ("c", "<f8"), ("s", "<f8"), ("shape", "<i4"), ("is_static", "<i4")])
     task = np.dtype([("n_obstacles", "<i4"), ("n_targets", "<i4"), ("n_blocks", "<i4"), ("reserved0", "<i4"),
                      ("obstacle_xz", "<f8", (BW_MAX_OBSTACLES, 2)), ("target_xz", "<f8", (BW_MAX_TARGETS, 2)),
@@ -175,6 +175,7 @@ SIGNATURES = {
     "bw_set_timing": (C.c_int, [_H, C.c_int32]),
     "bw_last_step_kernel_ms": (C.c_int, [_H, _P]),
     "bw_fp64_peak_gflops": (C.c_int, [_H, _P]),
+    "bw_debug_lp_stats": (C.c_int, [_H, _P]),
     "bw_kernel_launches": (C.c_int64, [_H]),
 }
 

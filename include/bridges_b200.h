@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 4
+#define BW_ABI_VERSION 5
 
 /* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
 #define BW_MAX_BLOCKS 16
@@ -148,10 +148,14 @@ typedef struct {
     uint8_t solver_status;        /* bit0 / bit1: frozen / unfrozen solve did not converge (stable=None);
                                      bit2 / bit3: frozen / unfrozen verdict implied without (finishing) its own solve
                                      (released-block equilibrium implies frozen-block equilibrium, within a step and
-                                     from the previous step's released verdict): residual is NaN or the implying one */
+                                     from the previous step's released verdict): residual is NaN or the implying one;
+                                     bit4 / bit5: frozen / unfrozen verdict certified by the warm-started LP path of a
+                                     real step (residual = ||b - A f|| of its basic solution when stable, NaN for a
+                                     certificate of infeasibility; newton_iters does not count its pivots) */
     uint8_t error;                /* 1 = invalid action indices, 2 = capacity exceeded */
     uint8_t n_targets_reached;
-    uint8_t reserved1[4];
+    uint8_t lp_pivots;            /* simplex pivots of the LP verdict path in this step (both problems, saturating) */
+    uint8_t reserved1[3];
 } bw_step_out;
 
 /* Optional observation outputs of a step; any pointer may be NULL.  The raster is
@@ -351,6 +355,9 @@ int bw_last_step_kernel_ms(bw_handle *h, float *h_ms2);
 /* sustained FP64 FMA throughput of the device (GFLOP/s), measured by a micro-benchmark:
  * the denominator of the solver's compute roofline */
 int bw_fp64_peak_gflops(bw_handle *h, double *h_gflops);
+/* counters of the LP verdict path (collected only when the handle was created with BW_LP_STATS set in the
+ * environment -- a tuning hook, not part of the reference interface): h_stats[32], layout in csrc/bw_step.cu */
+int bw_debug_lp_stats(bw_handle *h, uint64_t *h_stats);
 /* number of kernels launched by this handle so far */
 int64_t bw_kernel_launches(const bw_handle *h);
 

@@ -27,7 +27,7 @@ def regions_of(fname):
         if m2:
             out.append((i, m2.group(1)[:40]))
     return out
-regs = {f: regions_of(f) for f in ("bw_solver.cuh", "bw_step.cu", "bw_common.cuh")}
+regs = {f: regions_of(f) for f in ("bw_solver.cuh", "bw_lp.cuh", "bw_step.cu", "bw_common.cuh")}
 def region(key):
     if key is None: return "?"
     f, l = key
