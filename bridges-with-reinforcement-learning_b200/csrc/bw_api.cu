@@ -369,10 +369,11 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
     P.warm_start = getenv("BW_NO_WARM") ? 0 : 1;   // tuning hook (tools/ only): every solve from y = 0
     {   // stored bases of the LP verdict path (bw_lp.cuh); BW_NO_LP: tuning hook (tools/ only)
         const int mm = 3 * P.max_blocks;
-        P.lp_stride = (mm * mm + 1) & ~1;
+        P.lp_stride = mm * lp_row_stride(mm);
         CU(dev_alloc(h, &P.lp_meta, E));
         CU(dev_alloc(h, &P.lp_binv, (size_t)E * P.lp_stride, false));
         CU(dev_alloc(h, &P.lp_ids, (size_t)E * 3 * NB, false));
+        CU(dev_alloc(h, &P.lp_xb, (size_t)E * 3 * NB, false));
         h->lp_enabled = getenv("BW_NO_LP") == nullptr;
         if (getenv("BW_LP_STATS")) CU(dev_alloc(h, &P.lp_stats, 32));   // tuning hook (tools/ only)
     }

@@ -116,6 +116,7 @@ struct Params {
     int32_t lp_stride;         // doubles per environment in lp_binv: (3 max_blocks)^2 rounded up to an even count
     LpMeta *lp_meta;           // [E]
     double *lp_binv;           // [E][lp_stride] basis inverse, row stride 3 max_blocks
+    double *lp_xb;             // [E][3 NB] basic solution of the stored basis in physical units (times ||weights||)
     uint16_t *lp_ids;          // [E][3 NB] basic columns: LP_ART or pair index << 2 | contact point << 1 | ray sign
     unsigned long long *lp_stats;   // [32] counters of the LP path (tools/ only; see bw_debug_lp_stats)
     int32_t *cand_need;        // [1] largest untruncated candidate count an enumeration had to cut to `amax`

@@ -37,22 +37,27 @@ struct LpMeta {            // per environment, next to the stored basis
     double L0;             // torque-row scale (largest shape radius among the blocks) the stored inverse was built with
 };
 
-struct LpOff { int binv, xb, pi, w, b, f, ids, pos, rowbase, freebody, size; };
+struct LpOff { int binv, xb, pi, w, b, f, ids, pos, crow, rowbase, freebody, size; };
+
+// row stride of the basis inverse in shared memory and HBM: even, so that two columns are one 16-byte access
+__host__ __device__ inline int lp_row_stride(int MM) { return (MM + 1) & ~1; }
 
 __host__ __device__ inline LpOff lp_layout(int MM, int MC) {
     LpOff o;
     int p = 0;
-    o.binv = p; p += MM * MM * 8;
-    o.xb = p; p += MM * 8;
-    o.pi = p; p += MM * 8;
-    o.w = p; p += MM * 8;
-    o.b = p; p += MM * 8;
-    o.f = p; p += 2 * MC * 8;
-    o.ids = p; p += ((MM * 2 + 15) & ~15);
-    o.pos = p; p += ((2 * MC + 15) & ~15);
-    o.rowbase = p; p += ((NBODY + 15) & ~15);
-    o.freebody = p; p += ((NB + 15) & ~15);
-    o.size = (p + 15) & ~15;
+    auto a16 = [](int x) { return (x + 15) & ~15; };
+    o.binv = p; p += a16(MM * lp_row_stride(MM) * 8);
+    o.xb = p; p += a16(MM * 8);
+    o.pi = p; p += a16(MM * 8);
+    o.w = p; p += a16((MM + 4) * 8);          // padded: the update reads w four rows at a time
+    o.b = p; p += a16(MM * 8);
+    o.f = p; p += a16(2 * MC * 8);
+    o.ids = p; p += a16(MM * 2);
+    o.pos = p; p += a16(2 * MC);
+    o.crow = p; p += a16(2 * MC);
+    o.rowbase = p; p += a16(NBODY);
+    o.freebody = p; p += a16(NB);
+    o.size = p;
     return o;
 }
 
@@ -65,7 +70,7 @@ __device__ __forceinline__ unsigned ordered_key(float x) {
 struct Lp {
     static constexpr double PIV_TOL = 1e-7;     // smallest pivot element
     static constexpr double HARRIS = 1e-9;      // feasibility slack of the ratio test
-    static constexpr double D_TOL = 1e-10;      // reduced costs above -D_TOL count as non-negative
+    static constexpr double D_TOL = 1e-9;       // reduced costs above -D_TOL count as non-negative
     static constexpr double CERT_REL = 1e-5;    // certificate of infeasibility: pi . r <= CERT_REL pi . b for EVERY ray
 
     // contacts of the environment (shared with the Newton solver)
@@ -75,10 +80,12 @@ struct Lp {
     double *Binv, *xB, *pi, *w, *b, *f;
     uint16_t *ids;            // basic column of every row position: LP_ART or ray = 2 * contact + sign
     uint8_t *pos;             // ray -> position in the basis, 0xFF = non-basic
+    uint16_t *crow;           // contact point -> (first row of body a + 1) | (first row of body b + 1) << 8, 0 = support
     int8_t *rowbase;
     uint8_t *freebody;
-    int MS;                   // row stride of Binv (= 3 * max_blocks, also the layout in HBM)
+    int MS;                   // row stride of Binv (lp_row_stride(3 * max_blocks), also the layout in HBM)
     int m, nfree, nc, lane, pivots;
+    double flops;             // work estimate of the run (bw_step_out.solver_kflops): per pivot 28 nc + 2 m^2 + 16 m
     int why;                  // why the last run() returned LP_NONE (statistics: bw_debug_lp_stats)
     double mu, nb;
     unsigned long long artmask;   // positions that hold an artificial column
@@ -137,11 +144,14 @@ struct Lp {
     // with, B' = D B E with D = diag(1, 1, s, ...) and E = 1/s on the artificial columns of torque rows (they are unit
     // vectors in either scaling), so B'^-1 = E^-1 B^-1 D^-1: torque COLUMNS of the inverse times 1/s, the ROWS of
     // torque-row artificials times s.
-    __device__ bool setup(uint32_t free_mask, int n, const double *s_body, LpMeta meta, const uint16_t *gI,
-                          const uint8_t *pair_itf, double L0) {
+    // nb_: norm of the weights of the free blocks (b is normalised); gX: the stored basic solution in physical units.
+    // gid0/1, gx0/1: the stored column identities and basic solution of rows lane and lane + 32 (loaded by the caller
+    // long before they are needed).
+    __device__ bool setup(uint32_t free_mask, int n, const double *s_body, LpMeta meta, uint16_t gid0, uint16_t gid1,
+                          double gx0, double gx1, const uint8_t *pair_itf, double L0, double nb_) {
         const int m_old = usable_rows(meta, free_mask);
-        // stored column identities: issued first, needed last
-        const uint16_t gid0 = (lane < m_old) ? gI[lane] : LP_ART, gid1 = (lane + 32 < m_old) ? gI[lane + 32] : LP_ART;
+        if (lane >= m_old) { gid0 = LP_ART; gx0 = 0.0; }
+        if (lane + 32 >= m_old) { gid1 = LP_ART; gx1 = 0.0; }
         const bool is_free = lane < n && ((free_mask >> lane) & 1u);
         const unsigned fb = __ballot_sync(FULL, is_free);
         nfree = __popc(fb);
@@ -151,16 +161,24 @@ struct Lp {
         if (lane < n) rowbase[lane + 1] = is_free ? (int8_t)(3 * myrow) : (int8_t)-1;
         if (is_free) freebody[myrow] = (uint8_t)(lane + 1);
         const double wgt = is_free ? s_body[(lane + 1) * 8 + 2] : 0.0;
-        nb = sqrt(warp_sum(wgt * wgt));
+        nb = nb_;
+        const double inv_nb = 1.0 / nb_;
         if (is_free) {
             b[3 * myrow] = 0.0;
-            b[3 * myrow + 1] = wgt / nb;
+            b[3 * myrow + 1] = wgt * inv_nb;
             b[3 * myrow + 2] = 0.0;
         }
+        __syncwarp();
 #pragma unroll 1
-        for (int c = lane; c < 2 * nc; c += 32) pos[c] = 0xFF;
+        for (int c = lane; c < nc; c += 32) {
+            reinterpret_cast<uint16_t *>(pos)[c] = 0xFFFF;
+            crow[c] = (uint16_t)((rowbase[c_a[c]] + 1) | ((rowbase[c_b[c]] + 1) << 8));
+        }
         if (m_old > 0 && meta.L0 != L0) {
             const double s = meta.L0 / L0, is = L0 / meta.L0;
+            // (the basic solution: D^-1 b = b because the torque rows of b are zero, so x' = E^-1 x)
+            if ((lane % 3 == 2) && (gid0 & LP_ART)) gx0 *= s;
+            if (((lane + 32) % 3 == 2) && (gid1 & LP_ART)) gx1 *= s;
 #pragma unroll 1
             for (int i = 0; i < m_old; i++) {
                 const bool art_torque = (i % 3 == 2) && (__shfl_sync(FULL, (i < 32) ? gid0 : gid1, i & 31) & LP_ART);
@@ -207,17 +225,9 @@ struct Lp {
                 }
                 ids[i] = id;
                 art = (id & LP_ART) != 0;
-                // basic solution of the new right-hand side: only the weight rows of b are non-zero
-                double x;
-                if (i < m_old) {
-                    x = 0.0;
-                    const double *Bi = Binv + i * MS;
-#pragma unroll 2
-                    for (int k = 1; k < m_old; k += 3) x = fma(Bi[k], b[k], x);
-                    x = fmax(x, 0.0);
-                } else {
-                    x = b[i];
-                }
+                // basic solution: the stored one in the normalisation of this problem (the right-hand side of the old
+                // rows is the old one up to that factor); new rows start with their artificial column at b
+                const double x = (i < m_old) ? fmax((i0 ? gx1 : gx0) * inv_nb, 0.0) : b[i];
                 xB[i] = x;
             }
             am |= (unsigned long long)__ballot_sync(FULL, art) << i0;
@@ -265,11 +275,23 @@ struct Lp {
     __device__ int run(double r_exit, double z_inf, double &res) {
         const int maxpiv = 4 * m + 16;
         why = 0;
+        flops = 0.0;
 #ifdef BW_PROFILE
         tp[0] = tp[1] = tp[2] = tp[3] = 0;
 #endif
         double z = art_sum();                     // phase-1 objective: bounds ||b - A f|| of the basic solution
         res = nan("");
+        // lane = two adjacent columns of the basis inverse (one 16-byte access): update and dual vector
+        const int k2 = 2 * lane;
+        const bool hk = k2 < m;
+        const int MS2 = MS >> 1;                  // row stride in double2
+        double2 *col = reinterpret_cast<double2 *>(Binv + (hk ? k2 : 0));
+        double2 *pi2s = reinterpret_cast<double2 *>(pi);
+        const int i0 = lane, i1 = lane + 32;      // lane = row(s) in the ratio test
+        double2 pi2 = make_double2(0.0, 0.0);
+        bool fresh = false;                       // pi comes straight from the basis inverse (not from updates)
+        bool refreshed = false;                   // the basic solution was recomputed from the inverse
+        bool blocked = false;                     // the last entering column had no pivot row
 #pragma unroll 1
         while (true) {
             if (z <= r_exit) {
@@ -279,48 +301,70 @@ struct Lp {
                     const double r = primal_residual();
                     LP_ACC(3, t_d);
                     if (r <= r_exit) { res = r; return LP_FEASIBLE; }
-                    why = 3;
-                    return LP_NONE;
+                    // the updated basic solution has drifted from the basis: take it from the inverse again (once)
+                    if (refreshed) { why = 3; return LP_NONE; }
+                    refreshed = true;
+                    __syncwarp();
+#pragma unroll 1
+                    for (int i = lane; i < m; i += 32) {
+                        const double *Bi = Binv + i * MS;
+                        double x = 0.0;
+#pragma unroll 2
+                        for (int k = 1; k < m; k += 3) x = fma(Bi[k], b[k], x);
+                        xB[i] = fmax(x, 0.0);
+                    }
+                    __syncwarp();
+                    z = art_sum();
+                    if (z <= r_exit) {
+                        const double r2 = primal_residual();
+                        if (r2 <= r_exit) { res = r2; return LP_FEASIBLE; }
+                        why = 3;
+                        return LP_NONE;
+                    }
                 }
             }
             if (pivots >= maxpiv) { why = 1; return LP_NONE; }
             LP_T0(t_a);
-            // dual vector pi = sum of the artificial rows of the basis inverse (lane = column)
-            {
-                double p0 = 0.0, p1 = 0.0;
-                const int k0 = lane, k1 = lane + 32;
+            if (pivots == 0) {
+                // dual vector pi = sum of the artificial rows of the basis inverse; kept up to date by the pivots below
+                // (pi += d_q x new pivot row) and recomputed before an optimal basis is believed
+                pi2 = make_double2(0.0, 0.0);
 #pragma unroll 1
                 for (unsigned long long mm = artmask; mm; mm &= mm - 1) {
                     const int i = __ffsll((long long)mm) - 1;
-                    if (k0 < m) p0 += Binv[i * MS + k0];
-                    if (k1 < m) p1 += Binv[i * MS + k1];
+                    const double2 v = col[i * MS2];
+                    pi2.x += v.x; pi2.y += v.y;
                 }
-                if (k0 < m) pi[k0] = p0;
-                if (k1 < m) pi[k1] = p1;
+                if (hk) pi2s[lane] = pi2;
+                fresh = true;
+                __syncwarp();
             }
-            __syncwarp();
             // pricing: reduced cost of ray (c, +-) = -(pi . a_n +- mu pi . a_t); most negative non-basic one enters
             double best = 0.0, dall = 0.0;
             int bestray = -1;
 #pragma unroll 1
             for (int c = lane; c < nc; c += 32) {
-                const double *Gc = G + c * 12;
-                const int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
+                const double2 *G2 = reinterpret_cast<const double2 *>(G + c * 12);
+                const unsigned cr = crow[c];
+                const int ra = (int)(cr & 0xffu) - 1, rb = (int)(cr >> 8) - 1;
+                const unsigned bp = reinterpret_cast<const uint16_t *>(pos)[c];     // pos[2c] | pos[2c + 1] << 8
                 double pn = 0.0, pt = 0.0;
                 if (ra >= 0) {
+                    const double2 g0 = G2[0], g1 = G2[1], g2 = G2[2];               // n0 n1 | n2 t0 | t1 t2
                     const double v0 = pi[ra], v1 = pi[ra + 1], v2 = pi[ra + 2];
-                    pn = Gc[0] * v0 + Gc[1] * v1 + Gc[2] * v2;
-                    pt = Gc[3] * v0 + Gc[4] * v1 + Gc[5] * v2;
+                    pn = g0.x * v0 + g0.y * v1 + g1.x * v2;
+                    pt = g1.y * v0 + g2.x * v1 + g2.y * v2;
                 }
                 if (rb >= 0) {
+                    const double2 g3 = G2[3], g4 = G2[4], g5 = G2[5];
                     const double v0 = pi[rb], v1 = pi[rb + 1], v2 = pi[rb + 2];
-                    pn += Gc[6] * v0 + Gc[7] * v1 + Gc[8] * v2;
-                    pt += Gc[9] * v0 + Gc[10] * v1 + Gc[11] * v2;
+                    pn += g3.x * v0 + g3.y * v1 + g4.x * v2;
+                    pt += g4.y * v0 + g5.x * v1 + g5.y * v2;
                 }
                 const double dp = -(pn + mu * pt), dm = -(pn - mu * pt);
                 dall = fmin(dall, fmin(dp, dm));
-                if (dp < best && pos[2 * c] == 0xFF) { best = dp; bestray = 2 * c; }
-                if (dm < best && pos[2 * c + 1] == 0xFF) { best = dm; bestray = 2 * c + 1; }
+                if (dp < best && (bp & 0xffu) == 0xffu) { best = dp; bestray = 2 * c; }
+                if (dm < best && (bp >> 8) == 0xffu) { best = dm; bestray = 2 * c + 1; }
             }
             const unsigned key = (bestray >= 0) ? ((ordered_key((float)best) & 0xffffff00u) | (unsigned)bestray) : 0xffffffffu;
             const unsigned kmin = __reduce_min_sync(FULL, key);
@@ -332,7 +376,22 @@ struct Lp {
                 dq = __shfl_sync(FULL, best, src);
                 q = (int)(kmin & 0xffu);
             }
-            if (!(dq < -D_TOL)) {
+            if (!(dq < -D_TOL) || blocked) {
+                if (!fresh) {
+                    // optimal for the updated duals: look again with duals taken from the basis inverse itself
+                    pi2 = make_double2(0.0, 0.0);
+#pragma unroll 1
+                    for (unsigned long long mm = artmask; mm; mm &= mm - 1) {
+                        const int i = __ffsll((long long)mm) - 1;
+                        const double2 v = col[i * MS2];
+                        pi2.x += v.x; pi2.y += v.y;
+                    }
+                    __syncwarp();
+                    if (hk) pi2s[lane] = pi2;
+                    fresh = true;
+                    __syncwarp();
+                    continue;
+                }
                 // optimal basis: pi is a Farkas vector if it clears every ray (basic ones included: their reduced
                 // cost is zero only as far as the basis inverse is exact) and pi . b is clearly positive.  With
                 // pi . r <= eps for all rays, any lambda >= 0 with R lambda = b has pi . b <= eps sum(lambda): the
@@ -351,78 +410,95 @@ struct Lp {
             }
             LP_ACC(0, t_a);
             LP_T0(t_b);
-            // entering column in the current basis: w = Binv r_q (six non-zeros)
+            // entering column in the current basis: w = Binv r_q (six non-zeros), lane = row (two above 32 rows)
             const int c = q >> 1;
             const double sg = (q & 1) ? -mu : mu;
-            const double *Gc = G + c * 12;
-            const int ra = rowbase[c_a[c]], rb = rowbase[c_b[c]];
-            const double ca0 = Gc[0] + sg * Gc[3], ca1 = Gc[1] + sg * Gc[4], ca2 = Gc[2] + sg * Gc[5];
-            const double cb0 = Gc[6] + sg * Gc[9], cb1 = Gc[7] + sg * Gc[10], cb2 = Gc[8] + sg * Gc[11];
+            const double2 *G2 = reinterpret_cast<const double2 *>(G + c * 12);
+            const int ra = (int)(crow[c] & 0xffu) - 1, rb = (int)(crow[c] >> 8) - 1;
+            double a0 = 0.0, a1 = 0.0, x0 = 0.0, x1 = 0.0;
+            {
+                const double2 g0 = G2[0], g1 = G2[1], g2 = G2[2], g3 = G2[3], g4 = G2[4], g5 = G2[5];
+                const double ca0 = g0.x + sg * g1.y, ca1 = g0.y + sg * g2.x, ca2 = g1.x + sg * g2.y;
+                const double cb0 = g3.x + sg * g4.y, cb1 = g3.y + sg * g5.x, cb2 = g4.x + sg * g5.y;
+                if (i0 < m) {
+                    const double *Bi = Binv + i0 * MS;
+                    if (ra >= 0) a0 = Bi[ra] * ca0 + Bi[ra + 1] * ca1 + Bi[ra + 2] * ca2;
+                    if (rb >= 0) a0 += Bi[rb] * cb0 + Bi[rb + 1] * cb1 + Bi[rb + 2] * cb2;
+                    x0 = xB[i0];
+                }
+                if (i1 < m) {
+                    const double *Bi = Binv + i1 * MS;
+                    if (ra >= 0) a1 = Bi[ra] * ca0 + Bi[ra + 1] * ca1 + Bi[ra + 2] * ca2;
+                    if (rb >= 0) a1 += Bi[rb] * cb0 + Bi[rb + 1] * cb1 + Bi[rb + 2] * cb2;
+                    x1 = xB[i1];
+                }
+            }
             // Harris ratio test: bound from the relaxed ratios, then the largest pivot element under the bound
             unsigned krel = 0xffffffffu;
-#pragma unroll 1
-            for (int i = lane; i < m; i += 32) {
-                const double *Bi = Binv + i * MS;
-                double acc = 0.0;
-                if (ra >= 0) acc = Bi[ra] * ca0 + Bi[ra + 1] * ca1 + Bi[ra + 2] * ca2;
-                if (rb >= 0) acc += Bi[rb] * cb0 + Bi[rb + 1] * cb1 + Bi[rb + 2] * cb2;
-                w[i] = acc;
-                if (acc > PIV_TOL) krel = min(krel, __float_as_uint(__double2float_ru((xB[i] + HARRIS) * fast_rcp(acc) * (1.0 + 1e-9))));
-            }
+            if (a0 > PIV_TOL) krel = __float_as_uint(__double2float_ru((x0 + HARRIS) * fast_rcp(a0) * (1.0 + 1e-9)));
+            if (a1 > PIV_TOL) krel = min(krel, __float_as_uint(__double2float_ru((x1 + HARRIS) * fast_rcp(a1) * (1.0 + 1e-9))));
             krel = __reduce_min_sync(FULL, krel);
-            if (krel == 0xffffffffu) { why = 2; return LP_NONE; }   // no positive pivot element: numerical trouble
+            if (krel == 0xffffffffu) {
+                // no positive pivot element: the column cannot enter.  With a reduced cost that is only noise this is an
+                // optimal basis in disguise: let the certificate decide (it looks at every ray with fresh duals)
+                if (blocked || dq < -1e-6) { why = 2; return LP_NONE; }
+                blocked = true;
+                fresh = false;
+                continue;
+            }
             const double tmax = (double)__uint_as_float(krel);
             unsigned kpiv = 0u;
-#pragma unroll 1
-            for (int i = lane; i < m; i += 32) {
-                const double wi = w[i];
-                if (wi > PIV_TOL && xB[i] <= tmax * wi) kpiv = max(kpiv, (__float_as_uint((float)wi) & 0xffffffc0u) | (unsigned)i);
-            }
+            if (a0 > PIV_TOL && x0 <= tmax * a0) kpiv = (__float_as_uint((float)a0) & 0xffffffc0u) | (unsigned)i0;
+            if (a1 > PIV_TOL && x1 <= tmax * a1) kpiv = max(kpiv, (__float_as_uint((float)a1) & 0xffffffc0u) | (unsigned)i1);
             kpiv = __reduce_max_sync(FULL, kpiv);
             if (kpiv == 0u) { why = 2; return LP_NONE; }
             const int p = (int)(kpiv & 0x3fu);
+            const double wp = __shfl_sync(FULL, (p < 32) ? a0 : a1, p & 31);
+            const double xp = __shfl_sync(FULL, (p < 32) ? x0 : x1, p & 31);
+            double inv;
+            {   // 1 / wp: hardware approximation + two Newton steps (full precision for a normal wp > PIV_TOL)
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(wp));
+                inv = fma(fma(-wp, inv, 1.0), inv, inv);
+                inv = fma(fma(-wp, inv, 1.0), inv, inv);
+            }
+            const double theta = xp * inv;
+            // entering column for the update (the pivot row takes part as a no-op: w = 0; rows past the end likewise,
+            // the update reads four rows at a time) and the new basic solution
+            if (i0 < m) { w[i0] = (i0 == p) ? 0.0 : a0; xB[i0] = (i0 == p) ? theta : fmax(fma(-a0, theta, x0), 0.0); }
+            else if (i0 < m + 4) w[i0] = 0.0;
+            if (i1 < m) { w[i1] = (i1 == p) ? 0.0 : a1; xB[i1] = (i1 == p) ? theta : fmax(fma(-a1, theta, x1), 0.0); }
+            else if (i1 < m + 4) w[i1] = 0.0;
             __syncwarp();
             LP_ACC(1, t_b);
             LP_T0(t_c);
-            const double inv = 1.0 / w[p];
-            const double theta = xB[p] * inv;
-            // rank-one update of the basis inverse, lane = column; four rows per trip, loads first (the compiler cannot
-            // move a load above a store that may alias it, and one row at a time is one shared-memory round trip per row)
+            // rank-one update of the basis inverse: four rows per trip with all loads in front of the stores (the
+            // compiler cannot move a load above a store that may alias it, and a row at a time is a shared-memory
+            // round trip per row); rows with w = 0 are skipped
             {
-                const int k0 = lane, k1 = lane + 32;
-                const bool h0 = k0 < m, h1 = k1 < m;
-                const double t0 = h0 ? Binv[p * MS + k0] * inv : 0.0;
-                const double t1 = h1 ? Binv[p * MS + k1] * inv : 0.0;
-                double *c0 = Binv + (h0 ? k0 : 0), *c1 = Binv + (h1 ? k1 : 0);
+                double2 t = col[p * MS2];
+                t.x *= inv; t.y *= inv;
+                const double2 *w2 = reinterpret_cast<const double2 *>(w);
 #pragma unroll 1
                 for (int i = 0; i < m; i += 4) {
-                    // rows past the end and the pivot row itself take part with w = 0 (the value is written back as it is)
-                    const int i0 = i, i1 = min(i + 1, m - 1), i2 = min(i + 2, m - 1), i3 = min(i + 3, m - 1);
-                    const double w0 = (i0 == p) ? 0.0 : w[i0];
-                    const double w1 = (i + 1 >= m || i1 == p) ? 0.0 : w[i1];
-                    const double w2 = (i + 2 >= m || i2 == p) ? 0.0 : w[i2];
-                    const double w3 = (i + 3 >= m || i3 == p) ? 0.0 : w[i3];
-                    if ((w0 == 0.0) & (w1 == 0.0) & (w2 == 0.0) & (w3 == 0.0)) continue;       // uniform
-                    const double a0 = c0[i0 * MS], a1 = c0[i1 * MS], a2 = c0[i2 * MS], a3 = c0[i3 * MS];
-                    if (h1) {
-                        const double e0 = c1[i0 * MS], e1 = c1[i1 * MS], e2 = c1[i2 * MS], e3 = c1[i3 * MS];
-                        c1[i0 * MS] = fma(-w0, t1, e0);
-                        if (i + 1 < m) c1[i1 * MS] = fma(-w1, t1, e1);
-                        if (i + 2 < m) c1[i2 * MS] = fma(-w2, t1, e2);
-                        if (i + 3 < m) c1[i3 * MS] = fma(-w3, t1, e3);
-                    }
-                    if (h0) {
-                        c0[i0 * MS] = fma(-w0, t0, a0);
-                        if (i + 1 < m) c0[i1 * MS] = fma(-w1, t0, a1);
-                        if (i + 2 < m) c0[i2 * MS] = fma(-w2, t0, a2);
-                        if (i + 3 < m) c0[i3 * MS] = fma(-w3, t0, a3);
+                    const double2 wa = w2[i >> 1], wb = w2[(i >> 1) + 1];
+                    if ((wa.x == 0.0) & (wa.y == 0.0) & (wb.x == 0.0) & (wb.y == 0.0)) continue;     // uniform
+                    // rows past the end carry w = 0; their index is clamped (the value is written back as it is)
+                    const int j1 = min(i + 1, m - 1), j2 = min(i + 2, m - 1), j3 = min(i + 3, m - 1);
+                    const double2 b0 = col[i * MS2], b1 = col[j1 * MS2], b2 = col[j2 * MS2], b3 = col[j3 * MS2];
+                    if (hk) {
+                        col[i * MS2] = make_double2(fma(-wa.x, t.x, b0.x), fma(-wa.x, t.y, b0.y));
+                        if (i + 1 < m) col[j1 * MS2] = make_double2(fma(-wa.y, t.x, b1.x), fma(-wa.y, t.y, b1.y));
+                        if (i + 2 < m) col[j2 * MS2] = make_double2(fma(-wb.x, t.x, b2.x), fma(-wb.x, t.y, b2.y));
+                        if (i + 3 < m) col[j3 * MS2] = make_double2(fma(-wb.y, t.x, b3.x), fma(-wb.y, t.y, b3.y));
                     }
                 }
-                if (h0) Binv[p * MS + k0] = t0;
-                if (h1) Binv[p * MS + k1] = t1;
+                if (hk) col[p * MS2] = t;
+                // duals of the new basis: pi += d_q x (new pivot row)
+                pi2.x = fma(dq, t.x, pi2.x);
+                pi2.y = fma(dq, t.y, pi2.y);
+                if (hk) pi2s[lane] = pi2;
+                fresh = false;
             }
-#pragma unroll 1
-            for (int i = lane; i < m; i += 32) xB[i] = (i == p) ? theta : fmax(fma(-w[i], theta, xB[i]), 0.0);
             if (lane == 0) {
                 const uint16_t out = ids[p];
                 if (!(out & LP_ART)) pos[out] = 0xFF;
@@ -432,16 +508,18 @@ struct Lp {
             artmask &= ~(1ull << p);
             z += theta * dq;
             pivots++;
+            flops += 28.0 * nc + 2.0 * m * m + 16.0 * m;
             __syncwarp();
             LP_ACC(2, t_c);
         }
     }
 
     // keep the final basis for the next step (the matrix itself: store_rows)
-    __device__ void store(LpMeta *gmeta, uint16_t *gI, uint32_t free_mask, const uint8_t *itf_pair, bool feasible,
-                          double L0) const {
+    __device__ void store(LpMeta *gmeta, uint16_t *gI, double *gX, uint32_t free_mask, const uint8_t *itf_pair,
+                          bool feasible, double L0) const {
 #pragma unroll 1
         for (int i = lane; i < m; i += 32) {
+            gX[i] = xB[i] * nb;
             const uint16_t id = ids[i];
             uint16_t g = LP_ART;
             if (!(id & LP_ART)) {

@@ -285,6 +285,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __shared__ int sh_lp_res[2];           // verdicts of the LP path (LP_NONE: the problem goes to screen + Newton)
     __shared__ double sh_lp_r[2];
     __shared__ int sh_lp_piv;
+    __shared__ double sh_lp_flops;
 
 #ifdef BW_PROFILE
     long long prof_t[8];
@@ -310,7 +311,9 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     if (PG.lp_on && act.shape >= 0) {
         lp_meta0 = PG.lp_meta[e];
         const char *rows = reinterpret_cast<const char *>(PG.lp_binv + (size_t)e * PG.lp_stride);
-        const int bytes = (int)lp_meta0.m * 3 * PG.max_blocks * 8;
+        const int bytes = (int)lp_meta0.m * lp_row_stride(3 * PG.max_blocks) * 8;
+        if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(PG.lp_ids + (size_t)e * 3 * NB));
+        if (tid >= 1 && tid < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(PG.lp_xb + (size_t)e * 3 * NB + (tid - 1) * 16));
         for (int off = tid * 128; off < bytes; off += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + off));
     }
     const uint64_t old_bits = P.block_bits[(size_t)e * IMG + tid];   // image row tid, used after the placement
@@ -321,7 +324,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; sh_hlock = 0; }
     if (tid < 4) sh_coll[tid] = 0;
     if (tid < 2) sh_lp_res[tid] = LP_NONE;
-    if (tid == 2) sh_lp_piv = 0;
+    if (tid == 2) { sh_lp_piv = 0; sh_lp_flops = 0.0; }
 #ifdef BW_PROFILE
     if (tid < 8) sh_prof_lp[tid] = 0;
 #endif
@@ -708,6 +711,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         const LpMeta meta = lp_meta0;
         double *gB = PG.lp_binv + (size_t)e * PG.lp_stride;
         uint16_t *gI = PG.lp_ids + (size_t)e * 3 * NB;
+        double *gX = PG.lp_xb + (size_t)e * 3 * NB;
         const uint32_t allmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
         const uint32_t freeF = allmask & ~smask, freeR = freeF | (1u << (n - 1));
         Lp lp;
@@ -722,12 +726,30 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         lp.pos = lb + lo.pos;
         lp.rowbase = reinterpret_cast<int8_t *>(lb + lo.rowbase);
         lp.freebody = lb + lo.freebody;
-        lp.MS = L.MM;
+        lp.MS = lp_row_stride(L.MM);
+        lp.crow = reinterpret_cast<uint16_t *>(lb + lo.crow);
         lp.nc = nc;
         lp.lane = lane;
         lp.mu = P.mu[e];
         const double r_exit = fmin(P.stable_tol, 1e-6);
         const double z_inf = fmax(1e-5, 7.0 * P.stable_tol);
+        // norms of the two right-hand sides (weights of the free blocks): one reduction for both problems
+        double nbR, nbF;
+        {
+            const bool fr = lane < n && ((freeR >> lane) & 1u);
+            const double wl = fr ? s_body[(lane + 1) * BODY_DOUBLES + 2] : 0.0;
+            const double ss = warp_sum(wl * wl);
+            const double wn = s_body[n * BODY_DOUBLES + 2];
+            nbR = sqrt(ss);
+            nbF = sqrt(fmax(ss - wn * wn, 0.0));
+        }
+        // stored column identities and basic solution (rows lane, lane + 32): on their way while the rows are copied in
+        uint16_t gid0 = LP_ART, gid1 = LP_ART;
+        double gx0 = 0.0, gx1 = 0.0;
+        if (warp == 0) {
+            if (lane < (int)meta.m) { gid0 = gI[lane]; gx0 = gX[lane]; }
+            if (lane + 32 < (int)meta.m) { gid1 = gI[lane + 32]; gx1 = gX[lane + 32]; }
+        }
         // frozen problem: decided without a solve when nothing is free or the previous released verdict implies it
         const bool need_F = freeF != 0u && !prev_released_ok;
         int resF = LP_FEASIBLE;
@@ -740,19 +762,19 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 #pragma unroll 1
         for (int which = need_F ? 0 : 1; which < 2; which++) {
             const uint32_t fm = which ? freeR : freeF;
-            Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * L.MM, tid, 64);
+            Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * lp.MS, tid, 64);
             __syncthreads();
             BW_LP_STAMP(0);
             if (warp == 0) {
                 int res = LP_NONE;
                 double r = 0.0;
-                const bool ready = lp.setup(fm, n, s_body, meta, gI, sh_pair_itf, sh_L0);
+                const bool ready = lp.setup(fm, n, s_body, meta, gid0, gid1, gx0, gx1, sh_pair_itf, sh_L0, which ? nbR : nbF);
 #ifdef BW_PROFILE
                 if (tid == 0) { const long long now_ = clock64(); sh_prof_lp[1] += now_ - lpt; lpt = now_; }
 #endif
                 if (ready) res = lp.run(r_exit, z_inf, r);
-                if (which == 1 && res != LP_NONE) lp.store(PG.lp_meta + e, gI, freeR, sh_itf_pair, res == LP_FEASIBLE, sh_L0);
-                if (lane == 0) { sh_lp_res[which] = res; sh_lp_r[which] = r; sh_lp_piv += lp.pivots; }
+                if (which == 1 && res != LP_NONE) lp.store(PG.lp_meta + e, gI, gX, freeR, sh_itf_pair, res == LP_FEASIBLE, sh_L0);
+                if (lane == 0) { sh_lp_res[which] = res; sh_lp_r[which] = r; sh_lp_piv += lp.pivots; if (ready) sh_lp_flops += lp.flops; }
                 lp_count(PG, lp, res, which);
 #ifdef BW_PROFILE
                 if (tid == 0 && ready) for (int q = 0; q < 4; q++) sh_prof_lp[4 + q] += lp.tp[q];
@@ -764,7 +786,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                 resF = sh_lp_res[0];
                 if (resF != LP_FEASIBLE) break;
             } else if (sh_lp_res[1] != LP_NONE) {
-                Lp::store_rows(gB, lp.Binv, 3 * __popc(freeR) * L.MM, tid, 64);
+                Lp::store_rows(gB, lp.Binv, 3 * __popc(freeR) * lp.MS, tid, 64);
                 BW_LP_STAMP(3);
             }
         }
@@ -1072,7 +1094,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         o.residual = sh_res[0];
         o.residual_unfrozen = sh_res[1];
         o.newton_iters = sh_iters[0] + sh_iters[1];
-        o.solver_kflops = (int32_t)fmin(2e9, (sh_flops[0] + sh_flops[1]) * 1e-3);
+        o.solver_kflops = (int32_t)fmin(2e9, (sh_flops[0] + sh_flops[1] + sh_lp_flops) * 1e-3);
         o.n_blocks = n;
         o.n_interfaces = nitf;
         o.n_targets_reached = (uint8_t)n_reached;
