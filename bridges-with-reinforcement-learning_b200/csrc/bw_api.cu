@@ -375,6 +375,7 @@ int bw_create(const bw_config *cfg, bw_handle **out) {
         CU(dev_alloc(h, &P.lp_ids, (size_t)E * 3 * NB, false));
         CU(dev_alloc(h, &P.lp_xb, (size_t)E * 3 * NB, false));
         h->lp_enabled = getenv("BW_NO_LP") == nullptr;
+        P.lp_par = getenv("BW_LP_SEQ") ? 0 : 1;        // tuning hook (tools/ only): the two problems one after the other
         if (getenv("BW_LP_STATS")) CU(dev_alloc(h, &P.lp_stats, 32));   // tuning hook (tools/ only)
     }
     CU(dev_alloc(h, &P.cand_need, 1));

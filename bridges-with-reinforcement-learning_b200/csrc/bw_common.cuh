@@ -113,6 +113,8 @@ struct Params {
     int32_t lib_in_smem;
     // warm-started LP verdicts of real steps (bw_lp.cuh): the optimal basis of the released problem of the last step
     int32_t lp_on;             // 0: every verdict by the screen + Newton path (tuning hook BW_NO_LP)
+    int32_t lp_par;            // 1: frozen and released problem side by side on the two warps when their rows fit (BW_LP_SEQ: off)
+    int32_t lp_pad;
     int32_t lp_stride;         // doubles per environment in lp_binv: (3 max_blocks)^2 rounded up to an even count
     LpMeta *lp_meta;           // [E]
     double *lp_binv;           // [E][lp_stride] basis inverse, row stride 3 max_blocks

@@ -42,11 +42,13 @@ struct LpOff { int binv, xb, pi, w, b, f, ids, pos, crow, rowbase, freebody, siz
 // row stride of the basis inverse in shared memory and HBM: even, so that two columns are one 16-byte access
 __host__ __device__ inline int lp_row_stride(int MM) { return (MM + 1) & ~1; }
 
-__host__ __device__ inline LpOff lp_layout(int MM, int MC) {
+// One problem = a set of vectors (`vec` bytes, offsets below) + its basis inverse (rows x lp_row_stride doubles).
+// The region holds  [vectors 0 | vectors 1 | matrix 0 | matrix 1]: one problem at a time may use all 3 max_blocks rows
+// (matrix 0 then runs over matrix 1), two problems side by side need (m0 + m1) rows to fit.
+__host__ __device__ inline LpOff lp_layout(int MM, int MC, bool two_sets = true) {
     LpOff o;
     int p = 0;
     auto a16 = [](int x) { return (x + 15) & ~15; };
-    o.binv = p; p += a16(MM * lp_row_stride(MM) * 8);
     o.xb = p; p += a16(MM * 8);
     o.pi = p; p += a16(MM * 8);
     o.w = p; p += a16((MM + 4) * 8);          // padded: the update reads w four rows at a time
@@ -57,8 +59,13 @@ __host__ __device__ inline LpOff lp_layout(int MM, int MC) {
     o.crow = p; p += a16(2 * MC);
     o.rowbase = p; p += a16(NBODY);
     o.freebody = p; p += a16(NB);
-    o.size = p;
+    o.size = p;                               // bytes of one vector set
+    o.binv = two_sets ? 2 * p : p;            // offset of matrix 0 (a small region holds one vector set only)
     return o;
+}
+// bytes the region needs for one problem with all rows
+__host__ __device__ inline int lp_region_bytes(int MM, int MC, bool two_sets) {
+    return lp_layout(MM, MC, two_sets).binv + MM * lp_row_stride(MM) * 8;
 }
 
 // monotone map float -> uint32 (a < b  <=>  key(a) < key(b))
@@ -285,7 +292,7 @@ struct Lp {
         const int k2 = 2 * lane;
         const bool hk = k2 < m;
         const int MS2 = MS >> 1;                  // row stride in double2
-        double2 *col = reinterpret_cast<double2 *>(Binv + (hk ? k2 : 0));
+        double2 *__restrict__ col = reinterpret_cast<double2 *>(Binv + (hk ? k2 : 0));
         double2 *pi2s = reinterpret_cast<double2 *>(pi);
         const int i0 = lane, i1 = lane + 32;      // lane = row(s) in the ratio test
         double2 pi2 = make_double2(0.0, 0.0);
@@ -342,7 +349,7 @@ struct Lp {
             // pricing: reduced cost of ray (c, +-) = -(pi . a_n +- mu pi . a_t); most negative non-basic one enters
             double best = 0.0, dall = 0.0;
             int bestray = -1;
-#pragma unroll 1
+#pragma unroll 2
             for (int c = lane; c < nc; c += 32) {
                 const double2 *G2 = reinterpret_cast<const double2 *>(G + c * 12);
                 const unsigned cr = crow[c];
@@ -477,7 +484,7 @@ struct Lp {
             {
                 double2 t = col[p * MS2];
                 t.x *= inv; t.y *= inv;
-                const double2 *w2 = reinterpret_cast<const double2 *>(w);
+                const double2 *__restrict__ w2 = reinterpret_cast<const double2 *>(w);
 #pragma unroll 1
                 for (int i = 0; i < m; i += 4) {
                     const double2 wa = w2[i >> 1], wb = w2[(i >> 1) + 1];

@@ -138,7 +138,7 @@ int step_problem_bytes(int max_blocks, int max_itf, bool share_h) {
     const ProbOff po = prob_layout(L.MM, L.MC, L.HS, !share_h);
     return 2 * po.size + (share_h ? align16(L.HS * 8) : 0);
 }
-int lp_bytes(int max_blocks, int max_itf) { return lp_layout(3 * max_blocks, 2 * max_itf).size; }
+int lp_bytes(int max_blocks, int max_itf) { return lp_region_bytes(3 * max_blocks, 2 * max_itf, false); }
 
 // The optional image outputs of a step (bw_obs_out): the raster of all blocks as f32 [1,64,64] / u8 [64,64] /
 // bit-packed [64], from the CTA's shared copy `bits` (64 threads, 16-byte coalesced streaming stores).
@@ -286,6 +286,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __shared__ double sh_lp_r[2];
     __shared__ int sh_lp_piv;
     __shared__ double sh_lp_flops;
+    __shared__ int sh_lp_pivs[2];
+    __shared__ double sh_lp_flop2[2];
 
 #ifdef BW_PROFILE
     long long prof_t[8];
@@ -306,6 +308,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     const bw_action act = actions[e];
     const int n_old = P.n_blocks[e];
     // the LP path's stored basis: its header now, its rows on their way into L2 (they are read after the interfaces)
+    const double mu_e = P.mu[e];
     LpMeta lp_meta0;
     lp_meta0.mask = 0u; lp_meta0.m = 0; lp_meta0.feasible = 0; lp_meta0.L0 = 0.0;
     if (PG.lp_on && act.shape >= 0) {
@@ -324,7 +327,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     if (tid == 0) { sh_error = 0; sh_placed = 0; sh_nitf = 0; sh_verdict[0] = -1; sh_verdict[1] = -1; sh_hlock = 0; }
     if (tid < 4) sh_coll[tid] = 0;
     if (tid < 2) sh_lp_res[tid] = LP_NONE;
-    if (tid == 2) { sh_lp_piv = 0; sh_lp_flops = 0.0; }
+    if (tid == 2) { sh_lp_piv = 0; sh_lp_flops = 0.0; sh_lp_pivs[0] = sh_lp_pivs[1] = 0; sh_lp_flop2[0] = sh_lp_flop2[1] = 0.0; }
 #ifdef BW_PROFILE
     if (tid < 8) sh_prof_lp[tid] = 0;
 #endif
@@ -699,14 +702,16 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         smask |= 1u << (n - 1);                  // action.frozen = True; freeze_block(n-1)
     }
     // ---------------- phase 3a: the verdicts of a real step as warm-started linear programmes (bw_lp.cuh).
-    // The two problems run one after the other on warp 0 in the memory of the two Newton problems (the basis
-    // inverse takes most of it); both start from the basis the released problem of the previous step ended
-    // with.  The frozen problem first -- unless the previous released verdict already implies it -- and the
-    // released one only if the frozen one has an equilibrium (no frozen equilibrium => no released one; the
-    // episode ends there).  All threads copy the stored rows in and the final ones out.
+    // Both problems start from the basis the released problem of the previous step ended with and work in the
+    // memory of the two Newton problems (the basis inverses take most of it).  The frozen problem is decided
+    // without a run when the previous released verdict implies it; when both are needed and their rows fit side
+    // by side, warp 0 runs the frozen and warp 1 the released problem at the same time, else warp 0 runs them one
+    // after the other (the released one only if the frozen one has an equilibrium: no frozen equilibrium => no
+    // released one, and the episode ends there).
     const bool lp_try = PG.lp_on != 0 && placed && save_itf == nullptr && !overflow && nitf > 0 && n >= 1;
     if (lp_try) {
-        const LpOff lo = lp_layout(L.MM, L.MC);
+        const int region = 2 * prob_layout(L.MM, L.MC, L.HS, PG.share_h == 0).size + (PG.share_h ? align16(L.HS * 8) : 0);
+        const LpOff lo = lp_layout(L.MM, L.MC, lp_region_bytes(L.MM, L.MC, true) <= region);
         unsigned char *lb = smem + L.prob[0];
         const LpMeta meta = lp_meta0;
         double *gB = PG.lp_binv + (size_t)e * PG.lp_stride;
@@ -714,23 +719,34 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         double *gX = PG.lp_xb + (size_t)e * 3 * NB;
         const uint32_t allmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
         const uint32_t freeF = allmask & ~smask, freeR = freeF | (1u << (n - 1));
+        const int MS = lp_row_stride(L.MM);
+        const int mF = 3 * __popc(freeF), mR = mF + 3;
+        // frozen problem: decided without a run when nothing is free or the previous released verdict implies it
+        const bool need_F = freeF != 0u && !prev_released_ok;
+        const bool par = need_F && PG.lp_par != 0 && lo.binv == 2 * lo.size && lo.binv + (mF + mR) * MS * 8 <= region;
+        const int set = par ? warp : 0;           // vector set / matrix this warp works on
         Lp lp;
         lp.G = s_G; lp.c_a = s_ca; lp.c_b = s_cb; lp.adj_ptr = s_adj_ptr; lp.adj = s_adj;
-        lp.Binv = reinterpret_cast<double *>(lb + lo.binv);
-        lp.xB = reinterpret_cast<double *>(lb + lo.xb);
-        lp.pi = reinterpret_cast<double *>(lb + lo.pi);
-        lp.w = reinterpret_cast<double *>(lb + lo.w);
-        lp.b = reinterpret_cast<double *>(lb + lo.b);
-        lp.f = reinterpret_cast<double *>(lb + lo.f);
-        lp.ids = reinterpret_cast<uint16_t *>(lb + lo.ids);
-        lp.pos = lb + lo.pos;
-        lp.rowbase = reinterpret_cast<int8_t *>(lb + lo.rowbase);
-        lp.freebody = lb + lo.freebody;
-        lp.MS = lp_row_stride(L.MM);
-        lp.crow = reinterpret_cast<uint16_t *>(lb + lo.crow);
+        {
+            unsigned char *vb = lb + set * lo.size;
+            lp.Binv = reinterpret_cast<double *>(lb + lo.binv) + (set ? mF * MS : 0);
+            lp.xB = reinterpret_cast<double *>(vb + lo.xb);
+            lp.pi = reinterpret_cast<double *>(vb + lo.pi);
+            lp.w = reinterpret_cast<double *>(vb + lo.w);
+            lp.b = reinterpret_cast<double *>(vb + lo.b);
+            lp.f = reinterpret_cast<double *>(vb + lo.f);
+            lp.ids = reinterpret_cast<uint16_t *>(vb + lo.ids);
+            lp.pos = vb + lo.pos;
+            lp.crow = reinterpret_cast<uint16_t *>(vb + lo.crow);
+            lp.rowbase = reinterpret_cast<int8_t *>(vb + lo.rowbase);
+            lp.freebody = vb + lo.freebody;
+        }
+        lp.MS = MS;
         lp.nc = nc;
         lp.lane = lane;
-        lp.mu = P.mu[e];
+        lp.mu = mu_e;
+        lp.pivots = 0;
+        lp.flops = 0.0;
         const double r_exit = fmin(P.stable_tol, 1e-6);
         const double z_inf = fmax(1e-5, 7.0 * P.stable_tol);
         // norms of the two right-hand sides (weights of the free blocks): one reduction for both problems
@@ -746,35 +762,39 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         // stored column identities and basic solution (rows lane, lane + 32): on their way while the rows are copied in
         uint16_t gid0 = LP_ART, gid1 = LP_ART;
         double gx0 = 0.0, gx1 = 0.0;
-        if (warp == 0) {
+        if (par || warp == 0) {
             if (lane < (int)meta.m) { gid0 = gI[lane]; gx0 = gX[lane]; }
             if (lane + 32 < (int)meta.m) { gid1 = gI[lane + 32]; gx1 = gX[lane + 32]; }
         }
-        // frozen problem: decided without a solve when nothing is free or the previous released verdict implies it
-        const bool need_F = freeF != 0u && !prev_released_ok;
-        int resF = LP_FEASIBLE;
 #ifdef BW_PROFILE
         long long lpt = clock64();
 #define BW_LP_STAMP(i) if (tid == 0) { const long long now_ = clock64(); sh_prof_lp[i] += now_ - lpt; lpt = now_; }
 #else
 #define BW_LP_STAMP(i)
 #endif
+        const int first = need_F ? 0 : 1;
+        const int trips = par ? 1 : 2 - first;
 #pragma unroll 1
-        for (int which = need_F ? 0 : 1; which < 2; which++) {
+        for (int it = 0; it < trips; it++) {
+            const int which = par ? warp : first + it;
             const uint32_t fm = which ? freeR : freeF;
-            Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * lp.MS, tid, 64);
-            __syncthreads();
+            const bool active = par || warp == 0;
+            // copy-in: every thread that will wait for this problem anyway takes part
+            if (par) {
+                Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * MS, lane, 32);
+                __syncwarp();
+            } else {
+                Lp::load_rows(lp.Binv, gB, Lp::usable_rows(meta, fm) * MS, tid, 64);
+                __syncthreads();
+            }
             BW_LP_STAMP(0);
-            if (warp == 0) {
+            if (active) {
                 int res = LP_NONE;
                 double r = 0.0;
                 const bool ready = lp.setup(fm, n, s_body, meta, gid0, gid1, gx0, gx1, sh_pair_itf, sh_L0, which ? nbR : nbF);
-#ifdef BW_PROFILE
-                if (tid == 0) { const long long now_ = clock64(); sh_prof_lp[1] += now_ - lpt; lpt = now_; }
-#endif
+                BW_LP_STAMP(1);
                 if (ready) res = lp.run(r_exit, z_inf, r);
-                if (which == 1 && res != LP_NONE) lp.store(PG.lp_meta + e, gI, gX, freeR, sh_itf_pair, res == LP_FEASIBLE, sh_L0);
-                if (lane == 0) { sh_lp_res[which] = res; sh_lp_r[which] = r; sh_lp_piv += lp.pivots; if (ready) sh_lp_flops += lp.flops; }
+                if (lane == 0) { sh_lp_res[which] = res; sh_lp_r[which] = r; sh_lp_pivs[which] = lp.pivots; sh_lp_flop2[which] = ready ? lp.flops : 0.0; }
                 lp_count(PG, lp, res, which);
 #ifdef BW_PROFILE
                 if (tid == 0 && ready) for (int q = 0; q < 4; q++) sh_prof_lp[4 + q] += lp.tp[q];
@@ -782,18 +802,24 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             }
             __syncthreads();
             BW_LP_STAMP(2);
-            if (which == 0) {
-                resF = sh_lp_res[0];
-                if (resF != LP_FEASIBLE) break;
-            } else if (sh_lp_res[1] != LP_NONE) {
-                Lp::store_rows(gB, lp.Binv, 3 * __popc(freeR) * lp.MS, tid, 64);
-                BW_LP_STAMP(3);
-            }
+            if (!par && which == 0 && sh_lp_res[0] != LP_FEASIBLE) break;
         }
-        if (resF == LP_INFEASIBLE && tid == 0) { sh_lp_res[1] = LP_INFEASIBLE; sh_lp_r[1] = nan(""); }
-        // an answer the LP could not certify: both problems go to the Newton path; without a final released basis the
-        // next step starts from an empty one
+        const int resF = need_F ? sh_lp_res[0] : LP_FEASIBLE;
+        // the final basis of the released problem goes back to HBM (all threads); it is only worth keeping when the
+        // episode goes on, i.e. when the frozen problem has an equilibrium
+        if (resF == LP_FEASIBLE && sh_lp_res[1] != LP_NONE) {
+            const double *BR = reinterpret_cast<const double *>(lb + lo.binv) + (par ? mF * MS : 0);
+            // (column identities, basic solution and header by the warp that ran the released problem: nobody reads
+            // the stored ones any more)
+            if (warp == (par ? 1 : 0)) lp.store(PG.lp_meta + e, gI, gX, freeR, sh_itf_pair, sh_lp_res[1] == LP_FEASIBLE, sh_L0);
+            Lp::store_rows(gB, BR, mR * MS, tid, 64);
+            BW_LP_STAMP(3);
+        }
+        __syncthreads();
         if (tid == 0) {
+            if (resF == LP_INFEASIBLE) { sh_lp_res[1] = LP_INFEASIBLE; sh_lp_r[1] = nan(""); }
+            // an answer the LP could not certify: both problems go to the Newton path; without a final released basis
+            // the next step starts from an empty one
             const bool failed = (need_F && sh_lp_res[0] == LP_NONE) || (resF == LP_FEASIBLE && sh_lp_res[1] == LP_NONE);
             if (failed) { sh_lp_res[0] = LP_NONE; sh_lp_res[1] = LP_NONE; }
             if (failed || resF != LP_FEASIBLE) {
@@ -801,6 +827,8 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
                 none.mask = 0u; none.m = 0; none.feasible = 0; none.L0 = 0.0;
                 PG.lp_meta[e] = none;
             }
+            sh_lp_piv = sh_lp_pivs[0] + sh_lp_pivs[1];
+            sh_lp_flops = sh_lp_flop2[0] + sh_lp_flop2[1];
         }
         __syncthreads();
     }
