@@ -37,7 +37,7 @@ struct LpMeta {            // per environment, next to the stored basis
     double L0;             // torque-row scale (largest shape radius among the blocks) the stored inverse was built with
 };
 
-struct LpOff { int binv, xb, pi, w, b, f, ids, pos, crow, rowbase, freebody, size; };
+struct LpOff { int binv, xb, pi, w, b, ids, pos, crow, rowbase, freebody, size; };
 
 // row stride of the basis inverse in shared memory and HBM: even, so that two columns are one 16-byte access
 __host__ __device__ inline int lp_row_stride(int MM) { return (MM + 1) & ~1; }
@@ -53,7 +53,6 @@ __host__ __device__ inline LpOff lp_layout(int MM, int MC, bool two_sets = true)
     o.pi = p; p += a16(MM * 8);
     o.w = p; p += a16((MM + 4) * 8);          // padded: the update reads w four rows at a time
     o.b = p; p += a16(MM * 8);
-    o.f = p; p += a16(2 * MC * 8);
     o.ids = p; p += a16(MM * 2);
     o.pos = p; p += a16(2 * MC);
     o.crow = p; p += a16(2 * MC);
@@ -84,7 +83,7 @@ struct Lp {
     const double *G;
     const uint8_t *c_a, *c_b, *adj_ptr, *adj;
     // this problem
-    double *Binv, *xB, *pi, *w, *b, *f;
+    double *Binv, *xB, *pi, *w, *b;
     uint16_t *ids;            // basic column of every row position: LP_ART or ray = 2 * contact + sign
     uint8_t *pos;             // ray -> position in the basis, 0xFF = non-basic
     uint16_t *crow;           // contact point -> (first row of body a + 1) | (first row of body b + 1) << 8, 0 = support
@@ -246,16 +245,9 @@ struct Lp {
         return !__any_sync(FULL, bad);
     }
 
-    // ||b - A f|| of the basic solution (f = the forces the basic rays stand for), from the contact data
+    // ||b - A f|| of the basic solution (f = the forces the basic rays stand for: fn = lambda+ + lambda-,
+    // ft = mu (lambda+ - lambda-)), from the contact data
     __device__ double primal_residual() {
-#pragma unroll 1
-        for (int c = lane; c < nc; c += 32) {
-            const int p0 = pos[2 * c], p1 = pos[2 * c + 1];
-            const double lp = (p0 != 0xFF) ? xB[p0] : 0.0, lm = (p1 != 0xFF) ? xB[p1] : 0.0;
-            f[2 * c] = lp + lm;
-            f[2 * c + 1] = mu * (lp - lm);
-        }
-        __syncwarp();
         double acc = 0.0;
 #pragma unroll 1
         for (int i = lane; i < m; i += 32) {
@@ -266,8 +258,10 @@ struct Lp {
             for (int q = adj_ptr[body]; q < adj_ptr[body + 1]; q++) {
                 const int e = adj[q];
                 const int c = e & 0x7f;
+                const unsigned bp = reinterpret_cast<const uint16_t *>(pos)[c];
+                const double lp = ((bp & 0xffu) != 0xffu) ? xB[bp & 0xffu] : 0.0, lm = ((bp >> 8) != 0xffu) ? xB[bp >> 8] : 0.0;
                 const double *Gc = G + c * 12 + (e >> 7) * 6;
-                af += Gc[k] * f[2 * c] + Gc[3 + k] * f[2 * c + 1];
+                af += Gc[k] * (lp + lm) + Gc[3 + k] * (mu * (lp - lm));
             }
             const double r = b[i] - af;
             acc += r * r;

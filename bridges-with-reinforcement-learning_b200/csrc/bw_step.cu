@@ -734,7 +734,6 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
             lp.pi = reinterpret_cast<double *>(vb + lo.pi);
             lp.w = reinterpret_cast<double *>(vb + lo.w);
             lp.b = reinterpret_cast<double *>(vb + lo.b);
-            lp.f = reinterpret_cast<double *>(vb + lo.f);
             lp.ids = reinterpret_cast<uint16_t *>(vb + lo.ids);
             lp.pos = vb + lo.pos;
             lp.crow = reinterpret_cast<uint16_t *>(vb + lo.crow);

@@ -25,11 +25,17 @@ def _bridge(n, sq=0.6):
     return dict(obstacles=[(i * sq, 0, sq / 2) for i in range(1, n + 1)], targets=[(n * sq + 2.5 * sq, 0, sq / 2)])
 
 
-def _pair(monkeypatch, E, shapes, max_steps):
-    """(LP handle, Newton-only handle) with the same configuration"""
+def _pair(monkeypatch, E, shapes, max_steps, share_h=None):
+    """(LP handle, Newton-only handle) with the same configuration.  share_h: the shared-memory layout of
+    multi-wave launches for the LP handle (tuning hook BW_SHARE_H: one packed matrix for both Newton problems, hence
+    a smaller region for the LP, which then runs its two problems one after the other on one vector set)"""
     from bridges_b200.envs.batched import BatchedAssemblyGym
     urdfs = [f"shapes/{s}.urdf" for s in shapes]
+    if share_h is not None:
+        monkeypatch.setenv("BW_SHARE_H", str(share_h))
     a = BatchedAssemblyGym(E, urdfs, max_steps=max_steps)
+    if share_h is not None:
+        monkeypatch.delenv("BW_SHARE_H")
     monkeypatch.setenv("BW_NO_LP", "1")
     b = BatchedAssemblyGym(E, urdfs, max_steps=max_steps)
     monkeypatch.delenv("BW_NO_LP")
@@ -67,14 +73,15 @@ def _compare(oa, ob, tag, stats):
     stats["newton_plain"] += int(ob["newton_iters"].sum())
 
 
-@pytest.mark.parametrize("case", ["tower2", "tower4_max15", "bridge5_mixed_max15"])
+@pytest.mark.parametrize("case", ["tower2", "tower4_max15", "bridge5_mixed_max15", "bridge5_mixed_max15_lean_layout"])
 def test_lp_path_is_a_pure_shortcut_of_the_newton_path(case, monkeypatch):
     cfg = {"tower2": (["trapezoid"], _tower(2), 10, 128),
            "tower4_max15": (["trapezoid"], _tower(4), 15, 256),
-           "bridge5_mixed_max15": (["trapezoid", "hexagon"], _bridge(5), 15, 1024)}[case]
+           "bridge5_mixed_max15": (["trapezoid", "hexagon"], _bridge(5), 15, 1024),
+           "bridge5_mixed_max15_lean_layout": (["trapezoid", "hexagon"], _bridge(5), 15, 1024)}[case]
     shapes, task, max_steps, amax = cfg
     E, steps = 192, 70
-    a, b = _pair(monkeypatch, E, shapes, max_steps)
+    a, b = _pair(monkeypatch, E, shapes, max_steps, share_h=2 if case.endswith("lean_layout") else None)
     a.reset(task)
     b.reset(task)
     stats = dict(band=0, by_lp=0, verdicts=0, pivots=0, newton_lp_handle=0, newton_plain=0)
