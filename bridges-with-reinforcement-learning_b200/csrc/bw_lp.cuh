@@ -64,7 +64,7 @@ __host__ __device__ inline LpOff lp_layout(int MM, int MC, bool two_sets = true)
 }
 // bytes the region needs for one problem with all rows
 __host__ __device__ inline int lp_region_bytes(int MM, int MC, bool two_sets) {
-    return lp_layout(MM, MC, two_sets).binv + MM * lp_row_stride(MM) * 8;
+    return lp_layout(MM, MC, two_sets).binv + ((MM + 3) & ~3) * lp_row_stride(MM) * 8;     // rows in fours (update)
 }
 
 // monotone map float -> uint32 (a < b  <=>  key(a) < key(b))
@@ -274,7 +274,7 @@ struct Lp {
     // least-squares residual from below by z* / sqrt(m), so z_inf >= sqrt(m) stable_tol keeps the verdict rule).
     // Returns LP_FEASIBLE (res = ||b - A f|| <= r_exit), LP_INFEASIBLE (certificate), or LP_NONE.
     __device__ int run(double r_exit, double z_inf, double &res) {
-        const int maxpiv = 4 * m + 16;
+        const int maxpiv = 2 * m + 24;            // (an empty basis needs about 1.5 m pivots; warm runs 3, 30 at the most)
         why = 0;
         flops = 0.0;
 #ifdef BW_PROFILE
@@ -483,14 +483,15 @@ struct Lp {
                 for (int i = 0; i < m; i += 4) {
                     const double2 wa = w2[i >> 1], wb = w2[(i >> 1) + 1];
                     if ((wa.x == 0.0) & (wa.y == 0.0) & (wb.x == 0.0) & (wb.y == 0.0)) continue;     // uniform
-                    // rows past the end carry w = 0; their index is clamped (the value is written back as it is)
-                    const int j1 = min(i + 1, m - 1), j2 = min(i + 2, m - 1), j3 = min(i + 3, m - 1);
-                    const double2 b0 = col[i * MS2], b1 = col[j1 * MS2], b2 = col[j2 * MS2], b3 = col[j3 * MS2];
+                    // (the matrix is allocated in fours of rows: the rows past the end carry w = 0 and are written
+                    // back as they are)
+                    double2 *r = col + i * MS2;
+                    const double2 b0 = r[0], b1 = r[MS2], b2 = r[2 * MS2], b3 = r[3 * MS2];
                     if (hk) {
-                        col[i * MS2] = make_double2(fma(-wa.x, t.x, b0.x), fma(-wa.x, t.y, b0.y));
-                        if (i + 1 < m) col[j1 * MS2] = make_double2(fma(-wa.y, t.x, b1.x), fma(-wa.y, t.y, b1.y));
-                        if (i + 2 < m) col[j2 * MS2] = make_double2(fma(-wb.x, t.x, b2.x), fma(-wb.x, t.y, b2.y));
-                        if (i + 3 < m) col[j3 * MS2] = make_double2(fma(-wb.y, t.x, b3.x), fma(-wb.y, t.y, b3.y));
+                        r[0] = make_double2(fma(-wa.x, t.x, b0.x), fma(-wa.x, t.y, b0.y));
+                        r[MS2] = make_double2(fma(-wa.y, t.x, b1.x), fma(-wa.y, t.y, b1.y));
+                        r[2 * MS2] = make_double2(fma(-wb.x, t.x, b2.x), fma(-wb.x, t.y, b2.y));
+                        r[3 * MS2] = make_double2(fma(-wb.y, t.x, b3.x), fma(-wb.y, t.y, b3.y));
                     }
                 }
                 if (hk) col[p * MS2] = t;

@@ -320,7 +320,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         for (int off = tid * 128; off < bytes; off += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + off));
     }
     const uint64_t old_bits = P.block_bits[(size_t)e * IMG + tid];   // image row tid, used after the placement
-    if (tid < n_old) {
+    if (tid < NB) {     // all slots: the loads do not wait for the block count (slots past it hold stale poses)
         s_pose[tid] = P.pose[(size_t)e * NB + tid];
         s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
     }
@@ -723,13 +723,14 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         const int mF = 3 * __popc(freeF), mR = mF + 3;
         // frozen problem: decided without a run when nothing is free or the previous released verdict implies it
         const bool need_F = freeF != 0u && !prev_released_ok;
-        const bool par = need_F && PG.lp_par != 0 && lo.binv == 2 * lo.size && lo.binv + (mF + mR) * MS * 8 <= region;
+        const int aF = (mF + 3) & ~3, aR = (mR + 3) & ~3;       // matrices are allocated in fours of rows (Lp::run update)
+        const bool par = need_F && PG.lp_par != 0 && lo.binv == 2 * lo.size && lo.binv + (aF + aR) * MS * 8 <= region;
         const int set = par ? warp : 0;           // vector set / matrix this warp works on
         Lp lp;
         lp.G = s_G; lp.c_a = s_ca; lp.c_b = s_cb; lp.adj_ptr = s_adj_ptr; lp.adj = s_adj;
         {
             unsigned char *vb = lb + set * lo.size;
-            lp.Binv = reinterpret_cast<double *>(lb + lo.binv) + (set ? mF * MS : 0);
+            lp.Binv = reinterpret_cast<double *>(lb + lo.binv) + (set ? aF * MS : 0);
             lp.xB = reinterpret_cast<double *>(vb + lo.xb);
             lp.pi = reinterpret_cast<double *>(vb + lo.pi);
             lp.w = reinterpret_cast<double *>(vb + lo.w);
@@ -807,7 +808,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         // the final basis of the released problem goes back to HBM (all threads); it is only worth keeping when the
         // episode goes on, i.e. when the frozen problem has an equilibrium
         if (resF == LP_FEASIBLE && sh_lp_res[1] != LP_NONE) {
-            const double *BR = reinterpret_cast<const double *>(lb + lo.binv) + (par ? mF * MS : 0);
+            const double *BR = reinterpret_cast<const double *>(lb + lo.binv) + (par ? aF * MS : 0);
             // (column identities, basic solution and header by the warp that ran the released problem: nobody reads
             // the stored ones any more)
             if (warp == (par ? 1 : 0)) lp.store(PG.lp_meta + e, gI, gX, freeR, sh_itf_pair, sh_lp_res[1] == LP_FEASIBLE, sh_L0);
