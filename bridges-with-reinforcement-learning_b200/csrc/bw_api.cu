@@ -581,7 +581,7 @@ int bw_reset(bw_handle *h, const bw_task *d_tasks, const uint8_t *d_mask) {
     if (d_tasks != nullptr) {
         h->resets_unchecked = true;
         // pre-placed blocks: refresh the verdicts / distances as add_block does (gym_env.py:279-281)
-        launch_step(h->P, h->d_noop, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr,
+        launch_step(h->P, nullptr, d_mask, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr,
                     0, h->smem_step, h->stream);
         h->launches++;
     }
@@ -635,6 +635,20 @@ int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_
     // one kernel: placement, interfaces, both solves, bookkeeping, raster update and the
     // observation write
     launch_step(h->P, d_actions, d_mask, d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, 0,
+                h->smem_step, h->stream);
+    h->launches++;
+    if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_evaluate(bw_handle *h, const uint8_t *d_mask, bw_step_out *d_out, const bw_obs_out *obs) {
+    if (!h || !d_out) return BW_ERR_INVALID;
+    if (int rc = need_shapes(h)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->timing) CU(cudaEventRecord(h->ev[0], h->stream));
+    // the step kernel without an action: interfaces, both verdicts, distances, observations of what stands
+    launch_step(h->P, nullptr, d_mask, d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, 0,
                 h->smem_step, h->stream);
     h->launches++;
     if (h->timing) CU(cudaEventRecord(h->ev[1], h->stream));
@@ -1125,7 +1139,7 @@ int bw_get_forces(bw_handle *h, int32_t variant, bw_interface *h_itf, int32_t *h
     CU(cudaMemsetAsync(h->d_itf, 0, sizeof(bw_interface) * E * BW_MAX_INTERFACES, h->stream));
     // the state did not change since the last step: re-evaluating it reproduces the same
     // interfaces and dual iterates, this time with the read-back enabled
-    launch_step(h->P, h->d_noop, nullptr, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, h->d_itf, h->d_nitf,
+    launch_step(h->P, nullptr, nullptr, h->d_scratch_out, bw_obs_out{nullptr, nullptr, nullptr, nullptr}, h->d_itf, h->d_nitf,
                 variant, h->smem_step, h->stream);
     h->launches++;
     CU(cudaGetLastError());

@@ -194,7 +194,10 @@ __device__ __forceinline__ void lp_count(const Params &P, const Lp &lp, int res,
 }
 
 // ------------------------------------------------------------------ the kernel
-template <bool TWO>
+// EVAL: no action is read and nothing is placed (every action counts as Action.shape = -1) -- the verdicts, distances
+// and observations of the assemblies as they stand (bw_evaluate, the sweep).  Placement, raster update, the LP path
+// and the target book-keeping are compiled out: a smaller image for the launches that only evaluate.
+template <bool TWO, bool EVAL>
 __global__ void __launch_bounds__(64, 8)
 step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__restrict__ mask,
             bw_step_out *__restrict__ out, bw_obs_out obs, bw_interface *__restrict__ save_itf,
@@ -305,13 +308,19 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
         if (tid >= 32 && tid < 32 + NB / 4)
             reinterpret_cast<uint32_t *>(sh_occ)[tid - 32] = reinterpret_cast<const uint32_t *>(P.face_occ + (size_t)e * NB)[tid - 32];
     }
-    const bw_action act = actions[e];
+    bw_action act;
+    if (EVAL) {
+        act.target_block = -1; act.target_face = 0; act.shape = -1; act.face = 0;
+        act.offset_x = 0.0; act.offset_y = 0.0; act.frozen = 0; act.reserved0 = 0;
+    } else {
+        act = actions[e];
+    }
     const int n_old = P.n_blocks[e];
     // the LP path's stored basis: its header now, its rows on their way into L2 (they are read after the interfaces)
     const double mu_e = P.mu[e];
     LpMeta lp_meta0;
     lp_meta0.mask = 0u; lp_meta0.m = 0; lp_meta0.feasible = 0; lp_meta0.L0 = 0.0;
-    if (PG.lp_on && act.shape >= 0) {
+    if (!EVAL && PG.lp_on && act.shape >= 0) {
         lp_meta0 = PG.lp_meta[e];
         const char *rows = reinterpret_cast<const char *>(PG.lp_binv + (size_t)e * PG.lp_stride);
         const int bytes = (int)lp_meta0.m * lp_row_stride(3 * PG.max_blocks) * 8;
@@ -342,7 +351,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     // ---------------- phase 1: placement (thread 0)
     if (tid == 0) {
         int n = n_old;
-        if (act.shape >= 0) {
+        if (!EVAL && act.shape >= 0) {
             Pose np;
             const int err = place_block(P, s_pose, s_shape, n_old, act, np);
             if (err) sh_error = err;
@@ -358,7 +367,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     __syncthreads();
     const int n = sh_n;
     const int nbody = n + 1;
-    const bool placed = sh_placed != 0;
+    const bool placed = !EVAL && sh_placed != 0;
     if (sh_error != 0) {
         // a refused action (invalid indices / environment full) leaves the state alone, but the caller's
         // buffers are still written -- the unchanged observation -- and the episode is flagged as over, so a
@@ -708,7 +717,7 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
     // by side, warp 0 runs the frozen and warp 1 the released problem at the same time, else warp 0 runs them one
     // after the other (the released one only if the frozen one has an equilibrium: no frozen equilibrium => no
     // released one, and the episode ends there).
-    const bool lp_try = PG.lp_on != 0 && placed && save_itf == nullptr && !overflow && nitf > 0 && n >= 1;
+    const bool lp_try = !EVAL && PG.lp_on != 0 && placed && save_itf == nullptr && !overflow && nitf > 0 && n >= 1;
     if (lp_try) {
         const int region = 2 * prob_layout(L.MM, L.MC, L.HS, PG.share_h == 0).size + (PG.share_h ? align16(L.HS * 8) : 0);
         const LpOff lo = lp_layout(L.MM, L.MC, lp_region_bytes(L.MM, L.MC, true) <= region);
@@ -1194,18 +1203,27 @@ step_kernel(Params PG, const bw_action *__restrict__ actions, const uint8_t *__r
 void launch_step(Params &P, const bw_action *d_actions, const uint8_t *d_mask, bw_step_out *d_out,
                  const bw_obs_out &obs, bw_interface *d_itf, int32_t *d_nitf, int variant, int smem_bytes,
                  cudaStream_t stream) {
-    // 3 rows per free block + the right-hand side row: one row per lane up to 10 blocks
-    if (3 * P.max_blocks + 1 <= 32)
-        step_kernel<false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
-    else
-        step_kernel<true><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
+    // 3 rows per free block + the right-hand side row: one row per lane up to 10 blocks.  d_actions = nullptr:
+    // evaluation only (the EVAL instantiations)
+    const bool two = !(3 * P.max_blocks + 1 <= 32);
+    if (d_actions == nullptr) {
+        if (!two) step_kernel<false, true><<<P.E, 64, smem_bytes, stream>>>(P, nullptr, d_mask, d_out, obs, d_itf, d_nitf, variant);
+        else step_kernel<true, true><<<P.E, 64, smem_bytes, stream>>>(P, nullptr, d_mask, d_out, obs, d_itf, d_nitf, variant);
+    } else {
+        if (!two) step_kernel<false, false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
+        else step_kernel<true, false><<<P.E, 64, smem_bytes, stream>>>(P, d_actions, d_mask, d_out, obs, d_itf, d_nitf, variant);
+    }
     P.order_phase = (P.order_phase + 1) % 3;     // the queue this launch filled is the next one's order
 }
 
 cudaError_t configure_step(int smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = cudaFuncSetAttribute(step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
 }  // namespace bw

@@ -243,14 +243,25 @@ class BatchedAssemblyGym:
             res[name] = col.view(tmap[fdt.str]).reshape(self.num_envs)
         return res
 
-    def evaluate(self):
-        """Verdicts of the current assemblies without placing a block (Action.shape = -1)."""
-        if getattr(self, "_noop_actions", None) is None:
-            arr = np.zeros(self.num_envs, dtype=self.dt["action"])
-            arr["target_block"] = -1
-            arr["shape"] = -1
-            self._noop_actions = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(self.device)
-        return self.step(self._noop_actions)
+    def evaluate(self, mask=None, block_img=None, binary=None, block_bits=None):
+        """Verdicts, distances and (optionally) observations of the current assemblies without placing a block:
+        `bw_evaluate`, what `step` does for Action.shape = -1 from the evaluation-only kernel image.
+        mask: uint8 CUDA tensor [E] or None.  Returns the device tensor holding bw_step_out[E]."""
+        d_mask = None
+        if mask is not None:
+            d_mask = mask.to(torch.uint8).contiguous() if isinstance(mask, torch.Tensor) and mask.is_cuda \
+                else self._to_device_bytes(np.asarray(mask, dtype=np.uint8))
+            self._keep = d_mask
+        obs = None
+        if block_img is not None or binary is not None or block_bits is not None:
+            obs = L.bw_obs_out(block_img.data_ptr() if block_img is not None else None, None,
+                               binary.data_ptr() if binary is not None else None,
+                               block_bits.data_ptr() if block_bits is not None else None)
+        self._check(self.lib.bw_evaluate(self.handle, d_mask.data_ptr() if d_mask is not None else None,
+                                         self._out.data_ptr(), C.byref(obs) if obs is not None else None))
+        if d_mask is not None and not (isinstance(mask, torch.Tensor) and mask.is_cuda):
+            self.sync()
+        return self._out
 
     # ------------------------------------------------------------------ observations
     def observe(self, block=True, binary=True, obstacle=False, reward=False):

@@ -150,6 +150,7 @@ SIGNATURES = {
     "bw_reset_host": (C.c_int, [_H, _P, _P]),
     "bw_reset_done": (C.c_int, [_H]),
     "bw_step": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
+    "bw_evaluate": (C.c_int, [_H, _P, _P, C.POINTER(bw_obs_out)]),
     "bw_step_host": (C.c_int, [_H, _P, _P, _P, C.POINTER(bw_obs_out)]),
     "bw_set_host_transfer": (C.c_int, [_H, C.c_int32]),
     "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),

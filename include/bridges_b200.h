@@ -215,6 +215,11 @@ int bw_step(bw_handle *h, const bw_action *d_actions, const uint8_t *d_mask, bw_
             const bw_obs_out *obs);
 int bw_step_host(bw_handle *h, const bw_action *h_actions, const uint8_t *h_mask, bw_step_out *h_out,
                  const bw_obs_out *obs);
+/* The same without an action: interfaces, both verdicts (stabilities_freezing, gym_env.py:325-333), distances and
+ * observations of the assemblies as they stand -- AssemblyEnv._update_state_info (assembly_env.py:404-438) for every
+ * environment, what bw_step does for Action.shape = -1, from a smaller kernel image (no placement, no raster update,
+ * no LP path).  d_mask (NULL = all), d_out[E], obs as in bw_step (device pointers, may be NULL). */
+int bw_evaluate(bw_handle *h, const uint8_t *d_mask, bw_step_out *d_out, const bw_obs_out *obs);
 /* How bw_step_host moves its buffers.  0 (default): automatic -- when every host buffer of the call
  * is pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()) the step kernel reads the
  * actions from and writes records / images to host memory directly over PCIe, every environment
