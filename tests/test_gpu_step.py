@@ -275,6 +275,46 @@ def test_host_entry_point_pinned_buffers_zero_copy():
         assert np.array_equal(bufs[0]["u8"].numpy().astype(bool), a.bits_to_bool(bits))
 
 
+@pytest.mark.parametrize("max_steps", [10, None])
+def test_evaluate_equals_a_step_without_action(max_steps):
+    """bw_evaluate (the evaluation-only kernel image: no placement, no raster update, no LP path) against bw_step with
+    Action.shape = -1 on the same assemblies: identical records, rasters and binary features, with and without a
+    mask, in both solver instantiations; neither call changes the state."""
+    import torch
+    from oracle import synth
+    rng = np.random.default_rng(31)
+    N = 96
+    lib = synth.library()
+    plans = [synth.random_assembly(rng, lib, max_blocks=9, min_blocks=2) for _ in range(N)]
+    env = _gpu_env(N, ["shapes/trapezoid.urdf", "shapes/hexagon.urdf", "shapes/cube1.urdf"], max_steps=max_steps)
+    env.set_mu([synth.MUS[i % 3] for i in range(N)])
+    env.reset(dict(targets=[(0.5, 0, 2.5)]))
+    for k in range(max(len(p) for p in plans)):
+        env.step([(p[k].target_block, p[k].target_face, p[k].shape, p[k].face, p[k].offset_x, p[k].offset_y)
+                  if k < len(p) else None for p in plans])
+    blocks0, n0 = env.get_state()
+    names = ("stable", "stable_unfrozen", "n_blocks", "n_interfaces", "reward", "terminated", "truncated", "error",
+             "collision", "n_targets_reached", "newton_iters", "solver_status", "lp_pivots")
+    for mask in (None, (np.arange(N) % 3 != 0).astype(np.uint8)):
+        imgs = [torch.zeros((N, 1, 64, 64), dtype=torch.float32, device="cuda") for _ in range(2)]
+        bins = [torch.zeros((N, 6), dtype=torch.float32, device="cuda") for _ in range(2)]
+        env.step([None] * N, mask=mask, block_img=imgs[0], binary=bins[0])
+        a = env.read_out().copy()
+        env.evaluate(mask=mask, block_img=imgs[1], binary=bins[1])
+        b = env.read_out().copy()
+        sel = np.ones(N, dtype=bool) if mask is None else mask.astype(bool)
+        for name in names:
+            assert np.array_equal(a[name][sel], b[name][sel]), name
+        for name in ("residual", "residual_unfrozen", "distance_to_targets"):
+            assert np.array_equal(a[name][sel], b[name][sel], equal_nan=True), name
+        assert torch.equal(imgs[0][torch.from_numpy(sel)], imgs[1][torch.from_numpy(sel)])
+        assert torch.equal(bins[0][torch.from_numpy(sel)], bins[1][torch.from_numpy(sel)])
+        assert (a["lp_pivots"] == 0).all() and ((a["solver_status"] & 48) == 0).all()     # no history, no LP
+    blocks1, n1 = env.get_state()
+    assert np.array_equal(n0, n1) and np.array_equal(blocks0, blocks1)
+    assert (b["n_blocks"] >= 2).all() and b["stable"].any() and not b["stable"].all()
+
+
 def test_masks_empty_scene_and_capacity():
     env = _gpu_env(4, [H.URDF["cube"]])
     env.reset(dict())

@@ -19,5 +19,5 @@ $CMD2 > gpurun_out/${T}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 40 -c 3 -o gpurun_out/${T}_step_tower2_E1024 -f $CMD2 > gpurun_out/${T}_ncu3.log 2>&1
 CMD3="python tools/sweep_profile.py 65536 noprof"
 $CMD3 > gpurun_out/${T}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 15 -c 1 -o gpurun_out/${T}_step_sweep_E65536 -f $CMD3 > gpurun_out/${T}_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 17 -c 1 -o gpurun_out/${T}_step_sweep_E65536 -f $CMD3 > gpurun_out/${T}_ncu4.log 2>&1
 ls -la gpurun_out/${T}_*.ncu-rep
