@@ -92,6 +92,7 @@ struct Lp {
     int MS;                   // row stride of Binv (lp_row_stride(3 * max_blocks), also the layout in HBM)
     int m, nfree, nc, lane, pivots;
     double flops;             // work estimate of the run (bw_step_out.solver_kflops): per pivot 28 nc + 2 m^2 + 16 m
+    int ndegen;               // pivots of the last run() that did not move (theta = 0): statistics
     int why;                  // why the last run() returned LP_NONE (statistics: bw_debug_lp_stats)
     double mu, nb;
     unsigned long long artmask;   // positions that hold an artificial column
@@ -276,6 +277,7 @@ struct Lp {
     __device__ int run(double r_exit, double z_inf, double &res) {
         const int maxpiv = 2 * m + 24;            // (an empty basis needs about 1.5 m pivots; warm runs 3, 30 at the most)
         why = 0;
+        ndegen = 0;
         flops = 0.0;
 #ifdef BW_PROFILE
         tp[0] = tp[1] = tp[2] = tp[3] = 0;
@@ -509,6 +511,7 @@ struct Lp {
             }
             artmask &= ~(1ull << p);
             z += theta * dq;
+            ndegen += (theta <= 1e-13) ? 1 : 0;
             pivots++;
             flops += 28.0 * nc + 2.0 * m * m + 16.0 * m;
             __syncwarp();
