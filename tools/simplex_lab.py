@@ -1,6 +1,8 @@
 """Scratch: numpy emulation of a warm-started phase-1 simplex verdict solver on harvested episodes
 (tools/harvest_episodes.py): how many pivots does a step need when the basis of the previous step is kept?
-Test infrastructure only (reads oracle-made data).
+Test infrastructure only (reads oracle-made data).  The tidy form of the algorithm, with the certificates and the
+torque-scale similarity, is oracle/simplex.py (tests/test_oracle_simplex.py); this file keeps the pivot-rule variants
+that were compared.
 
 Problem of a step: rays r_{c,+-} = a_n(c) +- mu a_t(c) of every contact point c, find lambda >= 0 with R lambda = b
 (= A f = b, f in K).  Phase 1: min sum of artificials.  Basis identity across steps: ray = (a, b, point, sign)
