@@ -379,9 +379,26 @@ struct Lp {
                 dq = __shfl_sync(FULL, best, src);
                 q = (int)(kmin & 0xffu);
             }
-            if (!(dq < -D_TOL) || blocked) {
+            const bool optimal = !(dq < -D_TOL) || blocked;
+            // (an attempt is also made as soon as the most negative reduced cost is small against the objective: what is
+            // left to gain is then rounding noise of the duals, not a direction of descent)
+            if (optimal || (z > z_inf && dq >= -CERT_REL * z)) {
+                // optimal basis: pi is a Farkas vector if it clears every ray (basic ones included: their reduced
+                // cost is zero only as far as the basis inverse is exact) and pi . b is clearly positive.  With
+                // pi . r <= eps for all rays, any lambda >= 0 with R lambda = b has pi . b <= eps sum(lambda): the
+                // certificate stands unless the contact forces add up to more than 1 / CERT_REL = 1e5 times the
+                // weight of the structure (b is normalised).  The test holds for ANY vector pi, so the updated duals
+                // are tried as they are; only when they fail it are they recomputed from the basis inverse and the
+                // rays priced again (the run then either goes on or ends with the fresh duals' verdict).
+                double dmin = dall;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+                double pb = 0.0;
+#pragma unroll 1
+                for (int i = lane; i < m; i += 32) pb += pi[i] * b[i];
+                pb = warp_sum(pb);
+                if (pb > z_inf && dmin >= -CERT_REL * pb) return LP_INFEASIBLE;
                 if (!fresh) {
-                    // optimal for the updated duals: look again with duals taken from the basis inverse itself
                     pi2 = make_double2(0.0, 0.0);
 #pragma unroll 1
                     for (unsigned long long mm = artmask; mm; mm &= mm - 1) {
@@ -395,21 +412,10 @@ struct Lp {
                     __syncwarp();
                     continue;
                 }
-                // optimal basis: pi is a Farkas vector if it clears every ray (basic ones included: their reduced
-                // cost is zero only as far as the basis inverse is exact) and pi . b is clearly positive.  With
-                // pi . r <= eps for all rays, any lambda >= 0 with R lambda = b has pi . b <= eps sum(lambda): the
-                // certificate stands unless the contact forces add up to more than 1 / CERT_REL = 1e5 times the
-                // weight of the structure (b is normalised)
-                double dmin = dall;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
-                double pb = 0.0;
-#pragma unroll 1
-                for (int i = lane; i < m; i += 32) pb += pi[i] * b[i];
-                pb = warp_sum(pb);
-                if (pb > z_inf && dmin >= -CERT_REL * pb) return LP_INFEASIBLE;
-                why = (pb > z_inf) ? 4 : 5;
-                return LP_NONE;
+                if (optimal) {
+                    why = (pb > z_inf) ? 4 : 5;
+                    return LP_NONE;
+                }
             }
             LP_ACC(0, t_a);
             LP_T0(t_b);

@@ -106,13 +106,18 @@ def run_phase1(cols, b, basis, r_exit=1e-6, z_inf=1e-5):
             key = np.where(cand, key, 0xffffffff)
             q = int(np.argmin(key))
         dq = d[q] if q >= 0 else 0.0
-        if not (dq < -D_TOL) or blocked:
+        optimal = not (dq < -D_TOL) or blocked
+        # the certificate holds for any vector pi, so it is also tried as soon as the most negative reduced cost is
+        # small against the objective (what is left to gain is then rounding noise, not a direction of descent)
+        if optimal or (z > z_inf and dq >= -CERT_REL * z):
             pb = float(pi @ b)
             dmin = float(d.min()) if len(d) else 0.0
-            basis.Binv, basis.xB = Binv, xB
             if pb > z_inf and min(dmin, 0.0) >= -CERT_REL * pb:
+                basis.Binv, basis.xB = Binv, xB
                 return INFEASIBLE, pivots, None
-            return NOT_CERTIFIED, pivots, None
+            if optimal:
+                basis.Binv, basis.xB = Binv, xB
+                return NOT_CERTIFIED, pivots, None
         w = Binv @ R[:, q]
         ok = w > PIV_TOL
         if not np.any(ok):
