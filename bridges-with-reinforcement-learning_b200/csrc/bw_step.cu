@@ -183,7 +183,8 @@ __device__ __forceinline__ void enqueue_next(const Params &P, int e, int n_block
 //   [0..1] runs (frozen, released)  [2..3] feasible  [4..5] infeasible  [6..7] not certified
 //   [8 + why] reasons of "not certified": 1 pivot cap, 2 no pivot row, 3 primal residual, 4 / 5 dual certificate, 6 setup
 //   [16] pivots, [17] largest pivot count, [20] rows of all runs, [23] pivots without progress (theta = 0),
-//   [24..27] runs of >= 30 pivots: count, pivots, pivots without progress, rows; [28..29] of them frozen / released
+//   [24..27] runs of >= 20 pivots: count, pivots, pivots without progress, rows; [28..29] of them frozen / released,
+//   [30..31] of them feasible / not
 __device__ __forceinline__ void lp_count(const Params &P, const Lp &lp, int res, int which) {
     if (P.lp_stats == nullptr || lp.lane != 0) return;
     atomicAdd(&P.lp_stats[which], 1ull);
@@ -193,12 +194,13 @@ __device__ __forceinline__ void lp_count(const Params &P, const Lp &lp, int res,
     atomicMax(&P.lp_stats[17], (unsigned long long)lp.pivots);
     atomicAdd(&P.lp_stats[20], (unsigned long long)lp.m);
     atomicAdd(&P.lp_stats[23], (unsigned long long)lp.ndegen);
-    if (lp.pivots >= 30) {      // the long runs: how many of them, their pivots, of which without progress, their rows
+    if (lp.pivots >= 20) {      // the long runs: how many of them, their pivots, of which without progress, their rows
         atomicAdd(&P.lp_stats[24], 1ull);
         atomicAdd(&P.lp_stats[25], (unsigned long long)lp.pivots);
         atomicAdd(&P.lp_stats[26], (unsigned long long)lp.ndegen);
         atomicAdd(&P.lp_stats[27], (unsigned long long)lp.m);
         atomicAdd(&P.lp_stats[28 + (which & 1)], 1ull);
+        atomicAdd(&P.lp_stats[30 + (res == LP_FEASIBLE ? 0 : 1)], 1ull);
     }
 }
 

@@ -37,7 +37,7 @@ for k in sorted(names):
 runs = max(int(st[0] + st[1]), 1)
 print("  pivots per run %.2f, rows per run %.1f, pivots without progress %.1f %%" % (st[16] / runs, st[20] / runs, 100.0 * st[23] / max(int(st[16]), 1)))
 if st[24]:
-    print("  runs of >= 30 pivots: %d (frozen %d, released %d), %.1f pivots each of which %.1f without progress, %.1f rows" % (st[24], st[28], st[29], st[25] / st[24], st[26] / st[24], st[27] / st[24]))
+    print("  runs of >= 20 pivots: %d (frozen %d, released %d; feasible %d, infeasible %d), %.1f pivots each of which %.1f without progress, %.1f rows" % (st[24], st[28], st[29], st[30], st[31], st[25] / st[24], st[26] / st[24], st[27] / st[24]))
 piv = o["lp_pivots"]
 print("lp_pivots per step: mean %.2f p50 %d p90 %d p99 %d max %d" % (piv.mean(), *np.percentile(piv, [50, 90, 99]).astype(int), piv.max()))
 big = o[piv >= 40]
