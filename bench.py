@@ -40,6 +40,7 @@ if ROOT not in sys.path:
 METRIC = "stability-checked env steps/sec"
 UNIT = "env_steps/s"
 X_GROUND = [-2.0 + 2.0 * i / 9 for i in range(10)]   # np.linspace(-2, 0, 10), successor_dqn.py:611
+CAND_BITS = True if os.environ.get("BW_BENCH_CAND_BITS", "stored") == "dense" else "stored"   # rasters of the candidate stage
 
 # the env-loop workloads of BASELINE.json
 WORKLOADS = {
@@ -322,7 +323,7 @@ def measure_workload(job, wargs, K, W, steady_seconds, with_e2e_variants=True):
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        env.enumerate_actions(X_GROUND, (0.0,), amax=amax, with_bits=True)
+        env.enumerate_actions(X_GROUND, (0.0,), amax=amax, with_bits=CAND_BITS)
         acts = env.select_random(seed=args.seed * 1000003 + step_id * 7919 + rank)[0]
         if timed:
             b.record()
@@ -494,9 +495,11 @@ def measure_workload(job, wargs, K, W, steady_seconds, with_e2e_variants=True):
                       "mean_lp_pivots_per_step": float(outs["lp_pivots"].mean()), "max_lp_pivots": int(outs["lp_pivots"].max())},
         "with_candidate_stage": {"value": world * E * K / (t_dev + t_cand), "unit": UNIT,
                                  "candidate_ms_per_step": 1e3 * t_cand / K, "amax": amax,
-                                 "note": "step + enumerate/filter kernel (candidates with bit rasters and validity "
-                                         "mask, robotoddler/utils/actions.py:7-82) + random selection: the rate a "
-                                         "rollout sees"},
+                                 "candidate_rasters": "store slots" if CAND_BITS == "stored" else "dense copies",
+                                 "note": "step + enumerate/filter kernel (candidates, validity mask and their bit "
+                                         "rasters -- kept in the handle's candidate store and handed out as slots, "
+                                         "BW_BENCH_CAND_BITS=dense: copied out as [E,amax,64] -- "
+                                         "robotoddler/utils/actions.py:7-82) + random selection: the rate a rollout sees"},
         "wall_s_timed_region": wall,
     }
     if ss is not None:

@@ -12,31 +12,23 @@
 
 namespace bw {
 
-constexpr int ENUM_THREADS = 128;
-constexpr int ENUM_CHUNK = 64;        // candidates posed per pass (shared-memory tables)
-
-// Two phases per chunk of candidates.  A: one THREAD per candidate does everything that is uniform
-// for the candidate (placement, bounds test, posed half-planes, pixel window) -- FP64 work that must
-// not be replicated over the lanes of a warp.  B: one thread per (candidate, image row inside its
-// window) evaluates the row's bit mask and the overlap with the block / obstacle rasters.
-//
-// CACHED: a candidate is (group, ground offset) or (group, target block, target face, offset) -- its pose, its
-// bounds flag and its raster depend on nothing but the block library and the pose of the target block, so they
-// survive from call to call (CandCache: one slot per possible candidate of an environment).  A block whose pose
-// or shape differs from the copy taken when its slots were filled (a reset, a new block) invalidates its slots
-// at the start of the call; ground slots live until the library or the offset tables change (host side).
-// Only the overlap with the current block / obstacle rasters is recomputed for a cached candidate.
-constexpr uint32_t SLOT_VALID = 0x80000000u, SLOT_BAD = 0x40000000u;
-
 __device__ __forceinline__ bool same_bits(double a, double b) {
     return __double_as_longlong(a) == __double_as_longlong(b);
 }
 
-template <bool CACHED>
+constexpr int ENUM_THREADS = 128;
+constexpr int ENUM_CHUNK = 64;        // candidates posed per pass (shared-memory tables)
+
+// ------------------------------------------------------------------------------------------------------------
+// Plain kernel (no candidate store: BW_CAND_CACHE_MB=0, or no device memory left for it).  Two phases per chunk of
+// candidates.  A: one THREAD per candidate does everything that is uniform for the candidate (placement, bounds
+// test, posed half-planes, pixel window) -- FP64 work that must not be replicated over the lanes of a warp.
+// B: one thread per (candidate, image row inside its window) evaluates the row's bit mask and the overlap with the
+// block / obstacle rasters.
 __global__ void __launch_bounds__(ENUM_THREADS, 8)
 enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                  int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
-                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, CandCache C,
+                 int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits,
                  const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid) {
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
@@ -61,25 +53,15 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     __shared__ uint8_t s_free_b[NB * NF], s_free_f[NB * NF];
     __shared__ uint8_t s_grp_s[BW_MAX_SHAPES * NF], s_grp_f[BW_MAX_SHAPES * NF];
     __shared__ int s_nfree, s_ngrp;
-    // A chunk is CHUNK consecutive candidates.  Only candidates that have to be posed and rasterised ("misses":
-    // all of them without the cache) need a row of the posed-face tables; a chunk ends early when it would
-    // hold more than MISS_CAP of them.
-    constexpr int CHUNK = CACHED ? 2 * ENUM_CHUNK : ENUM_CHUNK;
-    constexpr int MISS_CAP = ENUM_CHUNK;
+    constexpr int CHUNK = ENUM_CHUNK;
     constexpr int CPL = CHUNK / 32;             // candidates per lane in the row-count scan
-    __shared__ double c_nx[MISS_CAP][NF], c_nz[MISS_CAP][NF], c_cx[MISS_CAP][NF], c_cz[MISS_CAP][NF],
-        c_inx[MISS_CAP][NF];
-    __shared__ int8_t c_nf[MISS_CAP], c_jlo[MISS_CAP], c_jhi[MISS_CAP];
+    __shared__ double c_nx[CHUNK][NF], c_nz[CHUNK][NF], c_cx[CHUNK][NF], c_cz[CHUNK][NF], c_inx[CHUNK][NF];
+    __shared__ int8_t c_nf[CHUNK], c_jlo[CHUNK], c_jhi[CHUNK];
     __shared__ int8_t c_ilo[CHUNK], c_bad[CHUNK];
-    __shared__ uint8_t c_mi[CHUNK];             // row of the posed-face tables (misses)
     __shared__ int c_rowstart[CHUNK + 1];
     __shared__ int c_overlap[CHUNK];
-    __shared__ int c_slot[CHUNK];               // cache slot of the candidate (-1: none)
-    __shared__ uint8_t c_cached[CHUNK];         // its slot was valid: raster rows are read, not computed
-    __shared__ int s_wmiss[ENUM_THREADS / 32], s_ncut;
     constexpr int OWNER_CAP = 2048;             // (candidate, row) pairs of a chunk with a direct owner entry
     __shared__ uint8_t c_owner[OWNER_CAP];      // pair -> candidate of the chunk
-    __shared__ unsigned s_inval;
 
     const int n = P.n_blocks[e];
     if (tid < n) {
@@ -127,35 +109,6 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         s_ngrp = g;
     }
     __syncthreads();
-    if (CACHED) {
-        // blocks that are not the ones their slots were filled for: drop those slots, remember the new block
-        if (tid == 0) s_inval = 0;
-        __syncthreads();
-        if (tid < n) {
-            const Pose cp = C.pose[(size_t)e * NB + tid];
-            const Pose p = s_pose[tid];
-            const bool same = same_bits(cp.x, p.x) && same_bits(cp.z, p.z) && same_bits(cp.c, p.c) &&
-                              same_bits(cp.s, p.s) && C.shape[(size_t)e * NB + tid] == s_shape[tid];
-            if (!same) {
-                C.pose[(size_t)e * NB + tid] = p;
-                C.shape[(size_t)e * NB + tid] = s_shape[tid];
-                atomicOr(&s_inval, 1u << tid);
-            }
-        }
-        __syncthreads();
-        unsigned inv = s_inval;
-        const int per_block = NF * n_offsets;
-        while (inv) {
-            const int b = __ffs(inv) - 1;
-            inv &= inv - 1;
-            for (int q = tid; q < s_ngrp * per_block; q += ENUM_THREADS) {
-                const int g = q / per_block, r = q - g * per_block;
-                C.meta[(size_t)e * C.slots + g * C.spg + n_ground + b * per_block + r] = 0;
-            }
-        }
-        __syncthreads();
-    }
-    const bool env_full = n >= P.max_blocks;     // no placement possible: nothing is cached, nothing is valid
     const int per_group = n_ground + s_nfree * n_offsets;
     const int total = s_ngrp * per_group;
     const int count = min(total, amax);
@@ -169,100 +122,57 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
 
     // only the first `count` slots are meaningful (n_cand); the rest of the caller's buffers is left alone
-    const int lane = tid & 31, warp = tid >> 5;
     int base = 0, nval = 0;
     while (base < count) {
-        const int nch = min(CHUNK, count - base);
-        // ---- phase A0: thread per candidate -- the action, its cache slot, hit or miss
-        const bool active = tid < nch;
-        bw_action act;
-        act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
-        act.shape = 0; act.face = 0; act.offset_x = 0.0;
-        int slot = -1, rows = 0, ilo = 0;
-        bool bad = false, hit = false;
-        if (tid == 0) s_ncut = nch;
-        if (active) {
+        const int nchunk = min(CHUNK, count - base);
+        // ---- phase A: thread per candidate -- the action, its pose (FP64 work that is uniform for a candidate)
+        if (tid < nchunk) {
             const int a = base + tid;
             const int g = a / per_group, w = a - g * per_group;
+            bw_action act;
+            act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
             act.shape = s_grp_s[g];
             act.face = s_grp_f[g];
             if (w < n_ground) {
                 act.offset_x = ground[w];
-                slot = g * C.spg + w;
             } else {
                 const int k = (w - n_ground) / n_offsets, oi = (w - n_ground) - k * n_offsets;
                 act.target_block = s_free_b[k];
                 act.target_face = s_free_f[k];
                 act.offset_x = offsets[oi];
-                slot = g * C.spg + n_ground + (act.target_block * NF + act.target_face) * n_offsets + oi;
             }
             cand[(size_t)e * amax + a] = act;
-            if (!CACHED || env_full) slot = -1;
-            if (CACHED && slot >= 0) {
-                const uint32_t m = C.meta[(size_t)e * C.slots + slot];
-                if (m & SLOT_VALID) {
-                    hit = true;
-                    bad = (m & SLOT_BAD) != 0;
-                    rows = (int)(m & 0xffu);
-                    ilo = (int)((m >> 8) & 0xffu);
+            int rows = 0, ilo = 0;
+            Pose ps;
+            const int err = place_block(P, s_pose, s_shape, n, act, ps);
+            bool bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
+            if (!bad) {
+                const ShapeDev &sh = P.shapes[act.shape];
+                // collision_on_action: any vertex outside the window (gym_env.py:304-323)
+                for (int v = 0; v < sh.n_verts; v++) {
+                    double vx, vz;
+                    rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+                    vx = dadd(vx, ps.x);
+                    vz = dadd(vz, ps.z);
+                    if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
                 }
-            }
-        }
-        // misses take the rows of the posed-face tables in candidate order; the chunk is cut in front of the
-        // candidate that would need row MISS_CAP (it starts the next chunk)
-        const bool miss = active && !hit;
-        const unsigned mb = __ballot_sync(0xffffffffu, miss);
-        if (lane == 0) s_wmiss[warp] = __popc(mb);
-        __syncthreads();
-        int before = __popc(mb & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; w++) before += s_wmiss[w];
-        const bool included = active && (before + (miss ? 1 : 0) <= MISS_CAP);
-        if (active && !included) atomicMin(&s_ncut, tid);
-        // ---- phase A1: the misses are posed (FP64 work that is uniform for a candidate: one thread each)
-        if (included) {
-            if (miss) {
-                const int mi = before;
-                Pose ps;
-                const int err = place_block(P, s_pose, s_shape, n, act, ps);
-                bad = (err != 0);     // a full environment (err 2) offers no placement: listed but invalid
-                if (!bad) {
-                    const ShapeDev &sh = P.shapes[act.shape];
-                    // collision_on_action: any vertex outside the window (gym_env.py:304-323)
-                    for (int v = 0; v < sh.n_verts; v++) {
-                        double vx, vz;
-                        rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
-                        vx = dadd(vx, ps.x);
-                        vz = dadd(vz, ps.z);
-                        if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
-                    }
-                    PosedShape o;
-                    pose_shape(P, sh, ps, o);
-                    for (int k = 0; k < NF; k++) {
-                        c_nx[mi][k] = o.nx[k]; c_nz[mi][k] = o.nz[k]; c_cx[mi][k] = o.cx[k]; c_cz[mi][k] = o.cz[k];
-                        c_inx[mi][k] = o.inv_nx[k];
-                    }
-                    c_nf[mi] = (int8_t)o.n_faces;
-                    c_jlo[mi] = (int8_t)o.j_lo; c_jhi[mi] = (int8_t)o.j_hi;
-                    ilo = o.i_lo;
-                    if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
+                PosedShape o;
+                pose_shape(P, sh, ps, o);
+                for (int k = 0; k < NF; k++) {
+                    c_nx[tid][k] = o.nx[k]; c_nz[tid][k] = o.nz[k]; c_cx[tid][k] = o.cx[k]; c_cz[tid][k] = o.cz[k];
+                    c_inx[tid][k] = o.inv_nx[k];
                 }
-                if (CACHED && slot >= 0) {
-                    if (err == 0)
-                        C.meta[(size_t)e * C.slots + slot] = SLOT_VALID | (bad ? SLOT_BAD : 0u) | ((uint32_t)ilo << 8) | (uint32_t)rows;
-                    else
-                        slot = -1;
-                }
-                c_mi[tid] = (uint8_t)mi;
+                c_nf[tid] = (int8_t)o.n_faces;
+                c_jlo[tid] = (int8_t)o.j_lo; c_jhi[tid] = (int8_t)o.j_hi;
+                ilo = o.i_lo;
+                if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
             }
             c_ilo[tid] = (int8_t)ilo;
-            c_slot[tid] = slot;
-            c_cached[tid] = hit ? 1 : 0;
             c_bad[tid] = bad ? 1 : 0;
             c_overlap[tid] = 0;
             c_rowstart[tid + 1] = rows;
         }
         __syncthreads();
-        const int nchunk = s_ncut;                  // candidates base .. base + nchunk - 1 are finished in this trip
         if (action_bits != nullptr) {   // rows outside the windows are zero
             uint64_t *dst = action_bits + ((size_t)e * amax + base) * IMG;
             for (int q = tid; q < nchunk * IMG; q += ENUM_THREADS) dst[q] = 0;
@@ -296,49 +206,22 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
         __syncthreads();
         // ---- phase B: thread per (candidate, row of its window)
         const int npairs = c_rowstart[nchunk];
-        // two pairs per trip: the loads of cached rows (global memory, possibly HBM) of both are in flight
-        // before either is used
-        for (int q0 = tid; q0 < npairs; q0 += 2 * ENUM_THREADS) {
-            int tt[2], rr[2];
-            uint64_t bb[2];
-            bool live[2], hitv[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int q = q0 + u * ENUM_THREADS;
-                live[u] = q < npairs;
-                hitv[u] = false;
-                tt[u] = 0; rr[u] = 0; bb[u] = 0;
-                if (live[u]) {
-                    int lo = 0;                             // largest t with rowstart[t] <= q
-                    if (q < OWNER_CAP) {
-                        lo = c_owner[q];
-                    } else {
-                        int hi = nchunk - 1;
-                        while (lo < hi) {
-                            const int mid = (lo + hi + 1) >> 1;
-                            if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
-                        }
-                    }
-                    tt[u] = lo;
-                    rr[u] = c_ilo[lo] + (q - c_rowstart[lo]);
-                    hitv[u] = CACHED && c_cached[lo];
-                    if (hitv[u]) bb[u] = __ldcs(&C.bits[((size_t)e * C.slots + c_slot[lo]) * IMG + rr[u]]);
+        for (int q = tid; q < npairs; q += ENUM_THREADS) {
+            int lo = 0;                             // largest t with rowstart[t] <= q
+            if (q < OWNER_CAP) {
+                lo = c_owner[q];
+            } else {
+                int hi = nchunk - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (c_rowstart[mid] <= q) lo = mid; else hi = mid - 1;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                if (!live[u]) continue;
-                const int t = tt[u], row = rr[u];
-                uint64_t bits = bb[u];
-                if (!hitv[u]) {
-                    const int mi = c_mi[t];
-                    bits = raster_row_posed_mixed(P, c_nf[mi], c_nx[mi], c_nz[mi], c_cx[mi], c_cz[mi], c_inx[mi],
-                                                  c_jlo[mi], c_jhi[mi], row);
-                    if (CACHED && c_slot[t] >= 0) C.bits[((size_t)e * C.slots + c_slot[t]) * IMG + row] = bits;
-                }
-                if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
-                if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
-            }
+            const int t = lo, row = c_ilo[lo] + (q - c_rowstart[lo]);
+            const uint64_t bits = raster_row_posed_mixed(P, c_nf[t], c_nx[t], c_nz[t], c_cx[t], c_cz[t], c_inx[t],
+                                                         c_jlo[t], c_jhi[t], row);
+            if (bits & (s_block[row] | s_obst[row])) atomicOr(&c_overlap[t], 1);
+            if (action_bits != nullptr && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
         }
         __syncthreads();
         const bool keep = tid < nchunk && !c_bad[tid] && !c_overlap[tid];
@@ -349,15 +232,470 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
     if (n_valid != nullptr && tid == 0) n_valid[e] = nval;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Kernel with the candidate store (CandCache, bw_kernels.cuh).  A candidate is (group, ground offset) or (group,
+// target block, target face, offset): its pose, its bounds flag and its raster depend on nothing but the block
+// library and the pose of the target block, so they survive from call to call in the slot of that candidate.  A
+// block whose pose or shape differs from the copy taken when its slots were filled (a reset, a new block)
+// invalidates its slots at the start of the call; ground slots live until the library or the offset tables change
+// (host side).  What changes from call to call is the overlap with the block / obstacle rasters -- and within an
+// episode those only grow: the store keeps the rasters the last call saw (seen_block, seen_obst) and every slot
+// the overlap verdict of that call (SLOT_OVL) with the call's stamp.  A candidate that was listed by the previous
+// call is therefore tested against the NEW pixels only (a handful of rows, or none at all once it overlaps);
+// a raster that lost pixels or whose obstacles changed (a reset) makes the call a fresh one: every listed
+// candidate is tested against the whole raster again.
+//
+// One CTA per environment.  Per chunk of CCH candidates:
+//   A0  thread per candidate: the action, its slot, hit / miss, the rows that need a test -> two dense lists
+//   Bh  hits with rows to test: 8 lanes per candidate, rows read back from the store
+//   A1  misses, DENSE (thread m poses the m-th miss; FP64 work that is uniform for a candidate), MISS_CAP per round
+//   Bm  thread per (miss, row of its window): the row's bit mask (exact half-plane walks), stored and tested
+//   C   thread per candidate: validity flag, slot word with the new verdict and stamp
+// COPY: the caller wants the rasters copied out ([E,amax,64]); every listed candidate is then read and tested in
+// full.  Without it the caller gets d_slot (where the raster lives) and gathers what it needs.
+constexpr int CCH = 256;
+constexpr int CPT = CCH / ENUM_THREADS;
+constexpr int MISS_CAP = 64;
+constexpr uint32_t W_INCR = 0x80000000u;          // working word only: the stored verdict holds, test new pixels only
+
+__device__ __forceinline__ int list_append(bool pred, int *counter, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    int start = 0;
+    if (lane == 0 && m) start = atomicAdd(counter, __popc(m));
+    start = __shfl_sync(0xffffffffu, start, 0);
+    return start + __popc(m & ((1u << lane) - 1u));
+}
+
+template <bool COPY>
+__global__ void __launch_bounds__(ENUM_THREADS, 8)
+enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
+                       int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
+                       int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, int32_t *__restrict__ slot_out,
+                       CandCache C, const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid) {
+    const int e = blockIdx.x;
+    if (mask != nullptr && mask[e] == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
+    __shared__ double s_grid[2 * IMG];
+    Params P = PG;
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(s_lib);
+        const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
+        for (int q = tid; q < words; q += ENUM_THREADS) dst[q] = src[q];
+        if (tid < IMG) { s_grid[tid] = PG.xs[tid]; s_grid[IMG + tid] = PG.ys[tid]; }
+        P.shapes = reinterpret_cast<const ShapeDev *>(s_lib);
+        P.xs = s_grid;
+        P.ys = s_grid + IMG;
+    }
+    __shared__ Pose s_pose[NB];
+    __shared__ uint8_t s_shape[NB];
+    __shared__ uint64_t s_full[IMG], s_delta[IMG];      // blocks | obstacles; the pixels the last call had not seen
+    __shared__ uint8_t s_free_b[NB * NF], s_free_f[NB * NF];
+    __shared__ uint8_t s_grp_s[BW_MAX_SHAPES * NF], s_grp_f[BW_MAX_SHAPES * NF];
+    __shared__ int s_nfree, s_ngrp;
+    __shared__ unsigned s_inval, s_dmask[2], s_prev;
+    // posed-face tables of the misses of one round
+    __shared__ double t_nx[MISS_CAP][NF], t_nz[MISS_CAP][NF], t_cx[MISS_CAP][NF], t_cz[MISS_CAP][NF], t_inx[MISS_CAP][NF];
+    __shared__ int8_t t_nf[MISS_CAP], t_jlo[MISS_CAP], t_jhi[MISS_CAP], t_ilo[MISS_CAP];
+    __shared__ int m_rowstart[MISS_CAP + 1];
+    constexpr int OWNER_CAP = 512;                      // (miss, row) pairs of a round with a direct owner entry
+    __shared__ uint8_t m_owner[OWNER_CAP];
+    // per candidate of the chunk
+    __shared__ uint32_t c_w[CCH];                       // SLOT_BAD | SLOT_OVL | window (slot word layout) | W_INCR
+    __shared__ int c_slot[CCH];
+    __shared__ uint8_t c_wlo[CCH], c_wn[CCH];           // rows a hit has to test
+    __shared__ uint16_t s_miss[CCH], s_work[CCH];
+    __shared__ int s_nmiss, s_nwork, s_nval;
+
+    const int n = P.n_blocks[e];
+    if (tid < n) {
+        s_pose[tid] = P.pose[(size_t)e * NB + tid];
+        s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
+    }
+    uint64_t regress = 0;
+    if (tid < IMG) {
+        const size_t i = (size_t)e * IMG + tid;
+        const uint64_t b = P.block_bits[i], o = P.obst_bits[i];
+        const uint64_t sb = C.seen_block[i], so = C.seen_obst[i];
+        regress = (sb & ~b) | (so ^ o);
+        s_full[tid] = b | o;
+        s_delta[tid] = b & ~sb;
+        C.seen_block[i] = b;
+        C.seen_obst[i] = o;
+    }
+    if (tid == 0) {
+        // stamp of this call (16 bits in every slot word it touches): 1 .. 0xffff, then the slots are wiped
+        s_prev = C.call[e];
+        s_nmiss = 0; s_nwork = 0; s_nval = 0; s_inval = 0;
+    }
+    const bool fresh = __syncthreads_or(regress != 0) != 0;
+    if (tid < IMG) {
+        if (fresh) s_delta[tid] = s_full[tid];
+        const unsigned nz = __ballot_sync(0xffffffffu, s_delta[tid] != 0);
+        if (lane == 0) s_dmask[tid >> 5] = nz;
+    }
+    unsigned prev = s_prev;
+    const bool wipe = prev >= 0xffffu;
+    const unsigned cur = wipe ? 1u : prev + 1u;
+    if (wipe) prev = 0xffffffffu;                       // matches no stamp
+    if (tid == 0) C.call[e] = cur;
+    if (tid < 32) {
+        // receiving faces of placed blocks: all faces (assembly_env.py:153), occupied ones skipped
+        // (max_blocks_per_face = 1, actions.py:42-44).  Lane = block: count, exclusive scan, then every lane
+        // lists the free faces of its block -- same (block, face) order as the reference's nested loops.
+        int nf = 0;
+        unsigned freem = 0;
+        if (tid < n) {
+            nf = P.shapes[s_shape[tid]].n_faces;
+            freem = ~(unsigned)P.face_occ[(size_t)e * NB + tid] & ((1u << nf) - 1u);
+        }
+        const int cnt = __popc(freem);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += v;
+        }
+        int k = inc - cnt;
+        while (freem) {
+            const int f = __ffs(freem) - 1;
+            freem &= freem - 1;
+            s_free_b[k] = (uint8_t)tid;
+            s_free_f[k] = (uint8_t)f;
+            k++;
+        }
+        if (tid == 31) s_nfree = inc;
+    } else if (tid == 32) {
+        int g = 0;
+        for (int s = 0; s < P.n_shapes; s++) {
+            const ShapeDev &sh = P.shapes[s];
+            for (int f = 0; f < sh.n_faces; f++)
+                if ((sh.target_faces_mask >> f) & 1u) { s_grp_s[g] = (uint8_t)s; s_grp_f[g] = (uint8_t)f; g++; }
+        }
+        s_ngrp = g;
+    }
+    // blocks that are not the ones their slots were filled for: drop those slots, remember the new block
+    if (tid < n) {
+        const Pose cp = C.pose[(size_t)e * NB + tid];
+        const Pose p = s_pose[tid];
+        const bool same = same_bits(cp.x, p.x) && same_bits(cp.z, p.z) && same_bits(cp.c, p.c) &&
+                          same_bits(cp.s, p.s) && C.shape[(size_t)e * NB + tid] == s_shape[tid];
+        if (!same) {
+            C.pose[(size_t)e * NB + tid] = p;
+            C.shape[(size_t)e * NB + tid] = s_shape[tid];
+            atomicOr(&s_inval, 1u << tid);
+        }
+    }
+    __syncthreads();
+    uint32_t *meta = C.meta + (size_t)e * C.slots;
+    const uint64_t *store = C.bits + (size_t)e * C.slots * IMG;
+    if (wipe) {
+        for (int q = tid; q < C.slots; q += ENUM_THREADS) meta[q] = 0;
+    } else {
+        unsigned inv = s_inval;
+        const int per_block = NF * n_offsets;
+        while (inv) {
+            const int b = __ffs(inv) - 1;
+            inv &= inv - 1;
+            for (int q = tid; q < s_ngrp * per_block; q += ENUM_THREADS) {
+                const int g = q / per_block, r = q - g * per_block;
+                meta[g * C.spg + n_ground + b * per_block + r] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t dmask = (uint64_t)s_dmask[0] | ((uint64_t)s_dmask[1] << 32);     // rows with new pixels
+    const bool env_full = n >= P.max_blocks;     // no placement possible: nothing is valid
+    const int per_group = n_ground + s_nfree * n_offsets;
+    const int total = s_ngrp * per_group;
+    const int count = min(total, amax);
+    if (tid == 0) {
+        n_cand[e] = count;
+        // generate_actions (actions.py:7-52) is unbounded: a list cut to the caller's capacity is reported
+        // (bw_candidate_overflow), never dropped silently
+        if (total > amax) atomicMax(P.cand_need, total);
+    }
+    // candidate a of the list: the action and the slot of its placement
+    auto make_action = [&](int a, int &slot) {
+        bw_action act;
+        act.target_block = -1; act.target_face = 0; act.frozen = 0; act.reserved0 = 0; act.offset_y = 0.0;
+        const int g = a / per_group, w = a - g * per_group;
+        act.shape = s_grp_s[g];
+        act.face = s_grp_f[g];
+        if (w < n_ground) {
+            act.offset_x = ground[w];
+            slot = g * C.spg + w;
+        } else {
+            const int k = (w - n_ground) / n_offsets, oi = (w - n_ground) - k * n_offsets;
+            act.target_block = s_free_b[k];
+            act.target_face = s_free_f[k];
+            act.offset_x = offsets[oi];
+            slot = g * C.spg + n_ground + (act.target_block * NF + act.target_face) * n_offsets + oi;
+        }
+        return act;
+    };
+    if (env_full) {
+        for (int a = tid; a < count; a += ENUM_THREADS) {
+            int slot;
+            cand[(size_t)e * amax + a] = make_action(a, slot);
+            valid[(size_t)e * amax + a] = 0;
+            if (slot_out != nullptr) slot_out[(size_t)e * amax + a] = -1;
+        }
+        if (COPY) {
+            uint64_t *dst = action_bits + (size_t)e * amax * IMG;
+            for (int q = tid; q < count * IMG; q += ENUM_THREADS) dst[q] = 0;
+        }
+        if (n_valid != nullptr && tid == 0) n_valid[e] = 0;
+        return;
+    }
+    const double eps = 1e-6;
+    const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
+
+    // only the first `count` entries of the caller's buffers are meaningful (n_cand); the rest is left alone
+    int myval = 0;
+    for (int base = 0; base < count; base += CCH) {
+        const int nch = min(CCH, count - base);
+        // ---- A0
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const int t = tid + j * ENUM_THREADS;
+            bool is_miss = false, has_work = false;
+            if (t < nch) {
+                const int a = base + t;
+                int slot;
+                cand[(size_t)e * amax + a] = make_action(a, slot);
+                const uint32_t m = meta[slot];
+                uint32_t w = 0;
+                int wlo = 0, wn = 0;
+                if (m & SLOT_VALID) {
+                    const int rows = slot_rows(m), ilo = slot_ilo(m);
+                    const bool incr = !COPY && !fresh && ((m >> SLOT_STAMP_SHIFT) & SLOT_STAMP_MASK) == prev;
+                    w = m & SLOT_GEOM;
+                    if (incr) w |= (m & SLOT_OVL) | W_INCR;
+                    if (COPY) {
+                        wlo = ilo; wn = rows;
+                    } else if (!(w & (SLOT_BAD | SLOT_OVL)) && rows > 0) {
+                        if (incr) {
+                            const uint64_t win = (rows >= 64) ? ~0ull : (((1ull << rows) - 1ull) << ilo);
+                            const uint64_t sub = dmask & win;
+                            if (sub) {
+                                wlo = __ffsll((long long)sub) - 1;
+                                wn = (63 - __clzll((long long)sub)) - wlo + 1;
+                            }
+                        } else {
+                            wlo = ilo; wn = rows;
+                        }
+                    }
+                    has_work = wn > 0;
+                } else {
+                    is_miss = true;
+                }
+                c_w[t] = w;
+                c_slot[t] = slot;
+                c_wlo[t] = (uint8_t)wlo;
+                c_wn[t] = (uint8_t)wn;
+            }
+            const int im = list_append(is_miss, &s_nmiss, lane);
+            if (is_miss) s_miss[im] = (uint16_t)t;
+            const int iw = list_append(has_work, &s_nwork, lane);
+            if (has_work) s_work[iw] = (uint16_t)t;
+        }
+        if (COPY) {   // rows outside the windows are zero
+            uint64_t *dst = action_bits + ((size_t)e * amax + base) * IMG;
+            for (int q = tid; q < nch * IMG; q += ENUM_THREADS) dst[q] = 0;
+        }
+        __syncthreads();
+        const int nmiss = s_nmiss, nwork = s_nwork;
+        // ---- Bh: 8 lanes per hit, two rows of a lane in flight
+        for (int q = tid; q < nwork * 8; q += ENUM_THREADS) {
+            const int t = s_work[q >> 3], r = q & 7;
+            const int wlo = c_wlo[t], wend = wlo + c_wn[t];
+            const uint64_t *tst = (c_w[t] & W_INCR) ? s_delta : s_full;
+            const uint64_t *src = store + (size_t)c_slot[t] * IMG;
+            uint64_t *dst = COPY ? action_bits + ((size_t)e * amax + base + t) * IMG : nullptr;
+            bool ovl = false;
+            for (int row = wlo + r; row < wend; row += 16) {
+                const int row2 = row + 8;
+                const bool two = row2 < wend;
+                const uint64_t b0 = __ldcs(src + row);
+                const uint64_t b1 = two ? __ldcs(src + row2) : 0ull;
+                if (b0 & tst[row]) ovl = true;
+                if (two && (b1 & tst[row2])) ovl = true;
+                if (COPY) {
+                    if (b0) dst[row] = b0;
+                    if (b1) dst[row2] = b1;
+                }
+            }
+            if (ovl) atomicOr(&c_w[t], SLOT_OVL);
+        }
+        // ---- misses, MISS_CAP per round
+        int r0 = 0;
+        do {
+            const int nm = max(0, min(MISS_CAP, nmiss - r0));
+            if (tid < nm) {   // A1
+                const int t = s_miss[r0 + tid];
+                int slot;
+                const bw_action act = make_action(base + t, slot);
+                Pose ps;
+                const int err = place_block(P, s_pose, s_shape, n, act, ps);
+                bool bad = (err != 0);
+                int rows = 0, ilo = 0;
+                if (!bad) {
+                    const ShapeDev &sh = P.shapes[act.shape];
+                    // collision_on_action: any vertex outside the window (gym_env.py:304-323)
+                    for (int v = 0; v < sh.n_verts; v++) {
+                        double vx, vz;
+                        rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
+                        vx = dadd(vx, ps.x);
+                        vz = dadd(vz, ps.z);
+                        if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
+                    }
+                    PosedShape o;
+                    pose_shape(P, sh, ps, o);
+                    for (int k = 0; k < NF; k++) {
+                        t_nx[tid][k] = o.nx[k]; t_nz[tid][k] = o.nz[k]; t_cx[tid][k] = o.cx[k]; t_cz[tid][k] = o.cz[k];
+                        t_inx[tid][k] = o.inv_nx[k];
+                    }
+                    t_nf[tid] = (int8_t)o.n_faces;
+                    t_jlo[tid] = (int8_t)o.j_lo; t_jhi[tid] = (int8_t)o.j_hi;
+                    ilo = o.i_lo;
+                    if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
+                } else {
+                    c_slot[t] = -1;          // a placement that failed is not kept
+                }
+                t_ilo[tid] = (int8_t)ilo;
+                m_rowstart[tid + 1] = rows;
+                c_w[t] = (bad ? SLOT_BAD : 0u) | ((uint32_t)ilo << 7) | (uint32_t)rows;
+            }
+            __syncthreads();
+            if (tid == 0) { s_nmiss = 0; s_nwork = 0; }      // every thread has its copy; next use after two barriers
+            if (nm > 0) {
+                if (tid < 32) {
+                    // inclusive scan of the row counts (two misses per lane), m_rowstart[m + 1] = rows of 0..m
+                    constexpr int CPL = MISS_CAP / 32;
+                    int av[CPL], sum = 0;
+#pragma unroll
+                    for (int j = 0; j < CPL; j++) {
+                        const int idx = CPL * tid + j;
+                        av[j] = (idx < nm) ? m_rowstart[idx + 1] : 0;
+                        sum += av[j];
+                    }
+                    int inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (tid >= o) inc += v;
+                    }
+                    int run = inc - sum;
+#pragma unroll
+                    for (int j = 0; j < CPL; j++) {
+                        const int idx = CPL * tid + j;
+                        for (int r = run; r < run + av[j] && r < OWNER_CAP; r++) m_owner[r] = (uint8_t)idx;
+                        run += av[j];
+                        if (idx < nm) m_rowstart[idx + 1] = run;
+                    }
+                    if (tid == 0) m_rowstart[0] = 0;
+                }
+                __syncthreads();
+                // ---- Bm
+                const int npairs = m_rowstart[nm];
+                for (int q = tid; q < npairs; q += ENUM_THREADS) {
+                    int mi = 0;                             // largest m with rowstart[m] <= q
+                    if (q < OWNER_CAP) {
+                        mi = m_owner[q];
+                    } else {
+                        int hi = nm - 1;
+                        while (mi < hi) {
+                            const int mid = (mi + hi + 1) >> 1;
+                            if (m_rowstart[mid] <= q) mi = mid; else hi = mid - 1;
+                        }
+                    }
+                    const int row = t_ilo[mi] + (q - m_rowstart[mi]);
+                    const int t = s_miss[r0 + mi];
+                    const uint64_t bits = raster_row_posed_mixed(P, t_nf[mi], t_nx[mi], t_nz[mi], t_cx[mi], t_cz[mi],
+                                                                 t_inx[mi], t_jlo[mi], t_jhi[mi], row);
+                    const int slot = c_slot[t];
+                    if (slot >= 0) C.bits[((size_t)e * C.slots + slot) * IMG + row] = bits;
+                    if (bits & s_full[row]) atomicOr(&c_w[t], SLOT_OVL);
+                    if (COPY && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
+                }
+            }
+            r0 += MISS_CAP;
+            if (r0 < nmiss) __syncthreads();                 // the tables are written again
+        } while (r0 < nmiss);
+        __syncthreads();
+        // ---- C
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const int t = tid + j * ENUM_THREADS;
+            if (t < nch) {
+                const uint32_t w = c_w[t];
+                const int slot = c_slot[t];
+                const bool keep = !(w & (SLOT_BAD | SLOT_OVL));
+                valid[(size_t)e * amax + base + t] = keep ? 1 : 0;
+                myval += keep ? 1 : 0;
+                if (slot_out != nullptr) slot_out[(size_t)e * amax + base + t] = slot;
+                if (slot >= 0) meta[slot] = SLOT_VALID | (w & (SLOT_GEOM | SLOT_OVL)) | (cur << SLOT_STAMP_SHIFT);
+            }
+        }
+    }
+    if (n_valid != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) myval += __shfl_xor_sync(0xffffffffu, myval, o);
+        if (lane == 0 && myval) atomicAdd(&s_nval, myval);
+        __syncthreads();
+        if (tid == 0) n_valid[e] = s_nval;
+    }
+}
+
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask, int32_t *d_n_valid) {
-    if (cache.meta != nullptr && cache.slots > 0)
-        enumerate_kernel<true><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                                 d_valid, d_n_cand, d_action_bits, cache, d_mask, d_n_valid);
-    else
-        enumerate_kernel<false><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
-                                                                  d_valid, d_n_cand, d_action_bits, cache, d_mask, d_n_valid);
+                      int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask,
+                      int32_t *d_n_valid) {
+    if (cache.meta != nullptr && cache.slots > 0) {
+        if (d_action_bits != nullptr)
+            enumerate_store_kernel<true><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax,
+                                                                           d_cand, d_valid, d_n_cand, d_action_bits, d_slot,
+                                                                           cache, d_mask, d_n_valid);
+        else
+            enumerate_store_kernel<false><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax,
+                                                                            d_cand, d_valid, d_n_cand, nullptr, d_slot,
+                                                                            cache, d_mask, d_n_valid);
+    } else {
+        enumerate_kernel<<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
+                                                           d_valid, d_n_cand, d_action_bits, d_mask, d_n_valid);
+    }
+}
+
+// rasters of chosen candidates out of the store (or out of a dense [E,amax,64] copy): thread per (item, row)
+__global__ void gather_bits_kernel(CandCache C, const int32_t *__restrict__ slot, const uint64_t *__restrict__ dense,
+                                   int amax, int E, const int32_t *__restrict__ env, const int32_t *__restrict__ index,
+                                   int64_t n, uint64_t *__restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * IMG) return;
+    const int64_t i = q / IMG;
+    const int row = (int)(q - i * IMG);
+    const int e = env ? env[i] : (int)i;
+    const int a = index[i];
+    uint64_t bits = 0;
+    if (e >= 0 && e < E && a >= 0 && a < amax) {
+        if (dense != nullptr) {
+            bits = dense[((size_t)e * amax + a) * IMG + row];
+        } else {
+            const int s = slot[(size_t)e * amax + a];
+            if (s >= 0 && s < C.slots) bits = cand_store_row(C, e, s, row);
+        }
+    }
+    out[q] = bits;
+}
+
+void launch_gather_bits(const CandCache &cache, const int32_t *d_slot, const uint64_t *d_dense, int amax, int E,
+                        const int32_t *d_env, const int32_t *d_index, int64_t n, uint64_t *d_out, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int64_t threads = n * IMG;
+    gather_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(cache, d_slot, d_dense, amax, E, d_env, d_index,
+                                                                              n, d_out);
 }
 
 // create_block + collision_on_action for one hypothetical action per env (state untouched)

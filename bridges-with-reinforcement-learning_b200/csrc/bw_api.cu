@@ -196,7 +196,7 @@ static void default_marker(ShapeDev &d) {
 // switches the cache off (plain kernel).
 static void release_cand_cache(bw_handle *h) {
     CandCache &c = h->cand;
-    void *old[4] = {c.meta, c.bits, c.pose, c.shape};
+    void *old[7] = {c.meta, c.bits, c.pose, c.shape, c.seen_block, c.seen_obst, c.call};
     for (void *q : old) {
         if (!q) continue;
         cudaFree(q);
@@ -210,7 +210,8 @@ static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
     const int spg = n_ground + h->P.max_blocks * NF * n_offsets;
     const int slots = h->n_groups * spg;
     const size_t E = (size_t)h->P.E;
-    const size_t need = E * (size_t)slots * (IMG * sizeof(uint64_t) + sizeof(uint32_t)) + E * NB * (sizeof(Pose) + 1);
+    const size_t need = E * (size_t)slots * (IMG * sizeof(uint64_t) + sizeof(uint32_t)) + E * NB * (sizeof(Pose) + 1) +
+                        E * (2 * IMG * sizeof(uint64_t) + sizeof(uint32_t));
     CandCache &c = h->cand;
     if (slots <= 0 || need > h->cand_budget) {
         if (c.meta) {
@@ -228,6 +229,9 @@ static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
         if (e == cudaSuccess) e = dev_alloc(h, &c.bits, E * slots * IMG, false);
         if (e == cudaSuccess) e = dev_alloc(h, &c.pose, E * NB, false);
         if (e == cudaSuccess) e = dev_alloc(h, &c.shape, E * NB, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.seen_block, E * IMG, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.seen_obst, E * IMG, false);
+        if (e == cudaSuccess) e = dev_alloc(h, &c.call, E, false);
         if (e != cudaSuccess) {
             // no room for it next to the caller's own allocations: enumerate without the cache from now on
             cudaGetLastError();
@@ -243,6 +247,9 @@ static int prepare_cand_cache(bw_handle *h, int n_ground, int n_offsets) {
         CU(cudaMemsetAsync(c.meta, 0, sizeof(uint32_t) * E * slots, h->stream));
         CU(cudaMemsetAsync(c.pose, 0xff, sizeof(Pose) * E * NB, h->stream));      // no block has this pose
         CU(cudaMemsetAsync(c.shape, 0xff, E * NB, h->stream));
+        CU(cudaMemsetAsync(c.seen_block, 0, sizeof(uint64_t) * E * IMG, h->stream));
+        CU(cudaMemsetAsync(c.seen_obst, 0, sizeof(uint64_t) * E * IMG, h->stream));
+        CU(cudaMemsetAsync(c.call, 0, sizeof(uint32_t) * E, h->stream));
         h->cand_dirty = false;
     }
     return BW_OK;
@@ -783,9 +790,9 @@ int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_
     return BW_OK;
 }
 
-int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
-                         int32_t n_offsets, int32_t amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand,
-                         uint64_t *d_action_bits) {
+static int enumerate_common(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
+                            int32_t n_offsets, int32_t amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand,
+                            uint64_t *d_action_bits, int32_t *d_slot) {
     if (!h || !d_cand || !d_valid || !d_n_cand || amax <= 0) return BW_ERR_INVALID;
     if (int rc = need_shapes(h)) return rc;
     if (n_ground < 0 || n_ground > 256 || n_offsets < 0 || n_offsets > 256)
@@ -794,9 +801,39 @@ int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n
     CU(cudaSetDevice(h->cfg.device));
     if (int rc = upload_offset_tables(h, h_x_discr_ground, n_ground, h_offset_values, n_offsets)) return rc;
     if (int rc = prepare_cand_cache(h, n_ground, n_offsets)) return rc;
+    if (d_slot != nullptr && h->cand.meta == nullptr)
+        return fail(h, BW_ERR_CAPACITY, "no candidate store (BW_CAND_CACHE_MB, device memory): use bw_enumerate_actions");
     launch_enumerate(h->P, h->d_ground, n_ground, h->d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand,
-                     d_action_bits, h->cand, h->stream);
+                     d_action_bits, d_slot, h->cand, h->stream);
     h->launches++;
+    CU(cudaGetLastError());
+    return BW_OK;
+}
+
+int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground, const double *h_offset_values,
+                         int32_t n_offsets, int32_t amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand,
+                         uint64_t *d_action_bits) {
+    return enumerate_common(h, h_x_discr_ground, n_ground, h_offset_values, n_offsets, amax, d_cand, d_valid, d_n_cand,
+                            d_action_bits, nullptr);
+}
+
+int bw_enumerate_actions_stored(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
+                                const double *h_offset_values, int32_t n_offsets, int32_t amax, bw_action *d_cand,
+                                uint8_t *d_valid, int32_t *d_n_cand, int32_t *d_slot) {
+    if (!d_slot) return BW_ERR_INVALID;
+    return enumerate_common(h, h_x_discr_ground, n_ground, h_offset_values, n_offsets, amax, d_cand, d_valid, d_n_cand,
+                            nullptr, d_slot);
+}
+
+int bw_gather_action_bits(bw_handle *h, const int32_t *d_slot, int32_t amax, const int32_t *d_env, const int32_t *d_index,
+                          int64_t n, uint64_t *d_bits) {
+    if (!h || !d_slot || !d_index || !d_bits || amax <= 0 || n < 0) return BW_ERR_INVALID;
+    if (h->cand.meta == nullptr) return fail(h, BW_ERR_STATE, "no candidate store: nothing was enumerated into it");
+    CU(cudaSetDevice(h->cfg.device));
+    if (n > 0) {
+        launch_gather_bits(h->cand, d_slot, nullptr, amax, h->P.E, d_env, d_index, n, d_bits, h->stream);
+        h->launches++;
+    }
     CU(cudaGetLastError());
     return BW_OK;
 }
@@ -835,8 +872,9 @@ int bw_rollout_configure(bw_handle *h, const double *h_x_discr_ground, int32_t n
     if (R.cand == nullptr || R.amax != amax) {
         if (R.cand != nullptr) {
             CU(cudaStreamSynchronize(h->stream));
-            void *old[3] = {R.cand, R.valid, R.bits};
+            void *old[4] = {R.cand, R.valid, R.bits, R.slot};
             for (void *q : old) {
+                if (!q) continue;
                 cudaFree(q);
                 for (size_t i = 0; i < h->allocs.size(); i++)
                     if (h->allocs[i] == q) { h->allocs.erase(h->allocs.begin() + i); break; }
@@ -844,7 +882,8 @@ int bw_rollout_configure(bw_handle *h, const double *h_x_discr_ground, int32_t n
         }
         CU(dev_alloc(h, &R.cand, E * amax));
         CU(dev_alloc(h, &R.valid, E * amax));
-        CU(dev_alloc(h, &R.bits, E * amax * IMG, false));
+        R.bits = nullptr;                 // dense raster copies: allocated by rollout_enumerate without a store
+        CU(dev_alloc(h, &R.slot, E * amax));
         if (R.n_cand == nullptr) {
             CU(dev_alloc(h, &R.n_cand, E));
             CU(dev_alloc(h, &R.n_valid, E));
@@ -869,12 +908,16 @@ static int rollout_enumerate(bw_handle *h, bw_transition *d_slots) {
     RolloutBufs &R = h->roll;
     if (int rc = upload_offset_tables(h, h->roll_ground, h->roll_n_ground, h->roll_offsets, h->roll_n_offsets)) return rc;
     if (int rc = prepare_cand_cache(h, h->roll_n_ground, h->roll_n_offsets)) return rc;
+    // with a candidate store the rasters stay where they are (R.slot says where); without one they are copied out
+    const bool stored = h->cand.meta != nullptr;
+    if (!stored && R.bits == nullptr) CU(dev_alloc(h, &R.bits, (size_t)h->P.E * R.amax * IMG, false));
+    uint64_t *bits = stored ? nullptr : R.bits;
     launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                     R.n_cand, R.bits, h->cand, h->stream, nullptr, R.n_valid);
+                     R.n_cand, bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
     launch_rollout_finalize(h->P, R, d_slots, h->stream);
     launch_reset(h->P, nullptr, R.stuck, 1, h->stream);
     launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                     R.n_cand, R.bits, h->cand, h->stream, R.stuck, R.n_valid);
+                     R.n_cand, bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
     h->launches += 4;
     CU(cudaGetLastError());
     return BW_OK;
@@ -888,7 +931,9 @@ int bw_rollout_begin(bw_handle *h, bw_rollout_view *out) {
     if (out) {
         const RolloutBufs &R = h->roll;
         out->cand = R.cand; out->valid = R.valid; out->n_cand = R.n_cand; out->n_valid = R.n_valid;
-        out->action_bits = R.bits; out->amax = R.amax; out->reserved0 = 0;
+        out->action_bits = (h->cand.meta != nullptr) ? nullptr : R.bits;
+        out->slot = (h->cand.meta != nullptr) ? R.slot : nullptr;
+        out->amax = R.amax; out->reserved0 = 0;
     }
     return BW_OK;
 }
@@ -896,7 +941,9 @@ int bw_rollout_begin(bw_handle *h, bw_rollout_view *out) {
 static int rollout_iteration(bw_handle *h, const int32_t *d_index, int random_policy, uint64_t seed, bw_transition *d_slots,
                              const bw_obs_out *obs) {
     RolloutBufs &R = h->roll;
-    launch_rollout_pick(h->P, R, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
+    RolloutBufs Rp = R;
+    if (h->cand.meta != nullptr) Rp.bits = nullptr;      // rasters are read out of the store
+    launch_rollout_pick(h->P, Rp, h->cand, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
     launch_step(h->P, R.actions, R.has_action, h->d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr,
                 nullptr, 0, h->smem_step, h->stream);
     launch_rollout_record(h->P, R, h->d_out, d_slots, h->stream);
@@ -924,6 +971,22 @@ int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transitio
         bw_transition *slots = d_ring + (start + (int64_t)k * E) % capacity;
         if (int rc = rollout_iteration(h, nullptr, 1, seed, slots, nullptr)) return rc;
     }
+    return BW_OK;
+}
+
+int bw_rollout_gather_bits(bw_handle *h, const int32_t *d_env, const int32_t *d_index, int64_t n, uint64_t *d_bits) {
+    if (!h || !d_index || !d_bits || n < 0) return BW_ERR_INVALID;
+    if (!h->roll_configured || h->roll.slot == nullptr)
+        return fail(h, BW_ERR_STATE, "bw_rollout_configure / bw_rollout_begin must be called first");
+    CU(cudaSetDevice(h->cfg.device));
+    if (n > 0) {
+        const RolloutBufs &R = h->roll;
+        const bool stored = h->cand.meta != nullptr;
+        if (!stored && R.bits == nullptr) return fail(h, BW_ERR_STATE, "bw_rollout_begin must be called first");
+        launch_gather_bits(h->cand, R.slot, stored ? nullptr : R.bits, R.amax, h->P.E, d_env, d_index, n, d_bits, h->stream);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
     return BW_OK;
 }
 

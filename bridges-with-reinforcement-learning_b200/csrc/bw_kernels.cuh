@@ -30,19 +30,48 @@ void launch_render_blocks(const Params &P, const ShapeDev *d_shapes, const bw_bl
 // bw_actions.cu
 void launch_query_placement(const Params &P, const bw_action *d_actions, double xl, double xh, double zl, double zh,
                             bw_block *d_blocks, uint8_t *d_flags, cudaStream_t stream);
-// cache of candidate placements (enumerate_kernel<true>): per environment `slots` = groups x `spg` slots, one per
-// (shape, face) group and ground offset / (target block, target face, offset)
+// store of candidate placements (enumerate_store_kernel): per environment `slots` = groups x `spg` slots, one per
+// (shape, face) group and ground offset / (target block, target face, offset).  Slot word:
+//   bit 31 SLOT_VALID   the slot holds the placement of its candidate (bounds flag, pixel window, raster rows)
+//   bit 30 SLOT_BAD     collision_on_action (gym_env.py:304-323): a vertex outside the window
+//   bit 29 SLOT_OVL     the raster overlapped the block / obstacle rasters at the call whose stamp it carries
+//   bits 13-28          stamp of the last call that listed the candidate (CandCache::call of the environment)
+//   bits 7-12 / 0-6     first window row / window rows (0..64)
+constexpr uint32_t SLOT_VALID = 0x80000000u, SLOT_BAD = 0x40000000u, SLOT_OVL = 0x20000000u;
+constexpr int SLOT_STAMP_SHIFT = 13;
+constexpr uint32_t SLOT_STAMP_MASK = 0xffffu;
+constexpr uint32_t SLOT_GEOM = 0x1fffu | SLOT_BAD;     // what the placement alone decides
+__host__ __device__ __forceinline__ int slot_rows(uint32_t m) { return (int)(m & 0x7fu); }
+__host__ __device__ __forceinline__ int slot_ilo(uint32_t m) { return (int)((m >> 7) & 0x3fu); }
 struct CandCache {
-    uint32_t *meta = nullptr;   // [E][slots] SLOT_VALID | SLOT_BAD | first window row << 8 | window rows
-    uint64_t *bits = nullptr;   // [E][slots][IMG] raster rows (only the window rows are meaningful)
-    Pose *pose = nullptr;       // [E][NB] pose and
-    uint8_t *shape = nullptr;   // [E][NB] shape of the block the slots of (block, *) were filled for
+    uint32_t *meta = nullptr;        // [E][slots] slot words
+    uint64_t *bits = nullptr;        // [E][slots][IMG] raster rows (only the window rows are meaningful)
+    Pose *pose = nullptr;            // [E][NB] pose and
+    uint8_t *shape = nullptr;        // [E][NB] shape of the block the slots of (block, *) were filled for
+    uint64_t *seen_block = nullptr;  // [E][IMG] block raster and
+    uint64_t *seen_obst = nullptr;   // [E][IMG] obstacle raster at the last call (SLOT_OVL refers to them)
+    uint32_t *call = nullptr;        // [E] stamp of the last call, 1 .. 0xffff
     int32_t slots = 0, spg = 0;
 };
+#ifdef __CUDACC__
+// row `row` of the raster kept in slot `slot` of environment e (rows outside the window are zero)
+__device__ __forceinline__ uint64_t cand_store_row(const CandCache &C, int e, int slot, int row) {
+    const uint32_t m = C.meta[(size_t)e * C.slots + slot];
+    const int ilo = slot_ilo(m);
+    if (!(m & SLOT_VALID) || row < ilo || row >= ilo + slot_rows(m)) return 0;
+    return C.bits[((size_t)e * C.slots + slot) * IMG + row];
+}
+#endif
+// d_action_bits: dense raster copies [E,amax,64] (may be null); d_slot: slot of every listed candidate [E,amax]
+// (may be null; only written with a store)
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
-                      const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask = nullptr,
+                      int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask = nullptr,
                       int32_t *d_n_valid = nullptr);
+// d_out[i] = raster of candidate d_index[i] of environment d_env[i] (d_env null: environment i), read from the
+// dense copies when d_dense is given, else through d_slot from the store
+void launch_gather_bits(const CandCache &cache, const int32_t *d_slot, const uint64_t *d_dense, int amax, int E,
+                        const int32_t *d_env, const int32_t *d_index, int64_t n, uint64_t *d_out, cudaStream_t stream);
 
 // bw_rollout.cu: the kernels around step / enumerate / reset of one lock-step rollout iteration
 struct RolloutBufs {
@@ -50,14 +79,15 @@ struct RolloutBufs {
     uint8_t *valid = nullptr;        // [E][amax]
     int32_t *n_cand = nullptr;       // [E]
     int32_t *n_valid = nullptr;      // [E]
-    uint64_t *bits = nullptr;        // [E][amax][IMG]
+    uint64_t *bits = nullptr;        // [E][amax][IMG] dense raster copies: only without a candidate store
+    int32_t *slot = nullptr;         // [E][amax] store slot of every listed candidate
     bw_action *actions = nullptr;    // [E] chosen actions (input of the step kernel)
     uint8_t *has_action = nullptr;   // [E] step mask
     uint8_t *stuck = nullptr;        // [E] live environment without a candidate: reset + enumerated again
     int32_t amax = 0, env_id_base = 0;
 };
-void launch_rollout_pick(const Params &P, const RolloutBufs &R, const int32_t *d_index, int random_policy, uint64_t seed,
-                         int32_t step, bw_transition *d_slots, cudaStream_t stream);
+void launch_rollout_pick(const Params &P, const RolloutBufs &R, const CandCache &cache, const int32_t *d_index,
+                         int random_policy, uint64_t seed, int32_t step, bw_transition *d_slots, cudaStream_t stream);
 void launch_rollout_record(const Params &P, const RolloutBufs &R, const bw_step_out *d_out, bw_transition *d_slots,
                            cudaStream_t stream);
 void launch_rollout_finalize(const Params &P, const RolloutBufs &R, bw_transition *d_slots, cudaStream_t stream);

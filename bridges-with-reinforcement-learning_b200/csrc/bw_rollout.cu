@@ -31,8 +31,8 @@ __device__ __forceinline__ uint8_t binary_bits(const bw_step_out &o) {    // get
 
 // One CTA of 64 threads per environment (thread = image row for the raster copies).
 __global__ void __launch_bounds__(64)
-rollout_pick_kernel(Params P, RolloutBufs R, const int32_t *__restrict__ index, int random_policy, uint64_t seed,
-                    int32_t step, bw_transition *__restrict__ slots) {
+rollout_pick_kernel(Params P, RolloutBufs R, CandCache C, const int32_t *__restrict__ index, int random_policy,
+                    uint64_t seed, int32_t step, bw_transition *__restrict__ slots) {
     const int e = blockIdx.x, tid = threadIdx.x;
     const int amax = R.amax;
     const int cnt = R.n_cand[e], nvalid = R.n_valid[e];
@@ -86,7 +86,13 @@ rollout_pick_kernel(Params P, RolloutBufs R, const int32_t *__restrict__ index, 
         return;
     }
     T.block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
-    T.action_bits[tid] = R.bits[((size_t)e * amax + choice) * IMG + tid];
+    // the chosen candidate's raster: from the dense copies, or straight out of the candidate store
+    if (R.bits != nullptr) {
+        T.action_bits[tid] = R.bits[((size_t)e * amax + choice) * IMG + tid];
+    } else {
+        const int s = R.slot[(size_t)e * amax + choice];
+        T.action_bits[tid] = (s >= 0) ? cand_store_row(C, e, s, tid) : 0ull;
+    }
     if (tid == 0) {
         const bw_action a = R.cand[(size_t)e * amax + choice];
         R.actions[e] = a;
@@ -145,9 +151,9 @@ __global__ void rollout_finalize_kernel(Params P, RolloutBufs R, bw_transition *
     if (stuck) P.done[e] = 1;
 }
 
-void launch_rollout_pick(const Params &P, const RolloutBufs &R, const int32_t *d_index, int random_policy, uint64_t seed,
-                         int32_t step, bw_transition *d_slots, cudaStream_t stream) {
-    rollout_pick_kernel<<<P.E, 64, 0, stream>>>(P, R, d_index, random_policy, seed, step, d_slots);
+void launch_rollout_pick(const Params &P, const RolloutBufs &R, const CandCache &cache, const int32_t *d_index,
+                         int random_policy, uint64_t seed, int32_t step, bw_transition *d_slots, cudaStream_t stream) {
+    rollout_pick_kernel<<<P.E, 64, 0, stream>>>(P, R, cache, d_index, random_policy, seed, step, d_slots);
 }
 
 void launch_rollout_record(const Params &P, const RolloutBufs &R, const bw_step_out *d_out, bw_transition *d_slots,

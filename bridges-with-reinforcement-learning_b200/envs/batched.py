@@ -43,6 +43,31 @@ def gaussian_kernel1d(kernel_size=101, sigma=16):
     return k
 
 
+class CandidateRasters:
+    """Bit rasters of listed candidates that live in the handle's candidate store (or in its dense copies):
+    `r[env_idx, cand_idx]` (two equally long integer CUDA tensors) -> int64 [n, 64], `r.dense()` -> [E, amax, 64].
+    Good until the next enumeration / rollout iteration."""
+
+    def __init__(self, env, E, amax, gather):
+        self.env, self.E, self.amax, self._gather = env, E, amax, gather
+
+    def __getitem__(self, key):
+        er, ar = key
+        er = torch.as_tensor(er, device=self.env.device).to(torch.int32).contiguous()
+        ar = torch.as_tensor(ar, device=self.env.device).to(torch.int32).contiguous()
+        if er.shape != ar.shape or er.dim() != 1:
+            raise L.BridgesError("CandidateRasters[env_idx, cand_idx]: two 1-D index tensors of equal length")
+        out = torch.empty((er.numel(), L.BW_IMG), dtype=torch.int64, device=self.env.device)
+        self.env._check(self._gather(er.data_ptr(), ar.data_ptr(), er.numel(), out.data_ptr()))
+        return out
+
+    def dense(self):
+        dev = self.env.device
+        er = torch.arange(self.E, device=dev, dtype=torch.int32).repeat_interleave(self.amax)
+        ar = torch.arange(self.amax, device=dev, dtype=torch.int32).repeat(self.E)
+        return self[er, ar].reshape(self.E, self.amax, L.BW_IMG)
+
+
 class BatchedAssemblyGym:
     def __init__(self, num_envs, shapes, max_steps=None, device=0, mu=0.8, density=1.0, xlim=(-3.0, 7.0),
                  ylim=(0.0, 10.0), bounds=None, tmax=1e-6, amin=1e-3, stable_tol=1e-6, stream=None,
@@ -301,20 +326,37 @@ class BatchedAssemblyGym:
 
     # ------------------------------------------------------------------ candidate actions
     def enumerate_actions(self, x_discr_ground, offset_values=(0.0,), amax=256, with_bits=True):
+        """generate_actions + get_action_features + filter_actions of every environment (actions.py:7-82,
+        successor_dqn.py:88-94).  with_bits=True: dense raster copies c["bits"] int64 [E,amax,64];
+        with_bits="stored": the rasters stay in the handle's candidate store, c["bits"] is a `CandidateRasters`
+        (`c["bits"][env_idx, cand_idx]` gathers the ones a caller looks at, `.dense()` all of them);
+        with_bits=False: no rasters."""
         E = self.num_envs
-        if self._cand is None or self._cand["amax"] != amax or (with_bits and self._cand["bits"] is None):
+        if self._cand is None or self._cand["amax"] != amax:
             self._cand = dict(
                 amax=amax,
                 cand=torch.zeros(E * amax * self.dt["action"].itemsize, dtype=torch.uint8, device=self.device),
                 valid=torch.zeros((E, amax), dtype=torch.uint8, device=self.device),
-                n=torch.zeros(E, dtype=torch.int32, device=self.device),
-                bits=torch.zeros((E, amax, L.BW_IMG), dtype=torch.int64, device=self.device) if with_bits else None)
+                n=torch.zeros(E, dtype=torch.int32, device=self.device), bits=None, dense=None, slot=None)
         c = self._cand
         g = np.ascontiguousarray(np.asarray(x_discr_ground, dtype=np.float64))
         o = np.ascontiguousarray(np.asarray(offset_values, dtype=np.float64))
+        if with_bits == "stored":
+            if c["slot"] is None:
+                c["slot"] = torch.zeros((E, amax), dtype=torch.int32, device=self.device)
+            self._check(self.lib.bw_enumerate_actions_stored(
+                self.handle, g.ctypes.data, g.size, o.ctypes.data, o.size, amax, c["cand"].data_ptr(),
+                c["valid"].data_ptr(), c["n"].data_ptr(), c["slot"].data_ptr()))
+            slot = c["slot"]
+            c["bits"] = CandidateRasters(self, E, amax, lambda env, idx, n, out: self.lib.bw_gather_action_bits(
+                self.handle, slot.data_ptr(), amax, env, idx, n, out))
+            return c
+        if with_bits and c["dense"] is None:
+            c["dense"] = torch.zeros((E, amax, L.BW_IMG), dtype=torch.int64, device=self.device)
         self._check(self.lib.bw_enumerate_actions(
             self.handle, g.ctypes.data, g.size, o.ctypes.data, o.size, amax, c["cand"].data_ptr(),
-            c["valid"].data_ptr(), c["n"].data_ptr(), c["bits"].data_ptr() if with_bits else None))
+            c["valid"].data_ptr(), c["n"].data_ptr(), c["dense"].data_ptr() if with_bits else None))
+        c["bits"] = c["dense"] if with_bits else None
         return c
 
     def candidate_overflow(self):

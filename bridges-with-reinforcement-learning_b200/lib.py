@@ -14,7 +14,7 @@ BW_MAX_OBSTACLES = 8
 BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
-BW_ABI_VERSION = 5
+BW_ABI_VERSION = 6
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")
@@ -95,7 +95,7 @@ class bw_transition(C.Structure):
 
 class bw_rollout_view(C.Structure):
     _fields_ = [("cand", C.c_void_p), ("valid", C.c_void_p), ("n_cand", C.c_void_p), ("n_valid", C.c_void_p),
-                ("action_bits", C.c_void_p), ("amax", C.c_int32), ("reserved0", C.c_int32)]
+                ("action_bits", C.c_void_p), ("slot", C.c_void_p), ("amax", C.c_int32), ("reserved0", C.c_int32)]
 
 
 # numpy views of the same layouts (for bulk transfers)
@@ -156,12 +156,15 @@ SIGNATURES = {
     "bw_observe": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_observe_host": (C.c_int, [_H, _P, _P, _P, _P]),
     "bw_enumerate_actions": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "bw_enumerate_actions_stored": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "bw_gather_action_bits": (C.c_int, [_H, _P, C.c_int32, _P, _P, C.c_int64, _P]),
     "bw_candidate_overflow": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bw_expand_bits": (C.c_int, [_H, _P, C.c_int64, _P]),
     "bw_select_random": (C.c_int, [_H, _P, _P, _P, C.c_int32, C.c_uint64, _P, _P]),
     "bw_rollout_configure": (C.c_int, [_H, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
     "bw_rollout_begin": (C.c_int, [_H, C.POINTER(bw_rollout_view)]),
     "bw_rollout_commit": (C.c_int, [_H, _P, _P, C.POINTER(bw_obs_out)]),
+    "bw_rollout_gather_bits": (C.c_int, [_H, _P, _P, C.c_int64, _P]),
     "bw_rollout_random": (C.c_int, [_H, C.c_int32, C.c_uint64, _P, C.c_int64, C.c_int64]),
     "bw_unpack_transitions": (C.c_int, [_H, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bw_get_state": (C.c_int, [_H, _P, _P]),

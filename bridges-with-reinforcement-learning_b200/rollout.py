@@ -204,14 +204,23 @@ class FusedRollout:
         E, A = self.E, self.amax
         dev = self.env.device
         wrap = lambda ptr, shape, ts: torch.as_tensor(_DevArray(ptr, shape, ts), device=dev)
+        env = self.env
+        if view.action_bits:             # no candidate store: dense raster copies
+            bits, slot = wrap(view.action_bits, (E, A, IMG), "<i8"), None
+        else:                            # the rasters stay in the handle's store: gathered on demand
+            from .envs.batched import CandidateRasters
+            slot = wrap(view.slot, (E, A), "<i4")
+            bits = CandidateRasters(env, E, A, lambda e_ptr, i_ptr, n, out: env.lib.bw_rollout_gather_bits(
+                env.handle, e_ptr, i_ptr, n, out))
         self._view = dict(amax=A, cand=wrap(view.cand, (E * A * 40,), "|u1"), valid=wrap(view.valid, (E, A), "|u1"),
-                          n=wrap(view.n_cand, (E,), "<i4"), n_valid=wrap(view.n_valid, (E,), "<i4"),
-                          bits=wrap(view.action_bits, (E, A, IMG), "<i8"))
+                          n=wrap(view.n_cand, (E,), "<i4"), n_valid=wrap(view.n_valid, (E,), "<i4"), bits=bits, slot=slot)
         return self._view
 
     def candidates(self):
         """Candidate buffers of the current states (torch views of the handle's memory, refreshed in place by
-        every iteration): cand bytes [E*amax*40], valid u8 [E,amax], n / n_valid i32 [E], bits i64 [E,amax,64]."""
+        every iteration): cand bytes [E*amax*40], valid u8 [E,amax], n / n_valid i32 [E]; bits[env_idx, cand_idx] ->
+        i64 [n,64] rasters of chosen candidates (a `CandidateRasters` over the handle's candidate store, or the dense
+        i64 [E,amax,64] tensor when the store is switched off)."""
         return self._view
 
     def step(self, index, obs=None):
@@ -292,7 +301,7 @@ def q_network_policy(policy_net, reward_features, obstacle_features, epsilon=0.0
         with torch.no_grad():
             for lo in range(0, e_idx.numel(), chunk_rows):
                 er, ar = e_idx[lo:lo + chunk_rows], a_idx[lo:lo + chunk_rows]
-                action_f = env.expand_bits(cand["bits"][er, ar].contiguous())
+                action_f = env.expand_bits(cand["bits"][er, ar].contiguous())      # only the valid candidates' rasters
                 q = policy_net(state["block"][er], state["binary"][er], action_f, reward_features[er], obstacle_features[er])
                 q = q[0] if isinstance(q, (tuple, list)) else q
                 q_full[er, ar] = q.reshape(-1).float()

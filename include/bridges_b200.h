@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 5
+#define BW_ABI_VERSION 6
 
 /* compile-time capacities (reference configs: <= 15 blocks, <= 7 obstacles, <= 3 targets) */
 #define BW_MAX_BLOCKS 16
@@ -245,6 +245,18 @@ int bw_observe_host(bw_handle *h, float *h_block_img, float *h_binary, float *h_
 int bw_enumerate_actions(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
                          const double *h_offset_values, int32_t n_offsets, int32_t amax,
                          bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits);
+/* The same enumeration WITHOUT the raster copies (filter_actions keeps a fraction of the candidates, a policy looks
+ * at those): d_slot[e,a] (i32 [E,Amax]) = where the raster of candidate a lives in the handle's candidate store, -1
+ * = none (never for a valid candidate).  bw_gather_action_bits copies the rasters of chosen candidates out:
+ * d_bits[i] ([n,64] u64) = raster of candidate d_index[i] of environment d_env[i] (d_env NULL: environment i).
+ * Slots are good until the next enumeration or state change of their environment.  Candidates that were listed by
+ * the previous call are only tested against the pixels the block raster gained since then (results identical to
+ * bw_enumerate_actions).  BW_ERR_CAPACITY when the store is switched off (BW_CAND_CACHE_MB = 0 / no memory). */
+int bw_enumerate_actions_stored(bw_handle *h, const double *h_x_discr_ground, int32_t n_ground,
+                                const double *h_offset_values, int32_t n_offsets, int32_t amax,
+                                bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, int32_t *d_slot);
+int bw_gather_action_bits(bw_handle *h, const int32_t *d_slot, int32_t amax, const int32_t *d_env,
+                          const int32_t *d_index, int64_t n, uint64_t *d_bits);
 /* generate_actions is unbounded, the buffers above hold amax candidates per environment: lists that did not
  * fit are cut to amax (d_n_cand[e] = amax) and remembered.  *h_needed = the largest untruncated count any
  * environment had since the last query (0 = every list was complete); synchronises and resets the mark. */
@@ -292,7 +304,8 @@ typedef struct {
     const uint8_t *valid;        /* [E,amax] filter_actions mask */
     const int32_t *n_cand;       /* [E] */
     const int32_t *n_valid;      /* [E] */
-    const uint64_t *action_bits; /* [E,amax,64] */
+    const uint64_t *action_bits; /* [E,amax,64] dense rasters -- NULL when the candidates live in the handle's store */
+    const int32_t *slot;         /* [E,amax] store slots (NULL without a store); read rasters with bw_rollout_gather_bits */
     int32_t amax;
     int32_t reserved0;
 } bw_rollout_view;
@@ -308,6 +321,9 @@ int bw_rollout_begin(bw_handle *h, bw_rollout_view *out);
  * where n_valid[e] = 0).  d_slots: E records (record e belongs to environment e).  obs: optional observation
  * outputs of the step as in bw_step (device pointers), may be NULL. */
 int bw_rollout_commit(bw_handle *h, const int32_t *d_index, bw_transition *d_slots, const bw_obs_out *obs);
+/* rasters of chosen candidates of the CURRENT candidate lists: d_bits[i] ([n,64] u64) = raster of candidate d_index[i]
+ * of environment d_env[i] (d_env NULL: environment i); works with and without a candidate store */
+int bw_rollout_gather_bits(bw_handle *h, const int32_t *d_env, const int32_t *d_index, int64_t n, uint64_t *d_bits);
 /* n_steps iterations with the built-in uniformly random policy (the synthetic policy of the benchmarks).  The
  * records of iteration k go to d_ring[(start + k*E + e) % capacity]; capacity must be a multiple of E. */
 int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transition *d_ring, int64_t capacity,

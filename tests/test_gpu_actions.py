@@ -142,3 +142,68 @@ def test_candidate_cache_matches_plain_kernel(monkeypatch):
     oa, ob = cached.read_out(), plain.read_out()
     assert np.array_equal(oa["n_blocks"], ob["n_blocks"])
     cached.close(); plain.close()
+
+
+def test_stored_candidates_match_plain_kernel(monkeypatch):
+    """bw_enumerate_actions_stored leaves the rasters in the handle's candidate store and tests a candidate that the
+    previous call listed against the NEW pixels of the block raster only (enumerate_store_kernel<false>).  Same
+    rollouts as a handle without a store (plain kernel, dense copies): candidates, validity and the gathered rasters
+    of every call -- through auto-resets, calls that are skipped (two blocks of new pixels), repeated calls on one
+    state, a dense call in between, a change of the offset table and a reset with pre-placed blocks."""
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    E, amax = 48, 512
+    urdfs = [H.URDF["trapezoid"], H.URDF["hexagon"]]
+    task = dict(obstacles=[(0.6, 0, 0.3), (1.2, 0, 0.3)], targets=[(2.4, 0, 0.3)])
+    stored = BatchedAssemblyGym(E, urdfs, max_steps=10)
+    monkeypatch.setenv("BW_CAND_CACHE_MB", "0")
+    plain = BatchedAssemblyGym(E, urdfs, max_steps=10)
+    monkeypatch.delenv("BW_CAND_CACHE_MB")
+    for env in (stored, plain):
+        env.reset(task)
+    sz = stored.dt["action"].itemsize
+
+    def compare(offsets, tag, mode="stored"):
+        a = stored.enumerate_actions(XG, offsets, amax=amax, with_bits=mode)
+        b = plain.enumerate_actions(XG, offsets, amax=amax)
+        ba = a["bits"].dense() if mode == "stored" else a["bits"]
+        stored.sync(); plain.sync()
+        n = a["n"].cpu().numpy()
+        assert np.array_equal(n, b["n"].cpu().numpy()), tag
+        ca = a["cand"].cpu().numpy().reshape(E, amax, sz)
+        cb = b["cand"].cpu().numpy().reshape(E, amax, sz)
+        va, vb = a["valid"].cpu().numpy(), b["valid"].cpu().numpy()
+        ba, bb = ba.cpu().numpy(), b["bits"].cpu().numpy()
+        for e in range(E):
+            assert np.array_equal(ca[e, :n[e]], cb[e, :n[e]]), (tag, e)
+            assert np.array_equal(va[e, :n[e]], vb[e, :n[e]]), (tag, e, np.flatnonzero(va[e, :n[e]] != vb[e, :n[e]]))
+            assert np.array_equal(ba[e, :n[e]], bb[e, :n[e]]), (tag, e)
+        if mode == "stored":      # a gather of chosen candidates: the first valid one of every environment
+            first = torch.as_tensor(np.argmax(vb, axis=1).astype(np.int32))
+            got = a["bits"][torch.arange(E), first].cpu().numpy()
+            assert np.array_equal(got, bb[np.arange(E), first.numpy()]), tag
+        return int(n.max()), int(va.sum()), b
+
+    n_max = n_valid = 0
+    for k in range(60):
+        offsets = (0.0,) if k < 40 else (0.0, 0.25)          # the offset table changes: every slot is stale
+        if k % 7 == 3:                                        # the stored side skips this call
+            b = plain.enumerate_actions(XG, offsets, amax=amax)
+        else:
+            m, v, b = compare(offsets, k, "stored" if k % 11 != 5 else True)
+            n_max, n_valid = max(n_max, m), n_valid + v
+            if k % 5 == 2:                                    # once more on the same state: nothing new to test
+                compare(offsets, (k, "again"))
+        acts, _ = plain.select_random(seed=2000 + k, cand=b)
+        acts = acts.clone()
+        stored.select_random(seed=2000 + k, cand=b)           # same states, same choice: the "no candidate" flags agree
+        stored.step(acts); plain.step(acts)
+        if k == 23:                                           # reset with pre-placed blocks, all environments
+            pre = dict(task, blocks=[(-1.5, 0.5, 1.0, 0.0, 1), (3.5, 0.4, 0.0, 1.0, 0)])     # (x, z, c, s, shape)
+            stored.reset(pre); plain.reset(pre)
+        else:
+            stored.reset_done(); plain.reset_done()
+    assert n_max > 150 and n_valid > 5000
+    oa, ob = stored.read_out(), plain.read_out()
+    assert np.array_equal(oa["n_blocks"], ob["n_blocks"])
+    stored.close(); plain.close()

@@ -223,7 +223,8 @@ def test_q_network_policy_around_begin_commit():
     valid = cand["valid"].cpu().numpy().astype(bool)
     valid &= np.arange(128)[None, :] < cand["n"].cpu().numpy()[:, None]
     assert np.array_equal(valid.sum(axis=1), cand["n_valid"].cpu().numpy())
-    bits = cand["bits"].cpu().numpy().view(np.uint64)
+    bits = cand["bits"].dense() if hasattr(cand["bits"], "dense") else cand["bits"]     # store or dense copies
+    bits = bits.cpu().numpy().view(np.uint64)
     reward = feats["reward"].cpu().numpy()[:, 0]
     cands = cand["cand"].cpu().numpy().view(env.dt["action"]).reshape(E, 128)
     assert seen[-1] == int(valid.sum())
