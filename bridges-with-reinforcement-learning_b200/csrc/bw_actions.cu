@@ -248,14 +248,14 @@ enumerate_kernel(Params PG, const double *__restrict__ ground, int n_ground, con
 // One CTA per environment.  Per chunk of CCH candidates:
 //   A0  thread per candidate: the action, its slot, hit / miss, the rows that need a test -> two dense lists
 //   Bh  hits with rows to test: 8 lanes per candidate, rows read back from the store
-//   A1  misses, DENSE (thread m poses the m-th miss; FP64 work that is uniform for a candidate), MISS_CAP per round
-//   Bm  thread per (miss, row of its window): the row's bit mask (exact half-plane walks), stored and tested
+//   A1  misses, DENSE (MISS_CAP per round): eight lanes pose the m-th miss (a vertex and a face each)
+//   Bm  sixteen lanes per miss, a row of its window each: the row's bit mask (exact where it matters), stored, tested
 //   C   thread per candidate: validity flag, slot word with the new verdict and stamp
 // COPY: the caller wants the rasters copied out ([E,amax,64]); every listed candidate is then read and tested in
 // full.  Without it the caller gets d_slot (where the raster lives) and gathers what it needs.
 constexpr int CCH = 256;
 constexpr int CPT = CCH / ENUM_THREADS;
-constexpr int MISS_CAP = 64;
+constexpr int MISS_CAP = 32;
 constexpr uint32_t W_INCR = 0x80000000u;          // working word only: the stored verdict holds, test new pixels only
 
 __device__ __forceinline__ int list_append(bool pred, int *counter, int lane) {
@@ -297,10 +297,7 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
     __shared__ unsigned s_inval, s_dmask[2], s_prev;
     // posed-face tables of the misses of one round
     __shared__ double t_nx[MISS_CAP][NF], t_nz[MISS_CAP][NF], t_cx[MISS_CAP][NF], t_cz[MISS_CAP][NF], t_inx[MISS_CAP][NF];
-    __shared__ int8_t t_nf[MISS_CAP], t_jlo[MISS_CAP], t_jhi[MISS_CAP], t_ilo[MISS_CAP];
-    __shared__ int m_rowstart[MISS_CAP + 1];
-    constexpr int OWNER_CAP = 512;                      // (miss, row) pairs of a round with a direct owner entry
-    __shared__ uint8_t m_owner[OWNER_CAP];
+    __shared__ int8_t t_nf[MISS_CAP], t_jlo[MISS_CAP], t_jhi[MISS_CAP], t_ilo[MISS_CAP], t_rows[MISS_CAP];
     // per candidate of the chunk
     __shared__ uint32_t c_w[CCH];                       // SLOT_BAD | SLOT_OVL | window (slot word layout) | W_INCR
     __shared__ int c_slot[CCH];
@@ -309,9 +306,17 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
     __shared__ int s_nmiss, s_nwork, s_nval;
 
     const int n = P.n_blocks[e];
+    Pose my_pose, kept_pose;                  // lane = block: its pose and the one its slots were filled for
+    uint8_t my_shape = 0, kept_shape = 0;
+    if (tid < NB) {                           // all loads of the prologue are in flight together
+        my_pose = P.pose[(size_t)e * NB + tid];
+        my_shape = P.shape_of[(size_t)e * NB + tid];
+        kept_pose = C.pose[(size_t)e * NB + tid];
+        kept_shape = C.shape[(size_t)e * NB + tid];
+    }
     if (tid < n) {
-        s_pose[tid] = P.pose[(size_t)e * NB + tid];
-        s_shape[tid] = P.shape_of[(size_t)e * NB + tid];
+        s_pose[tid] = my_pose;
+        s_shape[tid] = my_shape;
     }
     uint64_t regress = 0;
     if (tid < IMG) {
@@ -366,24 +371,42 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
             k++;
         }
         if (tid == 31) s_nfree = inc;
-    } else if (tid == 32) {
-        int g = 0;
-        for (int s = 0; s < P.n_shapes; s++) {
-            const ShapeDev &sh = P.shapes[s];
-            for (int f = 0; f < sh.n_faces; f++)
-                if ((sh.target_faces_mask >> f) & 1u) { s_grp_s[g] = (uint8_t)s; s_grp_f[g] = (uint8_t)f; g++; }
+    } else if (tid < 64) {
+        // candidate groups = (shape, face) pairs with the target_faces bit, shape-major: warp 1, two pairs per lane
+        static_assert(BW_MAX_SHAPES * NF <= 64, "two (shape, face) pairs per lane");
+        const int l = tid - 32;
+        unsigned has = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int idx = 2 * l + j, s = idx / NF, f = idx - s * NF;
+            if (s < P.n_shapes && f < P.shapes[s].n_faces && ((P.shapes[s].target_faces_mask >> f) & 1u)) has |= 1u << j;
         }
-        s_ngrp = g;
+        const int cnt = __popc(has);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (l >= o) inc += v;
+        }
+        int g = inc - cnt;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if ((has >> j) & 1u) {
+                const int idx = 2 * l + j, s = idx / NF;
+                s_grp_s[g] = (uint8_t)s;
+                s_grp_f[g] = (uint8_t)(idx - s * NF);
+                g++;
+            }
+        }
+        if (l == 31) s_ngrp = inc;
     }
     // blocks that are not the ones their slots were filled for: drop those slots, remember the new block
     if (tid < n) {
-        const Pose cp = C.pose[(size_t)e * NB + tid];
-        const Pose p = s_pose[tid];
-        const bool same = same_bits(cp.x, p.x) && same_bits(cp.z, p.z) && same_bits(cp.c, p.c) &&
-                          same_bits(cp.s, p.s) && C.shape[(size_t)e * NB + tid] == s_shape[tid];
+        const bool same = same_bits(kept_pose.x, my_pose.x) && same_bits(kept_pose.z, my_pose.z) &&
+                          same_bits(kept_pose.c, my_pose.c) && same_bits(kept_pose.s, my_pose.s) && kept_shape == my_shape;
         if (!same) {
-            C.pose[(size_t)e * NB + tid] = p;
-            C.shape[(size_t)e * NB + tid] = s_shape[tid];
+            C.pose[(size_t)e * NB + tid] = my_pose;
+            C.shape[(size_t)e * NB + tid] = my_shape;
             atomicOr(&s_inval, 1u << tid);
         }
     }
@@ -533,93 +556,89 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
         int r0 = 0;
         do {
             const int nm = max(0, min(MISS_CAP, nmiss - r0));
-            if (tid < nm) {   // A1
-                const int t = s_miss[r0 + tid];
-                int slot;
-                const bw_action act = make_action(base + t, slot);
+            // ---- A1: eight lanes per miss -- lane j takes vertex j (bounds test, bounding box) and face j (posed
+            // half-plane); the placement itself is computed by all eight
+            for (int m0 = 0; m0 < nm; m0 += ENUM_THREADS / 8) {
+                const int m = m0 + (tid >> 3), j = tid & 7;
+                const bool on = m < nm;
+                const int t = on ? s_miss[r0 + m] : 0;
+                int slot = -1, err = 1;
+                bw_action act;
                 Pose ps;
-                const int err = place_block(P, s_pose, s_shape, n, act, ps);
-                bool bad = (err != 0);
-                int rows = 0, ilo = 0;
-                if (!bad) {
-                    const ShapeDev &sh = P.shapes[act.shape];
-                    // collision_on_action: any vertex outside the window (gym_env.py:304-323)
-                    for (int v = 0; v < sh.n_verts; v++) {
-                        double vx, vz;
-                        rot(ps.c, ps.s, sh.vert_x[v], sh.vert_z[v], vx, vz);
-                        vx = dadd(vx, ps.x);
-                        vz = dadd(vz, ps.z);
-                        if (vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps) bad = true;
-                    }
-                    PosedShape o;
-                    pose_shape(P, sh, ps, o);
-                    for (int k = 0; k < NF; k++) {
-                        t_nx[tid][k] = o.nx[k]; t_nz[tid][k] = o.nz[k]; t_cx[tid][k] = o.cx[k]; t_cz[tid][k] = o.cz[k];
-                        t_inx[tid][k] = o.inv_nx[k];
-                    }
-                    t_nf[tid] = (int8_t)o.n_faces;
-                    t_jlo[tid] = (int8_t)o.j_lo; t_jhi[tid] = (int8_t)o.j_hi;
-                    ilo = o.i_lo;
-                    if (o.j_hi >= o.j_lo && o.i_hi >= o.i_lo) rows = o.i_hi - o.i_lo + 1;
-                } else {
-                    c_slot[t] = -1;          // a placement that failed is not kept
+                ps.x = ps.z = ps.s = 0.0; ps.c = 1.0;
+                if (on) {
+                    act = make_action(base + t, slot);
+                    err = place_block(P, s_pose, s_shape, n, act, ps);
                 }
-                t_ilo[tid] = (int8_t)ilo;
-                m_rowstart[tid + 1] = rows;
-                c_w[t] = (bad ? SLOT_BAD : 0u) | ((uint32_t)ilo << 7) | (uint32_t)rows;
+                const bool placed = on && err == 0;
+                const ShapeDev &sh = P.shapes[placed ? act.shape : 0];
+                bool outside = false;
+                double xmin = 1e300, xmax = -1e300, zmin = 1e300, zmax = -1e300;
+                if (placed && j < sh.n_verts) {
+                    double vx, vz;
+                    rot(ps.c, ps.s, sh.vert_x[j], sh.vert_z[j], vx, vz);
+                    vx = dadd(vx, ps.x);
+                    vz = dadd(vz, ps.z);
+                    // collision_on_action: any vertex outside the window (gym_env.py:304-323)
+                    outside = vx < xl || vx > xh || vz < zl || vz > zh || vz < -eps;
+                    xmin = xmax = vx;
+                    zmin = zmax = vz;
+                }
+                const unsigned grp = (__ballot_sync(0xffffffffu, outside) >> (lane & 24)) & 0xffu;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+                    xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                    zmin = fmin(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+                    zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                }
+                if (placed && j < sh.n_faces) {          // pose_shape, face j
+                    double fnx, fnz, ax, az;
+                    rot(ps.c, ps.s, sh.face_nx[j], sh.face_nz[j], fnx, fnz);
+                    rot(ps.c, ps.s, sh.face_cx[j], sh.face_cz[j], ax, az);
+                    t_nx[m][j] = fnx;
+                    t_nz[m][j] = fnz;
+                    t_cx[m][j] = dadd(ax, ps.x);
+                    t_cz[m][j] = dadd(az, ps.z);
+                    t_inx[m][j] = (fnx != 0.0) ? 1.0 / fnx : 0.0;
+                }
+                if (on && j == 0) {
+                    const bool bad = !placed || grp != 0;
+                    int rows = 0, ilo = 0;
+                    if (placed) {                        // conservative pixel window (pose_shape)
+                        const int j_lo = max((int)floor((xmin - P.xlim0) * P.inv_step_x) - 1, 0);
+                        const int j_hi = min((int)ceil((xmax - P.xlim0) * P.inv_step_x) + 1, IMG - 1);
+                        const int i_lo = max((int)floor((P.ylim1 - zmax) * P.inv_step_y) - 1, 0);
+                        const int i_hi = min((int)ceil((P.ylim1 - zmin) * P.inv_step_y) + 1, IMG - 1);
+                        t_nf[m] = (int8_t)sh.n_faces;
+                        t_jlo[m] = (int8_t)j_lo; t_jhi[m] = (int8_t)j_hi;
+                        ilo = i_lo;
+                        if (j_hi >= j_lo && i_hi >= i_lo) rows = i_hi - i_lo + 1;
+                    } else {
+                        c_slot[t] = -1;                  // a placement that failed is not kept
+                    }
+                    t_ilo[m] = (int8_t)ilo;
+                    t_rows[m] = (int8_t)rows;
+                    c_w[t] = (bad ? SLOT_BAD : 0u) | ((uint32_t)ilo << 7) | (uint32_t)rows;
+                }
             }
             __syncthreads();
-            if (tid == 0) { s_nmiss = 0; s_nwork = 0; }      // every thread has its copy; next use after two barriers
-            if (nm > 0) {
-                if (tid < 32) {
-                    // inclusive scan of the row counts (two misses per lane), m_rowstart[m + 1] = rows of 0..m
-                    constexpr int CPL = MISS_CAP / 32;
-                    int av[CPL], sum = 0;
-#pragma unroll
-                    for (int j = 0; j < CPL; j++) {
-                        const int idx = CPL * tid + j;
-                        av[j] = (idx < nm) ? m_rowstart[idx + 1] : 0;
-                        sum += av[j];
-                    }
-                    int inc = sum;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (tid >= o) inc += v;
-                    }
-                    int run = inc - sum;
-#pragma unroll
-                    for (int j = 0; j < CPL; j++) {
-                        const int idx = CPL * tid + j;
-                        for (int r = run; r < run + av[j] && r < OWNER_CAP; r++) m_owner[r] = (uint8_t)idx;
-                        run += av[j];
-                        if (idx < nm) m_rowstart[idx + 1] = run;
-                    }
-                    if (tid == 0) m_rowstart[0] = 0;
-                }
-                __syncthreads();
-                // ---- Bm
-                const int npairs = m_rowstart[nm];
-                for (int q = tid; q < npairs; q += ENUM_THREADS) {
-                    int mi = 0;                             // largest m with rowstart[m] <= q
-                    if (q < OWNER_CAP) {
-                        mi = m_owner[q];
-                    } else {
-                        int hi = nm - 1;
-                        while (mi < hi) {
-                            const int mid = (mi + hi + 1) >> 1;
-                            if (m_rowstart[mid] <= q) mi = mid; else hi = mid - 1;
-                        }
-                    }
-                    const int row = t_ilo[mi] + (q - m_rowstart[mi]);
-                    const int t = s_miss[r0 + mi];
+            if (tid == 0) { s_nmiss = 0; s_nwork = 0; }      // every thread has its copy; next use after the barrier in front of C
+            // ---- Bm: sixteen lanes per miss, lane r takes the rows r, r + 16, ... of its window
+            for (int q = tid; q < nm * 16; q += ENUM_THREADS) {
+                const int mi = q >> 4;
+                const int ilo = t_ilo[mi], iend = ilo + t_rows[mi];
+                const int t = s_miss[r0 + mi];
+                const int slot = c_slot[t];
+                bool ovl = false;
+                for (int row = ilo + (q & 15); row < iend; row += 16) {
                     const uint64_t bits = raster_row_posed_mixed(P, t_nf[mi], t_nx[mi], t_nz[mi], t_cx[mi], t_cz[mi],
                                                                  t_inx[mi], t_jlo[mi], t_jhi[mi], row);
-                    const int slot = c_slot[t];
                     if (slot >= 0) C.bits[((size_t)e * C.slots + slot) * IMG + row] = bits;
-                    if (bits & s_full[row]) atomicOr(&c_w[t], SLOT_OVL);
+                    if (bits & s_full[row]) ovl = true;
                     if (COPY && bits) action_bits[((size_t)e * amax + base + t) * IMG + row] = bits;
                 }
+                if (ovl) atomicOr(&c_w[t], SLOT_OVL);
             }
             r0 += MISS_CAP;
             if (r0 < nmiss) __syncthreads();                 // the tables are written again
@@ -747,74 +766,98 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-__global__ void select_random_kernel(Params P, const bw_action *__restrict__ cand, const uint8_t *__restrict__ valid,
-                                     const int32_t *__restrict__ n_cand, int amax, uint64_t seed,
-                                     bw_action *__restrict__ actions, int32_t *__restrict__ index) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// 16 validity flags (0/1 bytes) of a candidate list from position `base` on, as four words with one flag per byte;
+// flags at or past `cnt` (stale) read as 0
+__device__ __forceinline__ void load_flags16(const uint8_t *row, int base, int cnt, bool wide, uint32_t w[4]) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (base >= cnt) return;
+    if (wide) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + base);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        for (int i = 0; i < 16 && base + i < cnt; i++) w[i >> 2] |= (uint32_t)row[base + i] << (8 * (i & 3));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int keep = cnt - (base + 4 * q);
+        if (keep <= 0) w[q] = 0;
+        else if (keep < 4) w[q] &= (1u << (8 * keep)) - 1u;
+        w[q] &= 0x01010101u;
+    }
+}
+
+// One warp per environment: a lane looks at 16 flags at a time (512 per trip of the warp).
+__global__ void __launch_bounds__(128)
+select_random_kernel(Params P, const bw_action *__restrict__ cand, const uint8_t *__restrict__ valid,
+                     const int32_t *__restrict__ n_cand, int amax, uint64_t seed, bw_action *__restrict__ actions,
+                     int32_t *__restrict__ index) {
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= P.E) return;
     const int cnt = n_cand[e];
     const uint8_t *row = valid + (size_t)e * amax;
-    // valid flags are 0/1 bytes: count / search them 16 at a time when the row is 16-byte aligned
     const bool wide = (amax & 15) == 0 && (reinterpret_cast<uintptr_t>(valid) & 15) == 0;
     int nvalid = 0;
-    if (wide) {
-        const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
-        for (int q = 0; q * 16 < cnt; q++) {
-            uint4 v = row4[q];
-            const int left = cnt - q * 16;               // flags past n_cand are stale: mask them off
-            if (left < 16) {
-                uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                for (int k = 0; k < 4; k++) {
-                    const int keep = left - 4 * k;
-                    if (keep <= 0) w[k] = 0;
-                    else if (keep < 4) w[k] &= (1u << (8 * keep)) - 1;
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            nvalid += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
-                      __popc(v.w & 0x01010101u);
-        }
-    } else {
-        for (int a = 0; a < cnt; a++) nvalid += row[a];
+    for (int base = lane * 16; base < cnt; base += 512) {
+        uint32_t w[4];
+        load_flags16(row, base, cnt, wide, w);
+        nvalid += __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
     }
-    bw_action act;
-    act.target_block = -1; act.target_face = 0; act.shape = -1; act.face = 0;
-    act.offset_x = 0.0; act.offset_y = 0.0; act.frozen = 0; act.reserved0 = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
     int chosen = -1;
     if (nvalid > 0) {
+        // the k-th valid candidate, k uniform (counter-based hash of seed, environment and its block count)
         const uint64_t r = mix64(seed ^ mix64((uint64_t)e * 0x632BE59BD9B4E019ull + (uint64_t)P.n_blocks[e]));
         int k = (int)(r % (uint64_t)nvalid);
-        int a = 0;
-        if (wide) {                                       // skip whole 16-flag groups first
-            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
-            for (;; a += 16) {
-                const uint4 v = row4[a >> 4];
-                const int c16 = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
-                                __popc(v.w & 0x01010101u);
-                if (k < c16 || a + 16 >= cnt) break;
-                k -= c16;
+        for (int it = 0; it * 512 < cnt; it++) {
+            const int base = it * 512 + lane * 16;
+            uint32_t w[4];
+            load_flags16(row, base, cnt, wide, w);
+            const int c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-        }
-        for (; a < cnt; a++) {
-            if (row[a]) {
-                if (k == 0) { chosen = a; break; }
-                k--;
+            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+            if (k < tot) {
+                const bool mine = k >= inc - c && k < inc;
+                if (mine) {
+                    int kk = k - (inc - c);
+                    for (int i = 0; i < 16; i++) {
+                        if ((w[i >> 2] >> (8 * (i & 3))) & 1u) {
+                            if (kk == 0) { chosen = base + i; break; }
+                            kk--;
+                        }
+                    }
+                }
+                const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+                chosen = __shfl_sync(0xffffffffu, chosen, src);
+                break;
             }
+            k -= tot;
         }
-        act = cand[(size_t)e * amax + chosen];
-    } else {
-        // no candidate left: the episode ends here (rollout_episode, successor_dqn.py:409-411); the no-op
-        // action leaves the flag alone and the next bw_reset_done starts the environment afresh
-        P.done[e] = 1;
     }
-    actions[e] = act;
-    if (index != nullptr) index[e] = chosen;
+    if (lane == 0) {
+        bw_action act;
+        act.target_block = -1; act.target_face = 0; act.shape = -1; act.face = 0;
+        act.offset_x = 0.0; act.offset_y = 0.0; act.frozen = 0; act.reserved0 = 0;
+        if (chosen >= 0) {
+            act = cand[(size_t)e * amax + chosen];
+        } else {
+            // no candidate left: the episode ends here (rollout_episode, successor_dqn.py:409-411); the no-op
+            // action leaves the flag alone and the next bw_reset_done starts the environment afresh
+            P.done[e] = 1;
+        }
+        actions[e] = act;
+        if (index != nullptr) index[e] = chosen;
+    }
 }
 
 void launch_select_random(const Params &P, const bw_action *d_cand, const uint8_t *d_valid, const int32_t *d_n_cand,
                           int amax, uint64_t seed, bw_action *d_actions, int32_t *d_index, cudaStream_t stream) {
-    select_random_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, d_cand, d_valid, d_n_cand, amax, seed, d_actions,
-                                                                d_index);
+    select_random_kernel<<<(P.E + 3) / 4, 128, 0, stream>>>(P, d_cand, d_valid, d_n_cand, amax, seed, d_actions, d_index);
 }
 
 }  // namespace bw

@@ -317,7 +317,8 @@ __device__ inline uint64_t raster_row_posed_mixed(const Params &P, int n_faces, 
             if (!pixel_in_halfplane(P.xs[lo], fcx, fnx, vz)) hi = lo - 1;
             continue;
         }
-        const double g = (fcx - vz * inv_nx[k] - P.xlim0) * P.inv_step_x;
+        const double off = vz * inv_nx[k];    // cx - px* of the crossing
+        const double g = (fcx - off - P.xlim0) * P.inv_step_x;
         const bool inc = fnx > 0.0;           // inside = [lo, b] (inc) or [b, hi] (!inc)
         const int step = inc ? 1 : -1;
         const int near = inc ? lo : hi, far = inc ? hi : lo;
@@ -325,8 +326,16 @@ __device__ inline uint64_t raster_row_posed_mixed(const Params &P, int n_faces, 
         const double gr = inc ? floor(g) : ceil(g);
         int b = ((gr - (double)far) * (double)step >= 0.0) ? far
               : (((gr - (double)near) * (double)step < 0.0) ? near - step : (int)gr);
-        while (b != far && pixel_in_halfplane(P.xs[b + step], fcx, fnx, vz)) b += step;
-        while ((b - near) * step >= 0 && !pixel_in_halfplane(P.xs[b], fcx, fnx, vz)) b -= step;
+        // The exact test only has to decide when the estimate is close to a pixel node.  The rounded value
+        // fl(fl(fl(px - cx) nx) + vz) has the sign of (px - cx) nx (1 + d) + vz with |d| < 2.3e-16, i.e. the test
+        // moves the true crossing px* = cx - vz / nx by less than 2.3e-16 |px* - cx|; g carries a handful of
+        // roundings of the same size (and the nodes P.xs are within an ulp of their ideal positions).  With
+        // |px* - cx| < 1e3 all of that stays below 1e-11 pixels: an estimate further than 1e-9 from every node is
+        // on the same side of it as the exact crossing.
+        if (!(fabs(off) < 1e3 && fabs(g - rint(g)) > 1e-9)) {
+            while (b != far && pixel_in_halfplane(P.xs[b + step], fcx, fnx, vz)) b += step;
+            while ((b - near) * step >= 0 && !pixel_in_halfplane(P.xs[b], fcx, fnx, vz)) b -= step;
+        }
         hi = inc ? b : hi;
         lo = inc ? lo : b;
     }
