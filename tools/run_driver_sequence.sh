@@ -1,15 +1,16 @@
 #!/bin/bash
-# round 2, job 4: the driver's sequence -- GPU tests, smoke, default bench line (north star), reference arm
+# the driver's sequence (T=tag of the output files) -- GPU tests, smoke, default bench line (north star), reference arm
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/r2b_drv_pytest.log 2>&1
-tail -6 gpurun_out/r2b_drv_pytest.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2b_drv_smoke.log 2>&1; tail -2 gpurun_out/r2b_drv_smoke.log
-( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2b_drv_bench.json 2> gpurun_out/r2b_drv_bench.err
-tail -3 gpurun_out/r2b_drv_bench.err
+export T=${T:-r2e}
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/${T:-r2e}_drv_pytest.log 2>&1
+tail -6 gpurun_out/${T:-r2e}_drv_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T:-r2e}_drv_smoke.log 2>&1; tail -2 gpurun_out/${T:-r2e}_drv_smoke.log
+( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/${T:-r2e}_drv_bench.json 2> gpurun_out/${T:-r2e}_drv_bench.err
+tail -3 gpurun_out/${T:-r2e}_drv_bench.err
 python - <<'PY'
-import json
+import json, os
 try:
-    d = json.loads(open('gpurun_out/r2b_drv_bench.json').read().strip().splitlines()[0])
+    d = json.loads(open('gpurun_out/%s_drv_bench.json' % os.environ.get('T', 'r2e')).read().strip().splitlines()[0])
     def show(tag, r):
         ss = r.get('steady_state', {})
         print(tag, 'value %.3f M  ms %.4f | steady mean %.4f med %.4f p99 %.4f -> %.3f M | e2e %.3f M | cand %.4f ms | hbm frac %.4f fp64 frac %.5f' % (
@@ -26,4 +27,4 @@ try:
 except Exception as ex:
     print('ERR', ex)
 PY
-python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2b_drv_ref.json 2> gpurun_out/r2b_drv_ref.err; cut -c1-200 gpurun_out/r2b_drv_ref.json
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${T:-r2e}_drv_ref.json 2> gpurun_out/${T:-r2e}_drv_ref.err; cut -c1-200 gpurun_out/${T:-r2e}_drv_ref.json
