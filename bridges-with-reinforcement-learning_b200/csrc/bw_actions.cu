@@ -766,26 +766,6 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// 16 validity flags (0/1 bytes) of a candidate list from position `base` on, as four words with one flag per byte;
-// flags at or past `cnt` (stale) read as 0
-__device__ __forceinline__ void load_flags16(const uint8_t *row, int base, int cnt, bool wide, uint32_t w[4]) {
-    w[0] = w[1] = w[2] = w[3] = 0;
-    if (base >= cnt) return;
-    if (wide) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(row + base);
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    } else {
-        for (int i = 0; i < 16 && base + i < cnt; i++) w[i >> 2] |= (uint32_t)row[base + i] << (8 * (i & 3));
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int keep = cnt - (base + 4 * q);
-        if (keep <= 0) w[q] = 0;
-        else if (keep < 4) w[q] &= (1u << (8 * keep)) - 1u;
-        w[q] &= 0x01010101u;
-    }
-}
-
 // One warp per environment: a lane looks at 16 flags at a time (512 per trip of the warp).
 __global__ void __launch_bounds__(128)
 select_random_kernel(Params P, const bw_action *__restrict__ cand, const uint8_t *__restrict__ valid,
@@ -808,36 +788,7 @@ select_random_kernel(Params P, const bw_action *__restrict__ cand, const uint8_t
     if (nvalid > 0) {
         // the k-th valid candidate, k uniform (counter-based hash of seed, environment and its block count)
         const uint64_t r = mix64(seed ^ mix64((uint64_t)e * 0x632BE59BD9B4E019ull + (uint64_t)P.n_blocks[e]));
-        int k = (int)(r % (uint64_t)nvalid);
-        for (int it = 0; it * 512 < cnt; it++) {
-            const int base = it * 512 + lane * 16;
-            uint32_t w[4];
-            load_flags16(row, base, cnt, wide, w);
-            const int c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const int tot = __shfl_sync(0xffffffffu, inc, 31);
-            if (k < tot) {
-                const bool mine = k >= inc - c && k < inc;
-                if (mine) {
-                    int kk = k - (inc - c);
-                    for (int i = 0; i < 16; i++) {
-                        if ((w[i >> 2] >> (8 * (i & 3))) & 1u) {
-                            if (kk == 0) { chosen = base + i; break; }
-                            kk--;
-                        }
-                    }
-                }
-                const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-                chosen = __shfl_sync(0xffffffffu, chosen, src);
-                break;
-            }
-            k -= tot;
-        }
+        chosen = kth_valid_candidate(row, cnt, wide, (int)(r % (uint64_t)nvalid), lane);
     }
     if (lane == 0) {
         bw_action act;

@@ -914,11 +914,10 @@ static int rollout_enumerate(bw_handle *h, bw_transition *d_slots) {
     uint64_t *bits = stored ? nullptr : R.bits;
     launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
                      R.n_cand, bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
-    launch_rollout_finalize(h->P, R, d_slots, h->stream);
-    launch_reset(h->P, nullptr, R.stuck, 1, h->stream);
+    launch_rollout_finalize(h->P, R, d_slots, h->stream);          // restarts the environments left without a candidate
     launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
                      R.n_cand, bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
-    h->launches += 4;
+    h->launches += 3;
     CU(cudaGetLastError());
     return BW_OK;
 }
@@ -946,9 +945,8 @@ static int rollout_iteration(bw_handle *h, const int32_t *d_index, int random_po
     launch_rollout_pick(h->P, Rp, h->cand, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
     launch_step(h->P, R.actions, R.has_action, h->d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr,
                 nullptr, 0, h->smem_step, h->stream);
-    launch_rollout_record(h->P, R, h->d_out, d_slots, h->stream);
-    launch_reset(h->P, nullptr, nullptr, 1, h->stream);           // finished episodes start afresh (their task is kept)
-    h->launches += 4;
+    launch_rollout_record(h->P, R, h->d_out, d_slots, h->stream);  // finished episodes start afresh (their task is kept)
+    h->launches += 3;
     h->roll_step++;
     return rollout_enumerate(h, d_slots);
 }

@@ -73,6 +73,94 @@ void launch_enumerate(const Params &P, const double *d_ground, int n_ground, con
 void launch_gather_bits(const CandCache &cache, const int32_t *d_slot, const uint64_t *d_dense, int amax, int E,
                         const int32_t *d_env, const int32_t *d_index, int64_t n, uint64_t *d_out, cudaStream_t stream);
 
+// 16 validity flags (0/1 bytes) of a candidate list from position `base` on, as four words with one flag per byte;
+// flags at or past `cnt` (stale) read as 0
+__device__ __forceinline__ void load_flags16(const uint8_t *row, int base, int cnt, bool wide, uint32_t w[4]) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (base >= cnt) return;
+    if (wide) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + base);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        for (int i = 0; i < 16 && base + i < cnt; i++) w[i >> 2] |= (uint32_t)row[base + i] << (8 * (i & 3));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int keep = cnt - (base + 4 * q);
+        if (keep <= 0) w[q] = 0;
+        else if (keep < 4) w[q] &= (1u << (8 * keep)) - 1u;
+        w[q] &= 0x01010101u;
+    }
+}
+
+// Index of the k-th set flag (k < number of set flags below `cnt`), found by one warp: a lane counts 16 flags per
+// trip, an inclusive scan finds the lane that holds the k-th, that lane walks its 16.  All lanes return the index.
+__device__ __forceinline__ int kth_valid_candidate(const uint8_t *row, int cnt, bool wide, int k, int lane) {
+    int chosen = -1;
+    for (int it = 0; it * 512 < cnt; it++) {
+        const int base = it * 512 + lane * 16;
+        uint32_t w[4];
+        load_flags16(row, base, cnt, wide, w);
+        const int c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (k < tot) {
+            const bool mine = k >= inc - c && k < inc;
+            if (mine) {
+                int kk = k - (inc - c);
+                for (int i = 0; i < 16; i++) {
+                    if ((w[i >> 2] >> (8 * (i & 3))) & 1u) {
+                        if (kk == 0) { chosen = base + i; break; }
+                        kk--;
+                    }
+                }
+            }
+            const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+            chosen = __shfl_sync(0xffffffffu, chosen, src);
+            break;
+        }
+        k -= tot;
+    }
+    return chosen;
+}
+
+// A finished episode starts afresh on the task it already has (AssemblyGym.reset with the same arguments,
+// gym_env.py:255-289; obstacles, targets and their rasters stay): no blocks, empty raster, targets all remaining, the
+// record of an empty assembly, no warm starts.  Called by all 64 threads of the environment's CTA (thread = image
+// row); used by reset_kernel (bw_reset_done) and by the rollout kernels, which restart an environment in the kernel
+// that finds it finished.
+__device__ __forceinline__ void restart_env(const Params &P, int e, int tid) {
+    if (tid == 0) {
+        TaskDev &tk = P.task[e];
+        for (int i = 0; i < BW_MAX_TARGETS; i++) { tk.remaining[i] = (int8_t)i; tk.reached[i] = -1; }
+        tk.n_remaining = (int8_t)tk.n_targets;
+        tk.n_reached = 0;
+        P.static_mask[e] = 0;
+        P.n_blocks[e] = 0;
+        P.done[e] = 0;
+        bw_step_out o;
+        memset(&o, 0, sizeof(o));
+        o.stable = 1;                     // empty assembly: stability.py:53-56
+        o.stable_unfrozen = 1;
+        for (int i = 0; i < BW_MAX_TARGETS; i++) o.distance_to_targets[i] = INFINITY;
+        P.last_out[e] = o;
+        P.su_valid[e] = 1;
+        P.warm_ok[2 * e] = 0;
+        P.warm_ok[2 * e + 1] = 0;
+        if (P.lp_meta != nullptr) {       // LpMeta (16 bytes) all zero: no basis
+            reinterpret_cast<unsigned long long *>(P.lp_meta)[2 * e] = 0ull;
+            reinterpret_cast<unsigned long long *>(P.lp_meta)[2 * e + 1] = 0ull;
+        }
+    }
+    if (tid < NB) P.face_occ[(size_t)e * NB + tid] = 0;
+    if (tid < IMG) P.block_bits[(size_t)e * IMG + tid] = 0;
+}
+
 // bw_rollout.cu: the kernels around step / enumerate / reset of one lock-step rollout iteration
 struct RolloutBufs {
     bw_action *cand = nullptr;       // [E][amax]

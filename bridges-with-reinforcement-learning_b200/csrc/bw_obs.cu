@@ -26,8 +26,14 @@ __global__ void __launch_bounds__(64)
 reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restrict__ mask, int only_done) {
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
-    if (only_done && P.done[e] == 0) return;
+    const bool skip = only_done && P.done[e] == 0;
+    __syncthreads();                      // every thread has read the flag the reset clears
+    if (skip) return;
     const int tid = threadIdx.x;
+    if (tasks == nullptr) {               // the task is kept: bw_reset_done
+        restart_env(P, e, tid);
+        return;
+    }
     __shared__ TaskDev tk;
     __shared__ float s_tmp[IMG][IMG + 1];
     __shared__ uint64_t s_tbits[IMG];
@@ -36,7 +42,7 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
     __shared__ int s_n;
 
     if (tid == 0) {
-        if (tasks != nullptr) {
+        {
             const bw_task &t = tasks[e];
             tk.n_obstacles = min(max(t.n_obstacles, 0), BW_MAX_OBSTACLES);
             tk.n_targets = min(max(t.n_targets, 0), BW_MAX_TARGETS);
@@ -68,10 +74,6 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
             }
             s_n = nb;
             P.static_mask[e] = sm;
-        } else {
-            tk = P.task[e];
-            s_n = 0;
-            P.static_mask[e] = 0;
         }
         for (int i = 0; i < BW_MAX_TARGETS; i++) { tk.remaining[i] = (int8_t)i; tk.reached[i] = -1; }
         tk.n_remaining = (int8_t)tk.n_targets;
@@ -101,7 +103,6 @@ reset_kernel(Params P, const bw_task *__restrict__ tasks, const uint8_t *__restr
     uint64_t bbits = 0;
     for (int i = 0; i < s_n; i++) bbits |= raster_row(P, P.shapes[s_shape[i]], s_pose[i], row);
     P.block_bits[(size_t)e * IMG + row] = bbits;
-    if (tasks == nullptr) return;   // obstacles / targets unchanged: keep their rasters
 
     uint64_t obits = 0, tbits = 0;
     for (int i = 0; i < tk.n_obstacles; i++) {

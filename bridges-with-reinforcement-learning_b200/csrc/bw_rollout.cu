@@ -3,9 +3,10 @@
 //
 //   pick      policy choice -> chosen action, first half of the transition record (state raster, action raster,
 //             binary features of the state before); the built-in policy draws a uniformly random valid candidate
-//   record    second half after the step kernel: next-state raster, rewards, verdicts, termination
+//   record    second half after the step kernel: next-state raster, rewards, verdicts, termination; a finished
+//             episode is restarted on the spot
 //   finalize  after the candidates of the next state are known: done |= "no candidate left"
-//             (successor_dqn.py:409-411); such environments are flagged for a reset
+//             (successor_dqn.py:409-411); such environments are restarted and flagged for a second enumeration
 //   unpack    packed records -> the learner's float tensors (ReplayBuffer.sample, replay_memory.py:30-40)
 //
 // Records are 1.6 KB (three bit-packed rasters + scalars) instead of 3 x 16 KB float images: the rollout writes
@@ -37,30 +38,16 @@ rollout_pick_kernel(Params P, RolloutBufs R, CandCache C, const int32_t *__restr
     const int amax = R.amax;
     const int cnt = R.n_cand[e], nvalid = R.n_valid[e];
     const uint8_t *vrow = R.valid + (size_t)e * amax;
-    __shared__ int s_strip[64];
     __shared__ int s_choice;
     int choice = -1;
     if (nvalid > 0) {
         if (random_policy) {
-            // k-th valid candidate, k uniform: every thread counts its strip of the mask, the owner of k walks it
-            const int per = (cnt + 63) >> 6, lo = tid * per, hi = min(lo + per, cnt);
-            int c = 0;
-            for (int a = lo; a < hi; a++) c += vrow[a];
-            s_strip[tid] = c;
-            __syncthreads();
-            if (tid == 0) {
+            // k-th valid candidate, k uniform (counter-based hash of seed, environment and iteration): warp 0 finds it
+            if (tid < 32) {
                 const uint64_t r = rmix64(seed ^ rmix64((uint64_t)(R.env_id_base + e) * 0x632BE59BD9B4E019ull + (uint64_t)step));
-                int k = (int)(r % (uint64_t)nvalid);
-                int t = 0;
-                while (t < 63 && k >= s_strip[t]) { k -= s_strip[t]; t++; }
-                int a = t * per;
-                for (;; a++) {
-                    if (vrow[a]) {
-                        if (k == 0) break;
-                        k--;
-                    }
-                }
-                s_choice = a;
+                const bool wide = (amax & 15) == 0 && (reinterpret_cast<uintptr_t>(R.valid) & 15) == 0;
+                const int a = kth_valid_candidate(vrow, cnt, wide, (int)(r % (uint64_t)nvalid), tid);
+                if (tid == 0) s_choice = a;
             }
             __syncthreads();
             choice = s_choice;
@@ -106,49 +93,61 @@ rollout_pick_kernel(Params P, RolloutBufs R, CandCache C, const int32_t *__restr
     }
 }
 
+// After the step: second half of the record, then a finished episode starts afresh (its task is kept) -- the reset of
+// rollout_episode's next call, done by the CTA that sees the episode end.
 __global__ void __launch_bounds__(64)
 rollout_record_kernel(Params P, RolloutBufs R, const bw_step_out *__restrict__ out, bw_transition *__restrict__ slots) {
     const int e = blockIdx.x, tid = threadIdx.x;
-    if (!R.has_action[e]) return;
-    bw_transition &T = slots[e];
-    T.next_block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
-    if (tid == 0) {
-        const bw_step_out o = out[e];
-        T.reward = o.reward;
-        T.lin_reward = o.lin_reward;
-        T.next_binary = binary_bits(o);
-        T.terminated = o.terminated;
-        T.truncated = o.truncated;
-        T.stable = o.stable;
-        T.stable_unfrozen = o.stable_unfrozen;
-        T.done = (uint8_t)(o.terminated | o.truncated);
-        if (o.error) { T.valid = 0; T.done = 1; }      // a refused action is not a transition (the step ended the episode)
+    if (R.has_action[e]) {
+        bw_transition &T = slots[e];
+        T.next_block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
+        if (tid == 0) {
+            const bw_step_out o = out[e];
+            T.reward = o.reward;
+            T.lin_reward = o.lin_reward;
+            T.next_binary = binary_bits(o);
+            T.terminated = o.terminated;
+            T.truncated = o.truncated;
+            T.stable = o.stable;
+            T.stable_unfrozen = o.stable_unfrozen;
+            T.done = (uint8_t)(o.terminated | o.truncated);
+            if (o.error) { T.valid = 0; T.done = 1; }      // a refused action is not a transition (the step ended the episode)
+        }
     }
+    // P.done: set by the step (terminated | truncated, refused action) or by the pick (nothing to place)
+    const bool finished = P.done[e] != 0;
+    __syncthreads();                      // every thread has read the flag the restart clears
+    if (finished) restart_env(P, e, tid);
 }
 
-// thread per environment, after the enumeration of the next states
-__global__ void rollout_finalize_kernel(Params P, RolloutBufs R, bw_transition *__restrict__ slots) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P.E) return;
-    // finished episodes were reset before the enumeration: their candidates are those of a fresh environment and
+// After the enumeration of the next states, CTA of 64 per environment: done |= "no candidate left"
+// (successor_dqn.py:409-411); such an environment is restarted here and flagged for the second enumeration.
+__global__ void __launch_bounds__(64)
+rollout_finalize_kernel(Params P, RolloutBufs R, bw_transition *__restrict__ slots) {
+    const int e = blockIdx.x, tid = threadIdx.x;
+    // finished episodes were restarted before the enumeration: their candidates are those of a fresh environment and
     // say nothing about the recorded transition
     const int nv = R.n_valid[e];
-    uint8_t stuck = 0;
+    bool stuck = false;
     if (slots != nullptr) {
         bw_transition &T = slots[e];
-        if (T.valid && !T.done) {
-            T.n_next_candidates = nv;
-            if (nv == 0) { T.done = 1; stuck = 1; }
+        const bool live = T.valid && !T.done;
+        if (live) {
+            if (tid == 0) T.n_next_candidates = nv;
+            stuck = nv == 0;
         } else if (!T.valid && nv == 0) {
-            stuck = 1;
+            stuck = true;
         }
+        __syncthreads();                  // every thread has read T.done
+        if (live && stuck && tid == 0) T.done = 1;
     } else if (nv == 0) {
-        stuck = 1;
+        stuck = true;
     }
-    // a fresh environment always has its ground candidates; one without any is reset and enumerated again
-    if (stuck && P.n_blocks[e] == 0) stuck = 0;
-    R.stuck[e] = stuck;
-    if (stuck) P.done[e] = 1;
+    // a fresh environment always has its ground candidates; one without any is not restarted again
+    if (stuck && P.n_blocks[e] == 0) stuck = false;
+    __syncthreads();                      // ... and P.n_blocks, which the restart clears
+    if (tid == 0) R.stuck[e] = stuck ? 1 : 0;
+    if (stuck) restart_env(P, e, tid);
 }
 
 void launch_rollout_pick(const Params &P, const RolloutBufs &R, const CandCache &cache, const int32_t *d_index,
@@ -162,7 +161,7 @@ void launch_rollout_record(const Params &P, const RolloutBufs &R, const bw_step_
 }
 
 void launch_rollout_finalize(const Params &P, const RolloutBufs &R, bw_transition *d_slots, cudaStream_t stream) {
-    rollout_finalize_kernel<<<(P.E + 127) / 128, 128, 0, stream>>>(P, R, d_slots);
+    rollout_finalize_kernel<<<P.E, 64, 0, stream>>>(P, R, d_slots);
 }
 
 // One CTA of 256 threads per sampled record: three 16 KB images out (float4 streaming stores), scalars by thread 0.
