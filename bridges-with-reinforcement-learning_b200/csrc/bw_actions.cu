@@ -266,28 +266,15 @@ __device__ __forceinline__ int list_append(bool pred, int *counter, int lane) {
     return start + __popc(m & ((1u << lane) - 1u));
 }
 
+// The candidates of environment e (the whole CTA; P.shapes / P.xs / P.ys point into shared memory and the first
+// barrier inside also covers the caller's copy).  Returns the number of valid candidates (all threads).
 template <bool COPY>
-__global__ void __launch_bounds__(ENUM_THREADS, 8)
-enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
-                       int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
-                       int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, int32_t *__restrict__ slot_out,
-                       CandCache C, const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid) {
-    const int e = blockIdx.x;
-    if (mask != nullptr && mask[e] == 0) return;
+__device__ __forceinline__ int
+enumerate_store_env(const Params &P, const int e, const double *__restrict__ ground, int n_ground,
+                    const double *__restrict__ offsets, int n_offsets, int amax, bw_action *__restrict__ cand,
+                    uint8_t *__restrict__ valid, int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits,
+                    int32_t *__restrict__ slot_out, const CandCache &C, int32_t *__restrict__ n_valid) {
     const int tid = threadIdx.x, lane = tid & 31;
-    __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
-    __shared__ double s_grid[2 * IMG];
-    Params P = PG;
-    {
-        const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
-        uint64_t *dst = reinterpret_cast<uint64_t *>(s_lib);
-        const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
-        for (int q = tid; q < words; q += ENUM_THREADS) dst[q] = src[q];
-        if (tid < IMG) { s_grid[tid] = PG.xs[tid]; s_grid[IMG + tid] = PG.ys[tid]; }
-        P.shapes = reinterpret_cast<const ShapeDev *>(s_lib);
-        P.xs = s_grid;
-        P.ys = s_grid + IMG;
-    }
     __shared__ Pose s_pose[NB];
     __shared__ uint8_t s_shape[NB];
     __shared__ uint64_t s_full[IMG], s_delta[IMG];      // blocks | obstacles; the pixels the last call had not seen
@@ -470,7 +457,7 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
             for (int q = tid; q < count * IMG; q += ENUM_THREADS) dst[q] = 0;
         }
         if (n_valid != nullptr && tid == 0) n_valid[e] = 0;
-        return;
+        return 0;
     }
     const double eps = 1e-6;
     const double xl = dsub(P.xlim0, eps), xh = dadd(P.xlim1, eps), zl = dsub(P.ylim0, eps), zh = dadd(P.ylim1, eps);
@@ -659,28 +646,93 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
             }
         }
     }
-    if (n_valid != nullptr) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) myval += __shfl_xor_sync(0xffffffffu, myval, o);
-        if (lane == 0 && myval) atomicAdd(&s_nval, myval);
+    for (int o = 16; o > 0; o >>= 1) myval += __shfl_xor_sync(0xffffffffu, myval, o);
+    if (lane == 0 && myval) atomicAdd(&s_nval, myval);
+    __syncthreads();
+    const int nval = s_nval;
+    if (n_valid != nullptr && tid == 0) n_valid[e] = nval;
+    return nval;
+}
+
+// One CTA per environment.  In the fused rollout (fin_stuck given) the CTA also closes the iteration: the transition
+// that led here learns how many candidates its next state has, done |= "no candidate left" (successor_dqn.py:409-411),
+// and an environment left without a candidate is restarted and enumerated once more by the same CTA.
+template <bool COPY, bool FIN>
+__global__ void __launch_bounds__(ENUM_THREADS, FIN ? 7 : 8)      // 7 CTAs per SM hold 1,024 environments in one wave
+enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
+                       int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
+                       int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, int32_t *__restrict__ slot_out,
+                       CandCache C, const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid,
+                       bw_transition *__restrict__ fin_slots, uint8_t *__restrict__ fin_stuck) {
+    const int e = blockIdx.x;
+    if (mask != nullptr && mask[e] == 0) return;
+    const int tid = threadIdx.x;
+    // block library and pixel nodes in shared memory; the helpers of bw_common.cuh read them through P
+    __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
+    __shared__ double s_grid[2 * IMG];
+    __shared__ int s_stuck;
+    Params P = PG;
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(PG.shapes);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(s_lib);
+        const int words = PG.n_shapes * (int)(sizeof(ShapeDev) / 8);
+        for (int q = tid; q < words; q += ENUM_THREADS) dst[q] = src[q];
+        if (tid < IMG) { s_grid[tid] = PG.xs[tid]; s_grid[IMG + tid] = PG.ys[tid]; }
+        P.shapes = reinterpret_cast<const ShapeDev *>(s_lib);
+        P.xs = s_grid;
+        P.ys = s_grid + IMG;
+    }
+    if (!FIN) {
+        enumerate_store_env<COPY>(P, e, ground, n_ground, offsets, n_offsets, amax, cand, valid, n_cand, action_bits,
+                                  slot_out, C, n_valid);
+        return;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        const int nv = enumerate_store_env<COPY>(P, e, ground, n_ground, offsets, n_offsets, amax, cand, valid, n_cand,
+                                                 action_bits, slot_out, C, n_valid);
+        if (tid == 0) {       // rollout_finalize_kernel for this environment
+            bool stuck = false;
+            if (fin_slots != nullptr) {
+                bw_transition &T = fin_slots[e];
+                if (T.valid && !T.done) {
+                    T.n_next_candidates = nv;
+                    if (nv == 0) { T.done = 1; stuck = true; }
+                } else if (!T.valid && nv == 0) {
+                    stuck = true;
+                }
+            } else if (nv == 0) {
+                stuck = true;
+            }
+            // a fresh environment always has its ground candidates; one without any is not restarted again
+            if (stuck && P.n_blocks[e] == 0) stuck = false;
+            fin_stuck[e] = stuck ? 1 : 0;
+            s_stuck = stuck ? 1 : 0;
+        }
         __syncthreads();
-        if (tid == 0) n_valid[e] = s_nval;
+        if (!s_stuck) break;
+        restart_env(P, e, tid);
+        __syncthreads();
     }
 }
 
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask,
-                      int32_t *d_n_valid) {
+                      int32_t *d_n_valid, bw_transition *d_fin_slots, uint8_t *d_fin_stuck) {
     if (cache.meta != nullptr && cache.slots > 0) {
         if (d_action_bits != nullptr)
-            enumerate_store_kernel<true><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax,
-                                                                           d_cand, d_valid, d_n_cand, d_action_bits, d_slot,
-                                                                           cache, d_mask, d_n_valid);
+            enumerate_store_kernel<true, false><<<P.E, ENUM_THREADS, 0, stream>>>(
+                P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, d_action_bits, d_slot, cache,
+                d_mask, d_n_valid, nullptr, nullptr);
+        else if (d_fin_stuck == nullptr)
+            enumerate_store_kernel<false, false><<<P.E, ENUM_THREADS, 0, stream>>>(
+                P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, nullptr, d_slot, cache, d_mask,
+                d_n_valid, nullptr, nullptr);
         else
-            enumerate_store_kernel<false><<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax,
-                                                                            d_cand, d_valid, d_n_cand, nullptr, d_slot,
-                                                                            cache, d_mask, d_n_valid);
+            enumerate_store_kernel<false, true><<<P.E, ENUM_THREADS, 0, stream>>>(
+                P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, nullptr, d_slot, cache, d_mask,
+                d_n_valid, d_fin_slots, d_fin_stuck);
     } else {
         enumerate_kernel<<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
                                                            d_valid, d_n_cand, d_action_bits, d_mask, d_n_valid);

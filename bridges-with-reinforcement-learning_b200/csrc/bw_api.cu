@@ -912,12 +912,20 @@ static int rollout_enumerate(bw_handle *h, bw_transition *d_slots) {
     const bool stored = h->cand.meta != nullptr;
     if (!stored && R.bits == nullptr) CU(dev_alloc(h, &R.bits, (size_t)h->P.E * R.amax * IMG, false));
     uint64_t *bits = stored ? nullptr : R.bits;
-    launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                     R.n_cand, bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
-    launch_rollout_finalize(h->P, R, d_slots, h->stream);          // restarts the environments left without a candidate
-    launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                     R.n_cand, bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
-    h->launches += 3;
+    if (stored) {
+        // one launch: the CTA of an environment also closes the iteration (done |= no candidate left) and, when that
+        // leaves it without a candidate, restarts it and enumerates once more
+        launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
+                         R.n_cand, nullptr, R.slot, h->cand, h->stream, nullptr, R.n_valid, d_slots, R.stuck);
+        h->launches += 1;
+    } else {
+        launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
+                         R.n_cand, bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
+        launch_rollout_finalize(h->P, R, d_slots, h->stream);      // restarts the environments left without a candidate
+        launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
+                         R.n_cand, bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
+        h->launches += 3;
+    }
     CU(cudaGetLastError());
     return BW_OK;
 }

@@ -67,7 +67,10 @@ __device__ __forceinline__ uint64_t cand_store_row(const CandCache &C, int e, in
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask = nullptr,
-                      int32_t *d_n_valid = nullptr);
+                      int32_t *d_n_valid = nullptr, bw_transition *d_fin_slots = nullptr, uint8_t *d_fin_stuck = nullptr);
+// d_fin_stuck (fused rollout, only honoured with a candidate store): the kernel also does what
+// rollout_finalize_kernel does -- d_fin_slots may be null (no transition led here) -- and enumerates a restarted
+// environment once more
 // d_out[i] = raster of candidate d_index[i] of environment d_env[i] (d_env null: environment i), read from the
 // dense copies when d_dense is given, else through d_slot from the store
 void launch_gather_bits(const CandCache &cache, const int32_t *d_slot, const uint64_t *d_dense, int amax, int E,
