@@ -9,6 +9,7 @@
 // image rows.  Candidate rasters stay bit-packed (512 B instead of 16 KB per candidate).
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
+#include "bw_rollout.cuh"
 
 namespace bw {
 
@@ -663,11 +664,12 @@ __global__ void __launch_bounds__(ENUM_THREADS, FIN ? 7 : 8)      // 7 CTAs per 
 enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_ground, const double *__restrict__ offsets,
                        int n_offsets, int amax, bw_action *__restrict__ cand, uint8_t *__restrict__ valid,
                        int32_t *__restrict__ n_cand, uint64_t *__restrict__ action_bits, int32_t *__restrict__ slot_out,
-                       CandCache C, const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid,
-                       bw_transition *__restrict__ fin_slots, uint8_t *__restrict__ fin_stuck) {
+                       CandCache C, const uint8_t *__restrict__ mask, int32_t *__restrict__ n_valid, RollFuse F) {
     const int e = blockIdx.x;
     if (mask != nullptr && mask[e] == 0) return;
     const int tid = threadIdx.x;
+    bw_transition *const fin_slots = F.slots;
+    uint8_t *const fin_stuck = F.R.stuck;
     // block library and pixel nodes in shared memory; the helpers of bw_common.cuh read them through P
     __shared__ __align__(16) unsigned char s_lib[BW_MAX_SHAPES * sizeof(ShapeDev)];
     __shared__ double s_grid[2 * IMG];
@@ -688,9 +690,17 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
                                   slot_out, C, n_valid);
         return;
     }
+    if (F.out != nullptr) {   // rollout_record_kernel for this environment
+        rollout_record_env(P, F.R, F.out, fin_slots, e, tid);
+        const bool finished = P.done[e] != 0;
+        __syncthreads();                  // every thread has read the flag the restart clears
+        if (finished) restart_env(P, e, tid);
+        __syncthreads();
+    }
+    int nv = 0;
     for (int pass = 0; pass < 2; pass++) {
-        const int nv = enumerate_store_env<COPY>(P, e, ground, n_ground, offsets, n_offsets, amax, cand, valid, n_cand,
-                                                 action_bits, slot_out, C, n_valid);
+        nv = enumerate_store_env<COPY>(P, e, ground, n_ground, offsets, n_offsets, amax, cand, valid, n_cand,
+                                       action_bits, slot_out, C, n_valid);
         if (tid == 0) {       // rollout_finalize_kernel for this environment
             bool stuck = false;
             if (fin_slots != nullptr) {
@@ -714,25 +724,28 @@ enumerate_store_kernel(Params PG, const double *__restrict__ ground, int n_groun
         restart_env(P, e, tid);
         __syncthreads();
     }
+    // rollout_pick_kernel (random policy) for the next iteration: the list is this CTA's own, nv its valid count
+    if (F.next_slots != nullptr) rollout_pick_env(P, F.R, C, nullptr, 1, F.seed, F.next_step, F.next_slots, e, tid, nv);
 }
 
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask,
-                      int32_t *d_n_valid, bw_transition *d_fin_slots, uint8_t *d_fin_stuck) {
+                      int32_t *d_n_valid, const RollFuse *fuse) {
+    const RollFuse none;
     if (cache.meta != nullptr && cache.slots > 0) {
         if (d_action_bits != nullptr)
             enumerate_store_kernel<true, false><<<P.E, ENUM_THREADS, 0, stream>>>(
                 P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, d_action_bits, d_slot, cache,
-                d_mask, d_n_valid, nullptr, nullptr);
-        else if (d_fin_stuck == nullptr)
+                d_mask, d_n_valid, none);
+        else if (fuse == nullptr)
             enumerate_store_kernel<false, false><<<P.E, ENUM_THREADS, 0, stream>>>(
                 P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, nullptr, d_slot, cache, d_mask,
-                d_n_valid, nullptr, nullptr);
+                d_n_valid, none);
         else
             enumerate_store_kernel<false, true><<<P.E, ENUM_THREADS, 0, stream>>>(
                 P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand, d_valid, d_n_cand, nullptr, d_slot, cache, d_mask,
-                d_n_valid, d_fin_slots, d_fin_stuck);
+                d_n_valid, *fuse);
     } else {
         enumerate_kernel<<<P.E, ENUM_THREADS, 0, stream>>>(P, d_ground, n_ground, d_offsets, n_offsets, amax, d_cand,
                                                            d_valid, d_n_cand, d_action_bits, d_mask, d_n_valid);

@@ -902,28 +902,42 @@ int bw_rollout_configure(bw_handle *h, const double *h_x_discr_ground, int32_t n
     return BW_OK;
 }
 
-// candidates of the current states into the rollout buffers; environments without any candidate (other than fresh
-// ones) are reset and enumerated once more
-static int rollout_enumerate(bw_handle *h, bw_transition *d_slots) {
+// Candidates of the current states into the rollout buffers; environments left without any candidate (other than
+// fresh ones) are restarted and enumerated once more.  With a candidate store this is ONE launch that closes the
+// iteration (RollFuse): d_out given -> the record of the step that has just run + the restart of finished episodes
+// come first; d_next_slots given -> the built-in random policy picks for the next iteration right away (*picked).
+static int rollout_enumerate(bw_handle *h, bw_transition *d_slots, const bw_step_out *d_out, bw_transition *d_next_slots,
+                             uint64_t seed, bool *picked) {
     RolloutBufs &R = h->roll;
+    if (picked) *picked = false;
     if (int rc = upload_offset_tables(h, h->roll_ground, h->roll_n_ground, h->roll_offsets, h->roll_n_offsets)) return rc;
     if (int rc = prepare_cand_cache(h, h->roll_n_ground, h->roll_n_offsets)) return rc;
     // with a candidate store the rasters stay where they are (R.slot says where); without one they are copied out
     const bool stored = h->cand.meta != nullptr;
-    if (!stored && R.bits == nullptr) CU(dev_alloc(h, &R.bits, (size_t)h->P.E * R.amax * IMG, false));
-    uint64_t *bits = stored ? nullptr : R.bits;
     if (stored) {
-        // one launch: the CTA of an environment also closes the iteration (done |= no candidate left) and, when that
-        // leaves it without a candidate, restarts it and enumerates once more
+        RollFuse F;
+        F.R = R;
+        F.R.bits = nullptr;               // rasters are read out of the store
+        F.slots = d_slots;
+        F.out = d_out;
+        F.next_slots = d_next_slots;
+        F.seed = seed;
+        F.next_step = h->roll_step;
         launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                         R.n_cand, nullptr, R.slot, h->cand, h->stream, nullptr, R.n_valid, d_slots, R.stuck);
+                         R.n_cand, nullptr, R.slot, h->cand, h->stream, nullptr, R.n_valid, &F);
         h->launches += 1;
+        if (picked) *picked = d_next_slots != nullptr;
     } else {
+        if (R.bits == nullptr) CU(dev_alloc(h, &R.bits, (size_t)h->P.E * R.amax * IMG, false));
+        if (d_out != nullptr) {
+            launch_rollout_record(h->P, R, d_out, d_slots, h->stream);     // finished episodes start afresh (their task is kept)
+            h->launches += 1;
+        }
         launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                         R.n_cand, bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
+                         R.n_cand, R.bits, R.slot, h->cand, h->stream, nullptr, R.n_valid);
         launch_rollout_finalize(h->P, R, d_slots, h->stream);      // restarts the environments left without a candidate
         launch_enumerate(h->P, h->d_ground, h->roll_n_ground, h->d_offsets, h->roll_n_offsets, R.amax, R.cand, R.valid,
-                         R.n_cand, bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
+                         R.n_cand, R.bits, R.slot, h->cand, h->stream, R.stuck, R.n_valid);
         h->launches += 3;
     }
     CU(cudaGetLastError());
@@ -934,7 +948,7 @@ int bw_rollout_begin(bw_handle *h, bw_rollout_view *out) {
     if (!h) return BW_ERR_INVALID;
     if (!h->roll_configured) return fail(h, BW_ERR_STATE, "bw_rollout_configure must be called first");
     CU(cudaSetDevice(h->cfg.device));
-    if (int rc = rollout_enumerate(h, nullptr)) return rc;
+    if (int rc = rollout_enumerate(h, nullptr, nullptr, nullptr, 0, nullptr)) return rc;
     if (out) {
         const RolloutBufs &R = h->roll;
         out->cand = R.cand; out->valid = R.valid; out->n_cand = R.n_cand; out->n_valid = R.n_valid;
@@ -945,25 +959,29 @@ int bw_rollout_begin(bw_handle *h, bw_rollout_view *out) {
     return BW_OK;
 }
 
+// One iteration: pick (unless the candidate kernel of the previous iteration has picked already) -> step -> record,
+// restarts and the candidates of the next states (rollout_enumerate).
 static int rollout_iteration(bw_handle *h, const int32_t *d_index, int random_policy, uint64_t seed, bw_transition *d_slots,
-                             const bw_obs_out *obs) {
+                             const bw_obs_out *obs, bool already_picked, bw_transition *d_next_slots, bool *picked_next) {
     RolloutBufs &R = h->roll;
-    RolloutBufs Rp = R;
-    if (h->cand.meta != nullptr) Rp.bits = nullptr;      // rasters are read out of the store
-    launch_rollout_pick(h->P, Rp, h->cand, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
+    if (!already_picked) {
+        RolloutBufs Rp = R;
+        if (h->cand.meta != nullptr) Rp.bits = nullptr;      // rasters are read out of the store
+        launch_rollout_pick(h->P, Rp, h->cand, d_index, random_policy, seed, h->roll_step, d_slots, h->stream);
+        h->launches += 1;
+    }
     launch_step(h->P, R.actions, R.has_action, h->d_out, obs ? *obs : bw_obs_out{nullptr, nullptr, nullptr, nullptr}, nullptr,
                 nullptr, 0, h->smem_step, h->stream);
-    launch_rollout_record(h->P, R, h->d_out, d_slots, h->stream);  // finished episodes start afresh (their task is kept)
-    h->launches += 3;
+    h->launches += 1;
     h->roll_step++;
-    return rollout_enumerate(h, d_slots);
+    return rollout_enumerate(h, d_slots, h->d_out, d_next_slots, seed, picked_next);
 }
 
 int bw_rollout_commit(bw_handle *h, const int32_t *d_index, bw_transition *d_slots, const bw_obs_out *obs) {
     if (!h || !d_index || !d_slots) return BW_ERR_INVALID;
     if (!h->roll_configured) return fail(h, BW_ERR_STATE, "bw_rollout_configure / bw_rollout_begin must be called first");
     CU(cudaSetDevice(h->cfg.device));
-    return rollout_iteration(h, d_index, 0, 0, d_slots, obs);
+    return rollout_iteration(h, d_index, 0, 0, d_slots, obs, false, nullptr, nullptr);
 }
 
 int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transition *d_ring, int64_t capacity, int64_t start) {
@@ -973,9 +991,15 @@ int bw_rollout_random(bw_handle *h, int32_t n_steps, uint64_t seed, bw_transitio
     if (capacity < E || capacity % E != 0 || start % E != 0)
         return fail(h, BW_ERR_INVALID, "ring capacity and start must be multiples of num_envs");
     CU(cudaSetDevice(h->cfg.device));
+    // inside the call the candidate kernel of iteration k also picks for iteration k + 1 (two launches per iteration
+    // with a candidate store: step, candidates); the first iteration of a call has its own pick kernel
+    bool picked = false;
     for (int32_t k = 0; k < n_steps; k++) {
         bw_transition *slots = d_ring + (start + (int64_t)k * E) % capacity;
-        if (int rc = rollout_iteration(h, nullptr, 1, seed, slots, nullptr)) return rc;
+        bw_transition *next = (k + 1 < n_steps) ? d_ring + (start + (int64_t)(k + 1) * E) % capacity : nullptr;
+        bool picked_next = false;
+        if (int rc = rollout_iteration(h, nullptr, 1, seed, slots, nullptr, picked, next, &picked_next)) return rc;
+        picked = picked_next;
     }
     return BW_OK;
 }

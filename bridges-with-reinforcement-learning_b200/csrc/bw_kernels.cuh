@@ -67,10 +67,9 @@ __device__ __forceinline__ uint64_t cand_store_row(const CandCache &C, int e, in
 void launch_enumerate(const Params &P, const double *d_ground, int n_ground, const double *d_offsets, int n_offsets,
                       int amax, bw_action *d_cand, uint8_t *d_valid, int32_t *d_n_cand, uint64_t *d_action_bits,
                       int32_t *d_slot, const CandCache &cache, cudaStream_t stream, const uint8_t *d_mask = nullptr,
-                      int32_t *d_n_valid = nullptr, bw_transition *d_fin_slots = nullptr, uint8_t *d_fin_stuck = nullptr);
-// d_fin_stuck (fused rollout, only honoured with a candidate store): the kernel also does what
-// rollout_finalize_kernel does -- d_fin_slots may be null (no transition led here) -- and enumerates a restarted
-// environment once more
+                      int32_t *d_n_valid = nullptr, const struct RollFuse *fuse = nullptr);
+// fuse (fused rollout, only honoured with a candidate store): what the environment's CTA does around its candidates,
+// see RollFuse below
 // d_out[i] = raster of candidate d_index[i] of environment d_env[i] (d_env null: environment i), read from the
 // dense copies when d_dense is given, else through d_slot from the store
 void launch_gather_bits(const CandCache &cache, const int32_t *d_slot, const uint64_t *d_dense, int amax, int E,
@@ -176,6 +175,19 @@ struct RolloutBufs {
     uint8_t *has_action = nullptr;   // [E] step mask
     uint8_t *stuck = nullptr;        // [E] live environment without a candidate: reset + enumerated again
     int32_t amax = 0, env_id_base = 0;
+};
+// The candidate kernel of a fused-rollout iteration (enumerate_store_kernel<false, true>) closes the iteration for its
+// environment: [record of the step that has just run + restart of a finished episode] -> candidates of the next state
+// -> done |= "no candidate left", restart + second enumeration of an environment left without one
+// (rollout_finalize_kernel) -> [the built-in random policy's pick for the next iteration].
+struct RollFuse {
+    RolloutBufs R;
+    bw_transition *slots = nullptr;        // records of the iteration being closed (null: bw_rollout_begin, no transition)
+    const bw_step_out *out = nullptr;      // step results: record + restart first (null: done by rollout_record_kernel)
+    bw_transition *next_slots = nullptr;   // records of the next iteration: pick right away (null: a pick kernel follows)
+    uint64_t seed = 0;
+    int32_t next_step = 0;
+    int32_t pad = 0;
 };
 void launch_rollout_pick(const Params &P, const RolloutBufs &R, const CandCache &cache, const int32_t *d_index,
                          int random_policy, uint64_t seed, int32_t step, bw_transition *d_slots, cudaStream_t stream);

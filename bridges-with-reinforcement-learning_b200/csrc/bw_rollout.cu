@@ -13,84 +13,18 @@
 // 1.6 MB per 1024-environment iteration, nothing here is bound by anything but launch latency.
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
+#include "bw_rollout.cuh"
 
 namespace bw {
 
 static_assert(sizeof(bw_transition) == 1608, "bw_transition layout");
 
-__device__ __forceinline__ uint64_t rmix64(uint64_t x) {   // splitmix64, as select_random_kernel
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-
-__device__ __forceinline__ uint8_t binary_bits(const bw_step_out &o) {    // get_state_features, successor_dqn.py:53-60
-    return (uint8_t)((o.stable ? 1 : 0) | (o.collision ? 2 : 0) | (o.collision_block ? 4 : 0) |
-                     (o.collision_obstacle ? 8 : 0) | (o.collision_floor ? 16 : 0) | (o.collision_boundary ? 32 : 0));
-}
-
 // One CTA of 64 threads per environment (thread = image row for the raster copies).
 __global__ void __launch_bounds__(64)
 rollout_pick_kernel(Params P, RolloutBufs R, CandCache C, const int32_t *__restrict__ index, int random_policy,
                     uint64_t seed, int32_t step, bw_transition *__restrict__ slots) {
-    const int e = blockIdx.x, tid = threadIdx.x;
-    const int amax = R.amax;
-    const int cnt = R.n_cand[e], nvalid = R.n_valid[e];
-    const uint8_t *vrow = R.valid + (size_t)e * amax;
-    __shared__ int s_choice;
-    int choice = -1;
-    if (nvalid > 0) {
-        if (random_policy) {
-            // k-th valid candidate, k uniform (counter-based hash of seed, environment and iteration): warp 0 finds it
-            if (tid < 32) {
-                const uint64_t r = rmix64(seed ^ rmix64((uint64_t)(R.env_id_base + e) * 0x632BE59BD9B4E019ull + (uint64_t)step));
-                const bool wide = (amax & 15) == 0 && (reinterpret_cast<uintptr_t>(R.valid) & 15) == 0;
-                const int a = kth_valid_candidate(vrow, cnt, wide, (int)(r % (uint64_t)nvalid), tid);
-                if (tid == 0) s_choice = a;
-            }
-            __syncthreads();
-            choice = s_choice;
-        } else {
-            choice = index[e];
-            if (choice < 0 || choice >= cnt || !vrow[choice]) choice = -1;     // refused: treated like "no candidate"
-        }
-    }
-    bw_transition &T = slots[e];
-    if (choice < 0) {
-        if (tid == 0) {
-            bw_action a;
-            a.target_block = -1; a.target_face = 0; a.shape = -1; a.face = 0; a.offset_x = 0.0; a.offset_y = 0.0;
-            a.frozen = 0; a.reserved0 = 0;
-            R.actions[e] = a;
-            R.has_action[e] = 0;
-            T.valid = 0;
-            T.done = 1;
-            T.env = R.env_id_base + e;
-            T.step = step;
-            P.done[e] = 1;              // nothing to place: the episode is over (successor_dqn.py:409-411)
-        }
-        return;
-    }
-    T.block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
-    // the chosen candidate's raster: from the dense copies, or straight out of the candidate store
-    if (R.bits != nullptr) {
-        T.action_bits[tid] = R.bits[((size_t)e * amax + choice) * IMG + tid];
-    } else {
-        const int s = R.slot[(size_t)e * amax + choice];
-        T.action_bits[tid] = (s >= 0) ? cand_store_row(C, e, s, tid) : 0ull;
-    }
-    if (tid == 0) {
-        const bw_action a = R.cand[(size_t)e * amax + choice];
-        R.actions[e] = a;
-        R.has_action[e] = 1;
-        T.action = a;
-        T.binary = binary_bits(P.last_out[e]);
-        T.env = R.env_id_base + e;
-        T.step = step;
-        T.valid = 1;
-        T.n_next_candidates = 0;
-    }
+    const int e = blockIdx.x;
+    rollout_pick_env(P, R, C, index, random_policy, seed, step, slots, e, threadIdx.x, R.n_valid[e]);
 }
 
 // After the step: second half of the record, then a finished episode starts afresh (its task is kept) -- the reset of
@@ -98,22 +32,7 @@ rollout_pick_kernel(Params P, RolloutBufs R, CandCache C, const int32_t *__restr
 __global__ void __launch_bounds__(64)
 rollout_record_kernel(Params P, RolloutBufs R, const bw_step_out *__restrict__ out, bw_transition *__restrict__ slots) {
     const int e = blockIdx.x, tid = threadIdx.x;
-    if (R.has_action[e]) {
-        bw_transition &T = slots[e];
-        T.next_block_bits[tid] = P.block_bits[(size_t)e * IMG + tid];
-        if (tid == 0) {
-            const bw_step_out o = out[e];
-            T.reward = o.reward;
-            T.lin_reward = o.lin_reward;
-            T.next_binary = binary_bits(o);
-            T.terminated = o.terminated;
-            T.truncated = o.truncated;
-            T.stable = o.stable;
-            T.stable_unfrozen = o.stable_unfrozen;
-            T.done = (uint8_t)(o.terminated | o.truncated);
-            if (o.error) { T.valid = 0; T.done = 1; }      // a refused action is not a transition (the step ended the episode)
-        }
-    }
+    rollout_record_env(P, R, out, slots, e, tid);
     // P.done: set by the step (terminated | truncated, refused action) or by the pick (nothing to place)
     const bool finished = P.done[e] != 0;
     __syncthreads();                      // every thread has read the flag the restart clears
