@@ -254,3 +254,59 @@ def test_q_network_policy_around_begin_commit():
     assert len(ring) == 6 * E
     v = ring.numpy()
     assert np.array_equal(v["next_block_bits"], v["block_bits"] | v["action_bits"])
+
+
+@pytest.mark.gpu
+def test_fused_rollout_with_and_without_candidate_store(monkeypatch):
+    """With a candidate store an iteration of `bw_rollout_random` is two launches (step; the candidate kernel records
+    the step, restarts finished episodes, closes the iteration and picks for the next one), without one
+    (BW_CAND_CACHE_MB=0: plain candidate kernel, dense raster copies) the stand-alone pick / record / finalize kernels
+    run.  Same seeds, same records, byte for byte -- also across calls (the first iteration of a call has its own pick
+    kernel) and around a caller-driven `step` in between."""
+    import torch
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    from bridges_b200.rollout import FusedRollout, TransitionRing
+    from tests import helpers as H
+    from tests.test_gpu_rollout_parity import CASES
+    cfg = CASES["bridge5_mixed_max15"]
+    E, T = 64, 6
+    obstacles, targets = cfg["task"]
+
+    def make():
+        env = BatchedAssemblyGym(E, [H.URDF[n] for n in cfg["shapes"]], max_steps=cfg["max_steps"])
+        env.reset(dict(obstacles=obstacles, targets=targets))
+        ring = TransitionRing(5 * T * E, env.device)
+        return env, ring, FusedRollout(env, XG, (0.0,), amax=cfg["amax"], chunk_steps=T, ring=ring)
+
+    a_env, a_ring, a_roll = make()
+    monkeypatch.setenv("BW_CAND_CACHE_MB", "0")
+    b_env, b_ring, b_roll = make()
+    monkeypatch.delenv("BW_CAND_CACHE_MB")
+    assert a_roll.candidates()["slot"] is not None and b_roll.candidates()["slot"] is None
+    for roll in (a_roll, b_roll):
+        roll.collect_random(2, seed=5)
+    # T iterations around a caller's choice: the first valid candidate of every environment
+    for _ in range(T):
+        idx = []
+        for roll in (a_roll, b_roll):
+            c = roll.candidates()
+            valid = c["valid"].bool() & (torch.arange(c["amax"], device=c["valid"].device)[None, :] < c["n"][:, None])
+            index = torch.where(valid.any(dim=1), valid.float().argmax(dim=1), torch.full((E,), -1, device=valid.device)).to(torch.int32)
+            idx.append(index.cpu().numpy())
+            roll.ring.push(roll.step(index))
+        assert np.array_equal(idx[0], idx[1])
+    for roll in (a_roll, b_roll):
+        roll.collect_random(2, seed=9)
+        roll.drain()
+        roll.env.sync()
+    ra, rb = a_ring.numpy(), b_ring.numpy()
+    assert len(ra) == len(rb) == 5 * T * E
+    valid = ra["valid"] == 1
+    assert np.array_equal(ra["valid"], rb["valid"]) and valid.sum() > 0.9 * len(ra)
+    for name in ra.dtype.names:
+        if name == "reserved":
+            continue
+        assert np.array_equal(ra[name][valid], rb[name][valid]), name
+    assert np.array_equal(ra["done"], rb["done"]) and np.array_equal(ra["env"], rb["env"]) and np.array_equal(ra["step"], rb["step"])
+    assert (ra["done"][valid] == 1).sum() > E              # episodes ended and were restarted on both paths
+    a_env.close(); b_env.close()
