@@ -1,10 +1,16 @@
 """Attribute ncu samples / executed instructions of one kernel to source-line REGIONS of its .cu file, following
 inlined code back to the line of the kernel it was inlined at (nvdisasm -gi).
-usage: ncu_phases.py <src_page.csv> <nvdisasm -gi -c listing> <kernel substring> <file.cu> name:first_line ...
-(regions in ascending order; a region ends where the next begins)"""
+usage: ncu_phases.py <src_page.csv> <nvdisasm -gi -c listing> <kernel substring> <file.cu> [skip=lo:hi] name:first_line ...
+(regions in ascending order; a region ends where the next begins; an instruction belongs to the innermost frame of its
+inline chain that lies in <file.cu> outside the lines lo..hi -- a helper lambda that is inlined into several regions)"""
 import csv, re, sys, collections
 src_csv, sass, kern, cu = sys.argv[1:5]
-regions = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[5:]]
+rest = sys.argv[5:]
+skip = (0, -1)
+if rest and rest[0].startswith("skip="):
+    skip = tuple(int(v) for v in rest[0][5:].split(":"))
+    rest = rest[1:]
+regions = [(a.split(":")[0], int(a.split(":")[1])) for a in rest]
 lines, cur, inside = [], None, False
 for ln in open(sass):
     if ln.startswith(".text.") or (".section" in ln and ".text." in ln):
@@ -13,8 +19,8 @@ for ln in open(sass):
     if m:
         f, l = m.group(1).split("/")[-1], int(m.group(2))
         chain = [(f, l)] + [(a.split("/")[-1], int(b)) for a, b in re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))]
-        own = [l for f, l in chain if f == cu]
-        cur = own[-1] if own else None        # outermost frame inside the kernel's own file
+        own = [l for f, l in chain if f == cu and not (skip[0] <= l <= skip[1])]
+        cur = own[0] if own else None         # innermost frame inside the kernel's own file
     if inside and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
 rows = list(csv.reader(open(src_csv)))
