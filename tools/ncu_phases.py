@@ -11,18 +11,20 @@ if rest and rest[0].startswith("skip="):
     skip = tuple(int(v) for v in rest[0][5:].split(":"))
     rest = rest[1:]
 regions = [(a.split(":")[0], int(a.split(":")[1])) for a in rest]
-lines, cur, inside = [], None, False
+lines, inside = [], False
+frames = []          # frames named by the //## File comments since the last instruction, innermost first
 for ln in open(sass):
     if ln.startswith(".text.") or (".section" in ln and ".text." in ln):
         inside = kern in ln
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
     if m:
-        f, l = m.group(1).split("/")[-1], int(m.group(2))
-        chain = [(f, l)] + [(a.split("/")[-1], int(b)) for a, b in re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))]
-        own = [l for f, l in chain if f == cu and not (skip[0] <= l <= skip[1])]
-        cur = own[0] if own else None         # innermost frame inside the kernel's own file
-    if inside and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
-        lines.append(cur)
+        frames.append((m.group(1).split("/")[-1], int(m.group(2))))
+        frames += [(a.split("/")[-1], int(b)) for a, b in re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))]
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
+        if inside:
+            own = [l for f, l in frames if f == cu and not (skip[0] <= l <= skip[1])]
+            lines.append(own[0] if own else (lines[-1] if lines else None))
+        frames = []
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 si, ii, ti = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
