@@ -2,7 +2,6 @@
 candidate stage runs while another group's step kernel waits for its slowest environment.
 usage: python tools/pipelined_rollout.py [envs] [groups ...]      (transitions/s of bw_rollout_random per setting)"""
 import sys, time
-import numpy as np
 import torch
 sys.path.insert(0, ".")
 from bridges_b200.envs.batched import BatchedAssemblyGym
