@@ -5,8 +5,10 @@
 //   filter_actions        robotoddler/utils/actions.py:71-82  (collision_on_action
 //                         gym_env.py:304-323 + raster overlap with blocks / obstacles)
 //
-// One CTA (4 warps) per environment; a warp takes one candidate at a time, its lanes are
-// image rows.  Candidate rasters stay bit-packed (512 B instead of 16 KB per candidate).
+// One CTA (4 warps) per environment.  Candidate rasters stay bit-packed (512 B instead of 16 KB per candidate) and,
+// with the candidate store (enumerate_store_kernel, the default), stay in the handle's memory from call to call
+// together with their placements and overlap verdicts; enumerate_kernel is the form without a store.  In the fused
+// rollout the store kernel also closes the iteration for its environment (bw_rollout.cuh).
 #include "bw_common.cuh"
 #include "bw_kernels.cuh"
 #include "bw_rollout.cuh"
