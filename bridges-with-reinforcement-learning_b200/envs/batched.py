@@ -48,11 +48,14 @@ class CandidateRasters:
     `r[env_idx, cand_idx]` (two equally long integer CUDA tensors) -> int64 [n, 64], `r.dense()` -> [E, amax, 64].
     Good until the next enumeration / rollout iteration."""
 
-    def __init__(self, env, E, amax, gather):
-        self.env, self.E, self.amax, self._gather = env, E, amax, gather
+    def __init__(self, env, E, amax, gather, dense=None):
+        self.env, self.E, self.amax, self._gather, self._dense = env, E, amax, gather, dense
 
     def __getitem__(self, key):
         er, ar = key
+        if self._dense is not None:        # no candidate store: the handle copied the rasters out
+            dev = self.env.device
+            return self._dense[torch.as_tensor(er, device=dev).long(), torch.as_tensor(ar, device=dev).long()]
         er = torch.as_tensor(er, device=self.env.device).to(torch.int32).contiguous()
         ar = torch.as_tensor(ar, device=self.env.device).to(torch.int32).contiguous()
         if er.shape != ar.shape or er.dim() != 1:
@@ -62,6 +65,8 @@ class CandidateRasters:
         return out
 
     def dense(self):
+        if self._dense is not None:
+            return self._dense
         dev = self.env.device
         er = torch.arange(self.E, device=dev, dtype=torch.int32).repeat_interleave(self.amax)
         ar = torch.arange(self.amax, device=dev, dtype=torch.int32).repeat(self.E)
@@ -344,12 +349,18 @@ class BatchedAssemblyGym:
         if with_bits == "stored":
             if c["slot"] is None:
                 c["slot"] = torch.zeros((E, amax), dtype=torch.int32, device=self.device)
-            self._check(self.lib.bw_enumerate_actions_stored(
+            rc = self.lib.bw_enumerate_actions_stored(
                 self.handle, g.ctypes.data, g.size, o.ctypes.data, o.size, amax, c["cand"].data_ptr(),
-                c["valid"].data_ptr(), c["n"].data_ptr(), c["slot"].data_ptr()))
-            slot = c["slot"]
-            c["bits"] = CandidateRasters(self, E, amax, lambda env, idx, n, out: self.lib.bw_gather_action_bits(
-                self.handle, slot.data_ptr(), amax, env, idx, n, out))
+                c["valid"].data_ptr(), c["n"].data_ptr(), c["slot"].data_ptr())
+            if rc != L.BW_ERR_CAPACITY:
+                self._check(rc)
+                slot = c["slot"]
+                c["bits"] = CandidateRasters(self, E, amax, lambda env, idx, n, out: self.lib.bw_gather_action_bits(
+                    self.handle, slot.data_ptr(), amax, env, idx, n, out))
+                return c
+            # the handle has no candidate store (BW_CAND_CACHE_MB, device memory): dense copies behind the same interface
+            dense = self.enumerate_actions(x_discr_ground, offset_values, amax=amax, with_bits=True)["bits"]
+            c["bits"] = CandidateRasters(self, E, amax, None, dense=dense)
             return c
         if with_bits and c["dense"] is None:
             c["dense"] = torch.zeros((E, amax, L.BW_IMG), dtype=torch.int64, device=self.device)

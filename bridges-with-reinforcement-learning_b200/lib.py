@@ -15,6 +15,7 @@ BW_MAX_TARGETS = 4
 BW_MAX_INTERFACES = 48
 BW_IMG = 64
 BW_ABI_VERSION = 6
+BW_OK, BW_ERR_INVALID, BW_ERR_CUDA, BW_ERR_CAPACITY, BW_ERR_STATE = 0, -1, -2, -3, -4     # bw_status
 
 LIB_PATH = os.environ.get("BRIDGES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                             "libbridges_b200.so")

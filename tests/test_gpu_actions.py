@@ -206,4 +206,13 @@ def test_stored_candidates_match_plain_kernel(monkeypatch):
     assert n_max > 150 and n_valid > 5000
     oa, ob = stored.read_out(), plain.read_out()
     assert np.array_equal(oa["n_blocks"], ob["n_blocks"])
+    # a handle without a store answers with_bits="stored" with dense copies behind the same interface
+    d = plain.enumerate_actions(XG, (0.0, 0.25), amax=amax, with_bits="stored")
+    s2 = stored.enumerate_actions(XG, (0.0, 0.25), amax=amax, with_bits="stored")
+    plain.sync(); stored.sync()
+    n = d["n"].cpu().numpy()
+    da, sa = d["bits"].dense().cpu().numpy(), s2["bits"].dense().cpu().numpy()
+    assert all(np.array_equal(da[e, :n[e]], sa[e, :n[e]]) for e in range(E))
+    er, ar = torch.arange(E), torch.zeros(E, dtype=torch.int64)
+    assert np.array_equal(d["bits"][er, ar].cpu().numpy(), s2["bits"][er, ar].cpu().numpy())
     stored.close(); plain.close()
