@@ -39,6 +39,10 @@ def test_struct_layouts():
     assert C.sizeof(L.bw_interface) == 96
     assert C.sizeof(L.bw_task) == 16 + 16 * L.BW_MAX_OBSTACLES + 16 * L.BW_MAX_TARGETS + 40 * L.BW_MAX_BLOCKS
     assert L.bw_step_out.distance_to_targets.offset == 16 and L.bw_step_out.stable.offset == 72
+    assert C.sizeof(L.bw_transition) == 1608 and dt["transition"].itemsize == 1608
+    # bw_rollout_view (ABI 6): five device pointers, the store-slot pointer, amax + reserved
+    assert C.sizeof(L.bw_rollout_view) == 56 and L.bw_rollout_view.slot.offset == 40 and L.bw_rollout_view.amax.offset == 48
+    assert (L.BW_OK, L.BW_ERR_INVALID, L.BW_ERR_CUDA, L.BW_ERR_CAPACITY, L.BW_ERR_STATE) == (0, -1, -2, -3, -4)
 
 
 def test_create_without_gpu_fails_loudly():
