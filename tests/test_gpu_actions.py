@@ -216,3 +216,64 @@ def test_stored_candidates_match_plain_kernel(monkeypatch):
     er, ar = torch.arange(E), torch.zeros(E, dtype=torch.int64)
     assert np.array_equal(d["bits"][er, ar].cpu().numpy(), s2["bits"][er, ar].cpu().numpy())
     stored.close(); plain.close()
+
+
+def test_stored_verdicts_are_not_believed_across_episodes(monkeypatch):
+    """The scenario that separates "listed by the previous call" from "has a verdict" (tests/test_oracle_candidate_store.py
+    holds the same rules against the oracle on the CPU): every episode opens with the same block, so its candidates' slots
+    outlive the reset; the second block of the even episodes covers as many of them as possible (they end the episode
+    with the verdict "overlaps"), the odd episodes place their second block where it covers fewest -- the same slots are
+    listed again and are valid.  Stored candidates against the plain kernel, call by call."""
+    from bridges_b200.envs.batched import BatchedAssemblyGym
+    E, amax = 4, 512
+    urdfs = [H.URDF["trapezoid"], H.URDF["hexagon"]]
+    task = dict(obstacles=[(0.6, 0, 0.3), (1.2, 0, 0.3)], targets=[(2.4, 0, 0.3)])
+    stored = BatchedAssemblyGym(E, urdfs, max_steps=6)
+    monkeypatch.setenv("BW_CAND_CACHE_MB", "0")
+    plain = BatchedAssemblyGym(E, urdfs, max_steps=6)
+    monkeypatch.delenv("BW_CAND_CACHE_MB")
+    offsets = (0.0, 0.25)
+    sz = stored.dt["action"].itemsize
+    dropped_then_valid = 0
+    end_of_even = None                    # validity of the first block's candidates at the end of an even episode
+    for episode in range(4):
+        for env in (stored, plain):
+            env.reset(task)
+        for step in range(4):
+            a = stored.enumerate_actions(XG, offsets, amax=amax, with_bits="stored")
+            b = plain.enumerate_actions(XG, offsets, amax=amax)
+            stored.sync(); plain.sync()
+            n = int(b["n"][0].item())
+            va, vb = a["valid"].cpu().numpy()[:, :n], b["valid"].cpu().numpy()[:, :n]
+            assert np.array_equal(a["n"].cpu().numpy(), b["n"].cpu().numpy())
+            assert np.array_equal(va, vb), (episode, step, np.flatnonzero(va[0] != vb[0]))
+            assert np.array_equal(a["bits"].dense().cpu().numpy()[:, :n], b["bits"].cpu().numpy()[:, :n])
+            cands = b["cand"].cpu().numpy().reshape(E, amax, sz)[0, :n].copy().view(stored.dt["action"]).reshape(n)
+            valid = np.flatnonzero(vb[0])
+            assert valid.size > 0
+            if step == 1:                 # one block placed: the candidates of that block, keyed by what identifies them
+                keys = [(int(c["shape"]), int(c["face"]), int(c["target_block"]), int(c["target_face"]), float(c["offset_x"])) for c in cands]
+                now = {k: bool(v) for k, v in zip(keys, vb[0]) if k[2] == 0}
+                if episode % 2 == 1 and end_of_even is not None:
+                    dropped_then_valid += sum(1 for k, ok in now.items() if ok and end_of_even.get(k) is False)
+            choice = int(valid[0])
+            if step == 1:
+                img = BatchedAssemblyGym.bits_to_bool(b["bits"][0, :n].cpu().numpy().view(np.uint64))[valid]
+                cover = [int((img[j][None] & img).any(axis=(1, 2)).sum()) for j in range(len(valid))]
+                choice = int(valid[int(np.argmax(cover) if episode % 2 == 0 else np.argmin(cover))])
+            elif step > 1:
+                choice = int(valid[(7 * episode + 3 * step) % valid.size])
+            acts = np.zeros(E, dtype=stored.dt["action"])
+            acts[:] = cands[choice]
+            stored.step(acts); plain.step(acts)
+            if step == 1 and episode % 2 == 0:
+                c = plain.enumerate_actions(XG, offsets, amax=amax)
+                plain.sync()
+                m = int(c["n"][0].item())
+                cc = c["cand"].cpu().numpy().reshape(E, amax, sz)[0, :m].copy().view(stored.dt["action"]).reshape(m)
+                end_of_even = {(int(q["shape"]), int(q["face"]), int(q["target_block"]), int(q["target_face"]), float(q["offset_x"])): bool(v)
+                               for q, v in zip(cc, c["valid"].cpu().numpy()[0, :m]) if int(q["target_block"]) == 0}
+    assert dropped_then_valid > 0         # the scenario happened: slots with the verdict "overlaps" came back valid
+    oa, ob = stored.read_out(), plain.read_out()
+    assert np.array_equal(oa["n_blocks"], ob["n_blocks"])
+    stored.close(); plain.close()

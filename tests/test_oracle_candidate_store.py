@@ -69,3 +69,53 @@ def test_candidates_keep_raster_and_bounds_flag_and_rasters_only_grow(case):
                 break
         n_episodes += 1
     assert n_episodes == 2 and n_kept > 50
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_store_restatement_equals_recomputing_from_scratch(case):
+    """oracle/candidate_store.py (the rules of `enumerate_store_kernel`: slots, dropped blocks, fresh calls, stamps,
+    new-pixels-only tests) against generate_actions + get_action_features + filter_actions recomputed at every call:
+    same candidates, same rasters, same validity -- through episode ends, calls the store skips (two blocks of new
+    pixels), repeated calls on one state and a store call in the middle of an episode it has not seen."""
+    from oracle.candidate_store import CandidateStore
+    cfg = CASES[case]
+    rng = np.random.default_rng(5)
+    env = H.oracle_env(cfg["shapes"], cfg["obstacles"], cfg["targets"], max_steps=7)
+    store = CandidateStore(XG, cfg["offsets"], H.XLIM, H.YLIM, H.IMG)
+    calls = 0
+    for episode in range(4):
+        obs, _ = env.reset()
+        _, obstacle_f = ofeat.get_task_features(obs, H.XLIM, H.YLIM, H.IMG)
+        for step in range(6):
+            block_f, _ = ofeat.get_state_features(obs, H.XLIM, H.YLIM, H.IMG)
+            cands = list(oact.generate_actions(env, XG, cfg["offsets"]))
+            feats = ofeat.get_action_features(env, cands, H.XLIM, H.YLIM, H.IMG)
+            _, _, mask = oact.filter_actions(env, cands, feats, block_f, obstacle_f, H.XLIM, H.YLIM)
+            skip = (episode * 6 + step) % 5 == 3 or (episode == 2 and step < 2)      # the store does not see every state
+            if not skip:
+                for _ in range(2 if step == 2 else 1):                                # ... and sees some of them twice
+                    got_a, got_mask, got_img = store.enumerate(env, block_f[0] > 0, obstacle_f[0] > 0)
+                    calls += 1
+                    assert [_key(a) for a in got_a] == [_key(a) for a in cands]
+                    assert np.array_equal(got_mask, mask), (case, episode, step, np.flatnonzero(got_mask != mask))
+                    assert all(np.array_equal(g, f[0] > 0) for g, f in zip(got_img, feats))
+            valid = np.flatnonzero(mask)
+            if valid.size == 0:
+                break
+            # every episode opens with the same block: its slots outlive the reset with the verdicts and the stamps of
+            # the previous episode, and must not be believed (a slot is only trusted when the PREVIOUS call listed it)
+            choice = valid[0] if step == 0 else rng.choice(valid)
+            if step == 1:
+                # ... the second block of the even episodes is the one whose raster covers most of the other valid
+                # candidates (their slots end the episode with the verdict "overlaps"), the odd episodes take the one
+                # that covers fewest: the same slots are listed again there and are valid
+                imgs = [feats[i][0] > 0 for i in valid]
+                cover = [sum(bool((imgs[j] & imgs[k]).any()) for k in range(len(valid)) if k != j) for j in range(len(valid))]
+                choice = valid[int(np.argmax(cover) if episode % 2 == 0 else np.argmin(cover))]
+            obs, _, terminated, truncated, _ = env.step(cands[int(choice)])
+            if terminated or truncated:
+                break
+    st = store.stats
+    assert calls > 10 and st["posed"] > 50 and st["incremental_tests"] > 50 and st["no_test"] > 20 and st["full_tests"] > 20, dict(st)
+    # the point of the store: most listed candidates are neither posed nor tested in full
+    assert st["incremental_tests"] + st["no_test"] > st["posed"], dict(st)
